@@ -1,0 +1,349 @@
+/*
+ * mfrec_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, single-threaded, float64 restatement of the reference's latent-factor
+ * hot path, used as the parity oracle for the CUDA implementation.  Nothing in the
+ * product (mfrec_b200/, include/) may link, import or call this file; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * Parity status: PINNED.  The reference ships no tests or golden vectors
+ * (SURVEY.md section 4), so this restatement is pinned by executing the reference's own
+ * kernels -- built unmodified from mfrec/lib/{kmf_train,gd_estimator}.pyx by
+ * oracle/build_ref.sh into oracle/_ref/ -- on seeded inputs; tests/test_oracle.py
+ * demands bit-equality (linear / Funk) or <=2 ulp (logistic: libm exp) against it, and
+ * tests/golden/ holds committed outputs of oracle/_ref made by tests/golden/make_golden.py.
+ *
+ * Layout follows the reference exactly: factors are feature-major [k][n] float64,
+ * `u` = ITEM factors, `v` = USER factors, ratings_index is [nnz][2] = (user, item).
+ *
+ * Compile with -O2 -ffp-contract=off (the reference build has no FMA contraction).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- mfrec/lib/gd_estimator.pyx:26-35 (same body kmf_train.pyx:22-31): the clamp
+ *      ignores its min/max arguments, the range [1,5] is hard-coded. */
+static double clamp15(double x)
+{
+    if (x > 5.0) x = 5.0;
+    if (x < 1.0) x = 1.0;
+    return x;
+}
+
+/* ---- mfrec/lib/gd_estimator.pyx:38-73 `estimator`: cached partial prediction + one
+ *      feature product, clamp, optional trailing term for the untrained features. */
+static double funk_estimate(double uf, double vf, int f, int dim, double f_init,
+                            double cache, int trailing, double overall_avg,
+                            double item_bias, double user_bias)
+{
+    double s;
+    if (cache > 0) s = cache;
+    else           s = overall_avg + item_bias + user_bias;
+    s += uf * vf;
+    s = clamp15(s);
+    if (trailing == 1) {
+        s += (dim - f - 1) * f_init * f_init;
+        s = clamp15(s);
+    }
+    return s;
+}
+
+/* ---- mfrec/lib/kmf_train.pyx:72-97 `full_estimator`: overall + b_i + b_u + sum_f u*v,
+ *      sequential in f, no clamp. */
+static double kmf_full_estimate(const double *u, const double *v, int64_t ni, int64_t nu,
+                                int dim, int item, int user, double overall_avg,
+                                double item_bias, double user_bias)
+{
+    double s = overall_avg + item_bias + user_bias;
+    for (int f = 0; f < dim; ++f)
+        s += u[(int64_t)f * ni + item] * v[(int64_t)f * nu + user];
+    return s;
+}
+
+/*
+ * mfrec/lib/kmf_train.pyx:195-277 (kernel==0, train_linear_kernel) and
+ * kmf_train.pyx:103-189 (kernel==1, train_logistic_kernel).
+ *
+ * Quirks kept on purpose:
+ *  - overall_avg is passed to full_estimator as the literal 0.0 (:159, :250);
+ *  - the linear kernel updates both biases unconditionally (:259-260), the logistic one
+ *    gates them on update_users / update_items (:168-171);
+ *  - only `learning_rate` is used; learning_rate_users/items and f_init are dead;
+ *  - features are updated from the OLD cf / mf pair (:263-270).
+ * rmse_out (nullable) receives sqrt(se/nnz) per epoch (the reference only prints it).
+ */
+void oracle_kmf_train(int kernel, int nbr_epochs, int dim, double lr, double K_users,
+                      double K_items, double K_bias, double *u, double *v,
+                      const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                      int64_t ni, int64_t nu, double *items_bias, double *users_bias,
+                      int update_users, int update_items, double *rmse_out)
+{
+    const double rating_range_size = 4.0, min_rating = 1.0;
+    for (int epoch = 0; epoch < nbr_epochs; ++epoch) {
+        double se = 0.0;
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+            const double rating = ratings[n];
+            const double dot = kmf_full_estimate(u, v, ni, nu, dim, item, user, 0.0,
+                                                 items_bias[item], users_bias[user]);
+            double err, grad;
+            if (kernel == 0) {
+                err = rating - dot;
+                se += err * err;
+                grad = err;
+                users_bias[user] += lr * (grad - K_bias * users_bias[user]);
+                items_bias[item] += lr * (grad - K_bias * items_bias[item]);
+            } else {
+                const double sig = 1.0 / (1.0 + exp(-dot));
+                const double p = min_rating + sig * rating_range_size;
+                err = rating - p;
+                se += err * err;
+                grad = err * sig * (1.0 - sig) * rating_range_size;
+                if (update_users)
+                    users_bias[user] += lr * (grad - K_bias * users_bias[user]);
+                if (update_items)
+                    items_bias[item] += lr * (grad - K_bias * items_bias[item]);
+            }
+            for (int f = 0; f < dim; ++f) {
+                double *pu = &u[(int64_t)f * ni + item], *pv = &v[(int64_t)f * nu + user];
+                const double cf = *pv, mf = *pu;
+                if (update_items) *pu += lr * (grad * cf - K_items * mf);
+                if (update_users) *pv += lr * (grad * mf - K_users * cf);
+            }
+        }
+        if (rmse_out) rmse_out[epoch] = sqrt(se / (double)nnz);
+    }
+}
+
+/*
+ * Funk-SVD per-feature loops:
+ *   variant 0: estimator_loop_without_bias   mfrec/lib/gd_estimator.pyx:691-779
+ *   variant 1: estimator_loop_with_bias      gd_estimator.pyx:489-582
+ *   variant 2: estimator_loop_with_bias_dev  gd_estimator.pyx:588-685 (update gates)
+ *
+ * Quirks kept: rmse (2.0) and rmse_last (0.0) carry across features; max_epochs is
+ * ignored; the per-rating cache is refreshed once per feature with trailing=0; biases
+ * are read-only; variant 0 uses the estimator's defaults overall_avg=1.0, biases 0.
+ * Returns the number of training passes done (sum over features); feature_epochs
+ * (nullable, [dim]) gets the per-feature pass count, feature_rmse (nullable, [dim])
+ * the rmse of the last pass of each feature.
+ */
+int64_t oracle_funk_train(int variant, int min_epochs, double min_improvement, int dim,
+                          double f_init, double lr, double K, double overall_avg,
+                          double *u, double *v, const int32_t *ratings_index,
+                          const double *ratings, int64_t nnz, int64_t ni, int64_t nu,
+                          const double *items_bias, const double *users_bias,
+                          int update_users, int update_items, int32_t *feature_epochs,
+                          double *feature_rmse)
+{
+    double rmse = 2.0, rmse_last = 0.0;
+    int64_t passes = 0;
+    double *cache = (double *)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(double));
+    for (int64_t n = 0; n < nnz; ++n) cache[n] = 0.0;
+    if (variant != 2) { update_users = 1; update_items = 1; }
+    for (int f = 0; f < dim; ++f) {
+        double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
+        int epoch = 0;
+        while (epoch < min_epochs || rmse <= rmse_last - min_improvement) {
+            double se = 0.0;
+            rmse_last = rmse;
+            for (int64_t n = 0; n < nnz; ++n) {
+                const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+                const double rating = ratings[n];
+                double p;
+                if (variant == 0)
+                    p = funk_estimate(uf[item], vf[user], f, dim, f_init, cache[n], 1,
+                                      1.0, 0.0, 0.0);
+                else
+                    p = funk_estimate(uf[item], vf[user], f, dim, f_init, cache[n], 1,
+                                      overall_avg, items_bias[item], users_bias[user]);
+                const double err = rating - p;
+                se += err * err;
+                const double cf = vf[user], mf = uf[item];
+                if (update_items) uf[item] += lr * (err * cf - K * mf);
+                if (update_users) vf[user] += lr * (err * mf - K * cf);
+            }
+            rmse = sqrt(se / (double)nnz);
+            ++epoch;
+            ++passes;
+        }
+        if (feature_epochs) feature_epochs[f] = epoch;
+        if (feature_rmse) feature_rmse[f] = rmse;
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+            if (variant == 0)
+                cache[n] = funk_estimate(uf[item], vf[user], f, dim, f_init, cache[n], 0,
+                                         1.0, 0.0, 0.0);
+            else
+                cache[n] = funk_estimate(uf[item], vf[user], f, dim, f_init, cache[n], 0,
+                                         overall_avg, items_bias[item], users_bias[user]);
+        }
+    }
+    free(cache);
+    return passes;
+}
+
+/*
+ * Predictors (one k-dot + affine / logistic map), by id:
+ *   0  GDRecommender.predict_rating            gradient_descent.py:621-631   dot + 1.0
+ *   1  GDRecommender.predict_rating_with_bias  gradient_descent.py:637-648   dot + (mu + (b_i + b_u))
+ *   2  KMFRecommender.predict_linear           kmf.py:88-94                  dot + (b_i + b_u)
+ *   3  KMFRecommender.predict_logistic         kmf.py:79-85                  1 + 4*sigmoid(dot + (b_i+b_u))
+ *   4  KMFRecommender.predict_linear_neg       kmf.py:97-103                 1 + 4*(dot + (b_i+b_u))
+ *   5  WRMFRecommender.predict                 wrmf.py:67-69                 dot
+ * min_rating / max_rating are the BaseRecommender attributes (base.py:92-93), 1 and 5.
+ */
+static double predict_one(int predictor, const double *u, const double *v, int64_t ni,
+                          int64_t nu, int dim, int item, int user, double mu,
+                          const double *ib, const double *ub, double min_rating,
+                          double max_rating)
+{
+    double dot = 0.0;
+    for (int f = 0; f < dim; ++f)
+        dot += u[(int64_t)f * ni + item] * v[(int64_t)f * nu + user];
+    switch (predictor) {
+    case 0: return dot + 1.0;
+    case 1: return dot + (mu + (ib[item] + ub[user]));
+    case 2: return dot + (ib[item] + ub[user]);
+    case 3: {
+        const double s = dot + (ib[item] + ub[user]);
+        return min_rating + (1.0 / (1.0 + exp(-s))) * (max_rating - min_rating);
+    }
+    case 4: return min_rating + (dot + (ib[item] + ub[user])) * (max_rating - min_rating);
+    default: return dot;
+    }
+}
+
+/* pairs are (user, item) rows like u_test / ratings_index. */
+void oracle_predict_pairs(int predictor, const double *u, const double *v, int64_t ni,
+                          int64_t nu, int dim, const int32_t *pairs, int64_t n, double mu,
+                          const double *ib, const double *ub, double min_rating,
+                          double max_rating, double *out)
+{
+    for (int64_t j = 0; j < n; ++j)
+        out[j] = predict_one(predictor, u, v, ni, nu, dim, pairs[2 * j + 1], pairs[2 * j],
+                             mu, ib, ub, min_rating, max_rating);
+}
+
+/*
+ * metrics.test_predict_rating  mfrec/recommendation/metrics.py:51-82:
+ * errors = real - predicted over the pairs, NaN errors dropped, then
+ * out = { rmse = sqrt(mean(|e|^2)), mae = mean|e|, var(|e|) (population), n_valid }.
+ * errors_out (nullable, [n]) receives every error in order (NaN kept in place).
+ */
+void oracle_rmse_pairs(int predictor, const double *u, const double *v, int64_t ni,
+                       int64_t nu, int dim, const int32_t *pairs, const double *real,
+                       int64_t n, double mu, const double *ib, const double *ub,
+                       double min_rating, double max_rating, double *errors_out,
+                       double out[4])
+{
+    double s2 = 0.0, s1 = 0.0;
+    int64_t cnt = 0;
+    double *tmp = (double *)malloc((size_t)(n > 0 ? n : 1) * sizeof(double));
+    for (int64_t j = 0; j < n; ++j) {
+        const double p = predict_one(predictor, u, v, ni, nu, dim, pairs[2 * j + 1],
+                                     pairs[2 * j], mu, ib, ub, min_rating, max_rating);
+        const double e = real[j] - p;
+        tmp[j] = e;
+        if (errors_out) errors_out[j] = e;
+        if (e == e) { s2 += e * e; s1 += fabs(e); ++cnt; }
+    }
+    const double mae = cnt ? s1 / (double)cnt : NAN;
+    double var = 0.0;
+    for (int64_t j = 0; j < n; ++j)
+        if (tmp[j] == tmp[j]) { const double d = fabs(tmp[j]) - mae; var += d * d; }
+    out[0] = cnt ? sqrt(s2 / (double)cnt) : NAN;
+    out[1] = mae;
+    out[2] = cnt ? var / (double)cnt : NAN;
+    out[3] = (double)cnt;
+    free(tmp);
+}
+
+/*
+ * Top-N for one user:
+ *   GDRecommender.find_user_top_match  gradient_descent.py:769-802 (all items, predictor 0)
+ *   MFRecommender.find_recommended_items  mf.py:144-193 (the first `n_candidates` item ids
+ *     -- the loop scores the enumeration index, not the sampled id -- any predictor).
+ * Score every candidate item i unless i is already rated by the user or i == user_index
+ * (quirk: the user id is appended to the rated-item list, mf.py:162 / gradient_descent.py:779);
+ * NaN -> 0 (mf.py:176); drop exact zeros; stable sort by score descending (ties keep
+ * ascending item id, Python's sorted(reverse=True) is stable); keep the first N.
+ * rated_items: the user's rated item ids (any order), n_rated of them.
+ * Returns how many results were written (<= N).
+ */
+typedef struct { double score; int32_t item; } scored_t;
+
+static int scored_cmp(const void *a, const void *b)
+{
+    const scored_t *x = (const scored_t *)a, *y = (const scored_t *)b;
+    if (x->score > y->score) return -1;
+    if (x->score < y->score) return 1;
+    return (x->item > y->item) - (x->item < y->item);
+}
+
+int oracle_topn_user(int predictor, const double *u, const double *v, int64_t ni, int64_t nu,
+                     int dim, int user, int n_candidates, const int32_t *rated_items,
+                     int64_t n_rated, double mu, const double *ib, const double *ub,
+                     double min_rating, double max_rating, int N, int32_t *out_items,
+                     double *out_scores)
+{
+    uint8_t *mask = (uint8_t *)calloc((size_t)(n_candidates > 0 ? n_candidates : 1), 1);
+    scored_t *sc = (scored_t *)malloc((size_t)(n_candidates > 0 ? n_candidates : 1) * sizeof(scored_t));
+    for (int64_t j = 0; j < n_rated; ++j)
+        if (rated_items[j] >= 0 && rated_items[j] < n_candidates) mask[rated_items[j]] = 1;
+    if (user >= 0 && user < n_candidates) mask[user] = 1;
+    int m = 0;
+    for (int i = 0; i < n_candidates; ++i) {
+        if (mask[i]) continue;
+        double s = predict_one(predictor, u, v, ni, nu, dim, i, user, mu, ib, ub,
+                               min_rating, max_rating);
+        if (s != s) s = 0.0;
+        if (s == 0.0) continue;
+        sc[m].score = s; sc[m].item = i; ++m;
+    }
+    qsort(sc, (size_t)m, sizeof(scored_t), scored_cmp);
+    const int outn = m < N ? m : N;
+    for (int j = 0; j < outn; ++j) { out_items[j] = sc[j].item; out_scores[j] = sc[j].score; }
+    free(mask); free(sc);
+    return outn;
+}
+
+/*
+ * Bias statistics (the step just before the hot path):
+ *   compute_overall_avg    base.py:504-508   mu = mean of stored ratings
+ *   compute_items_bias_bk  mf.py:78-97       b_i = sum_u (r - mu) / (K3 + n_i)
+ *   compute_users_bias_bk  mf.py:100-121     b_u = sum_i (r - mu - b_i) / (K2 + n_u)
+ * Inputs are the COO triples; empty rows/cols keep bias 0.  Sums run in ascending
+ * (user, item) order for items' columns / users' rows as scipy's csc / csr slicing does;
+ * callers pass triples sorted by (user, item) (lil_matrix.tocoo order).
+ */
+double oracle_bias_stats(const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                         int64_t ni, int64_t nu, double K2, double K3, double *items_bias,
+                         double *users_bias)
+{
+    double tot = 0.0;
+    for (int64_t n = 0; n < nnz; ++n) tot += ratings[n];
+    const double mu = nnz ? tot / (double)nnz : NAN;
+    double *cnt_i = (double *)calloc((size_t)(ni > 0 ? ni : 1), sizeof(double));
+    double *cnt_u = (double *)calloc((size_t)(nu > 0 ? nu : 1), sizeof(double));
+    for (int64_t i = 0; i < ni; ++i) items_bias[i] = 0.0;
+    for (int64_t j = 0; j < nu; ++j) users_bias[j] = 0.0;
+    for (int64_t n = 0; n < nnz; ++n) {
+        const int item = ratings_index[2 * n + 1];
+        items_bias[item] += ratings[n] - mu;
+        cnt_i[item] += 1.0;
+    }
+    for (int64_t i = 0; i < ni; ++i)
+        if (cnt_i[i] > 0) items_bias[i] = items_bias[i] / (K3 + cnt_i[i]);
+    for (int64_t n = 0; n < nnz; ++n) {
+        const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+        users_bias[user] += ratings[n] - mu - items_bias[item];
+        cnt_u[user] += 1.0;
+    }
+    for (int64_t j = 0; j < nu; ++j)
+        if (cnt_u[j] > 0) users_bias[j] = users_bias[j] / (K2 + cnt_u[j]);
+    free(cnt_i); free(cnt_u);
+    return mu;
+}
