@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the SGD hot path: rating updates/s on synthetic Netflix-shaped ratings.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU kernels
+
+A *step* is one epoch of ``train_linear_kernel`` semantics (kmf_train.pyx:195-277) over the
+whole rating set.  ``value`` times K epochs with everything resident in HBM (CUDA events on the
+library's stream); ``e2e`` times K calls of the drop-in ``train_linear_kernel(nbr_epochs=1)``
+with host (pinned) numpy buffers, i.e. H2D of ratings + factors, layout, one epoch, D2H of the
+factors inside the timed region.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "rating_updates_per_s"
+UNIT = "updates/s"
+HP = dict(lr=0.005, K_users=0.05, K_items=0.05, K_bias=0.007)
+
+
+def algorithmic_bytes_per_update(k, elem_bytes=4):
+    """read+write P_u and Q_i (4*k*s) + rating triple (12) + both biases r/w (16)."""
+    return 4 * k * elem_bytes + 12 + 16
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic data on the GPU (torch is plumbing here: RNG, sort/unique, host pinning)
+# --------------------------------------------------------------------------------------------
+def gpu_synth(torch, dev, nu, ni, nnz, seed, user_offset=0):
+    """Netflix-shaped unique (user, item, rating) triples in shuffled order (see
+    mfrec_b200/synth.py for the model; this is the same recipe with torch's generator)."""
+    from mfrec_b200 import synth
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    wu, wi = synth.marginals(nu, ni, seed)
+    cu = torch.from_numpy(np.cumsum(wu)).to(dev)
+    ci = torch.from_numpy(np.cumsum(wi)).to(dev)
+    keys = None
+    while keys is None or keys.numel() < nnz:
+        need = nnz - (0 if keys is None else keys.numel())
+        m = int(need * 1.12) + 4096
+        us = torch.searchsorted(cu, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=nu - 1)
+        it = torch.searchsorted(ci, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=ni - 1)
+        new = us * ni + it
+        del us, it
+        keys = torch.unique(new if keys is None else torch.cat([keys, new]))
+        del new
+    perm = torch.randperm(keys.numel(), device=dev, generator=g)[:nnz]
+    keys = keys[perm]
+    del perm
+    users = (keys // ni).to(torch.int32)
+    items = (keys % ni).to(torch.int32)
+    del keys
+    # planted rank-16 model
+    rank = 16
+    bu = torch.randn(nu, device=dev, generator=g) * 0.3
+    bi = torch.randn(ni, device=dev, generator=g) * 0.3
+    p = torch.randn(nu, rank, device=dev, generator=g) * 0.35
+    q = torch.randn(ni, rank, device=dev, generator=g) * 0.35
+    r = torch.empty(nnz, device=dev, dtype=torch.float32)
+    step = 1 << 24
+    for a in range(0, nnz, step):
+        ul, il = users[a:a + step].long(), items[a:a + step].long()
+        val = 3.6 + bu[ul] + bi[il] + (p[ul] * q[il]).sum(1)
+        val += torch.randn(val.shape[0], device=dev, generator=g) * 0.5
+        r[a:a + step] = val.round_().clamp_(1.0, 5.0)
+    idx = torch.stack([users + user_offset, items], dim=1).contiguous()
+    return idx, r
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from mfrec_b200 import _native, synth
+    from mfrec_b200.lib import kmf_train
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nu, ni, nnz, k = synth.SHAPES[args.workload]
+    if args.nnz:
+        nnz = args.nnz
+    if world > 1:
+        from mfrec_b200 import dsgd
+        return dsgd.bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, HP, gpu_synth,
+                                    ClockSampler, algorithmic_bytes_per_update, measured_peaks)
+
+    t_setup = time.time()
+    idx_d, r_d = gpu_synth(torch, dev, nu, ni, nnz, seed=0)
+    torch.cuda.synchronize()
+    ctx = _native.Context(local)
+    u0, v0 = synth.init_factors(nu, ni, k, seed=2)
+
+    # ---------------- device-resident arm: K epochs, CUDA events on the library stream ------
+    R = _native.Ratings(None, None, ni, nu, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
+                        nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
+                        workers=args.workers)
+    M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
+    se = torch.zeros(args.steps + args.warmup, device=dev, dtype=torch.float64)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    launches0 = ctx.launch_count
+    for e in range(args.warmup):
+        M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
+                    sq_err_ptr=se.data_ptr() + 8 * e)
+    ctx.sync()
+    launches_warm = ctx.launch_count - launches0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        launches1 = ctx.launch_count
+        ev0.record(stream)
+        for e in range(args.steps):
+            M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
+                        sq_err_ptr=se.data_ptr() + 8 * (args.warmup + e))
+        ev1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        launches_timed = ctx.launch_count - launches1
+    ms = ev0.elapsed_time(ev1)
+    ms_per_step = ms / args.steps
+    value = nnz * args.steps / (ms * 1e-3)
+    rmse_curve = torch.sqrt(se / nnz).cpu().numpy().tolist()
+
+    peak, peak_src = measured_peaks()
+    bpu = algorithmic_bytes_per_update(k)
+    # dominant kernel = sgd_block_kernel (launches_timed - steps reduce launches); per-launch
+    # figures: algorithmic bytes of one launch / its average duration
+    n_sgd = launches_timed - args.steps
+    achieved = value * bpu / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "sgd_block_kernel", "algorithmic_bytes_per_update": bpu,
+                "updates_per_launch": nnz * args.steps / max(n_sgd, 1),
+                "avg_launch_us": ms * 1e3 / max(n_sgd, 1)}
+
+    # ---------------- end-to-end arm: the public drop-in call with host buffers -----------------
+    e2e = None
+    if not args.no_e2e:
+        del M, R
+        idx_h = torch.empty((nnz, 2), dtype=torch.int32, pin_memory=True)
+        r_h = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
+        idx_h.copy_(idx_d)
+        r_h.copy_(r_d.double())
+        u_h = torch.from_numpy(u0).pin_memory()
+        v_h = torch.from_numpy(v0).pin_memory()
+        ib_h = torch.zeros(ni, dtype=torch.float64).pin_memory()
+        ub_h = torch.zeros(nu, dtype=torch.float64).pin_memory()
+        un, vn, ibn, ubn = u_h.numpy(), v_h.numpy(), ib_h.numpy(), ub_h.numpy()
+        idxn, rn = idx_h.numpy(), r_h.numpy()
+        kmf_train.options["device"] = local
+
+        def one_call():
+            kmf_train.train_linear_kernel(1, k, 0.1, HP["lr"], 0.0, 0.0, HP["K_users"], HP["K_items"],
+                                          HP["K_bias"], 0.0, un, vn, idxn, rn, ibn, ubn)
+            return kmf_train.last_rmse[-1]
+
+        one_call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            last = one_call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = idxn.nbytes + rn.nbytes + un.nbytes + vn.nbytes + ibn.nbytes + ubn.nbytes
+        d2h = un.nbytes + vn.nbytes + ibn.nbytes + ubn.nbytes + 8
+        e2e = {"value": nnz * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3 / args.e2e_steps,
+               "steps": args.e2e_steps, "epochs_per_call": 1, "last_rmse": float(last)}
+
+    cpu_baseline = None
+    if not args.no_cpu:
+        cpu_baseline = time_reference(args.workload, nnz_sample=args.cpu_sample, epochs=1)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "%s-shaped %dx%d nnz=%d k=%d (BASELINE configs[2])" % (args.workload, nu, ni, nnz, k),
+                      "kernel": "train_linear_kernel", "schedule": "stratified B=%d W=%d" % (R_B_W[0], R_B_W[1]) if False else None,
+                      "l2": "inputs (1.2 GB ratings + 255 MB factors) exceed the 126 MB L2",
+                      "hyper": HP},
+           "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+           "gpu_launches": int(launches_timed), "clocks": clocks.summary(),
+           "rmse_per_epoch": rmse_curve, "setup_s": time.time() - t_setup}
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU kernel (oracle/_ref, else our C port) on host cores
+# --------------------------------------------------------------------------------------------
+def time_reference(workload, nnz_sample, epochs=1):
+    """Times kmf_train.train_linear_kernel (the reference's own Cython build when available) on a
+    bounded sample: the first `nnz_sample` ratings of the workload with FULL-SIZE factor matrices
+    (so the strided access pattern is the real one).  Single thread: the reference holds the GIL
+    and has no threading."""
+    from mfrec_b200 import synth
+    from oracle import cpu, ref
+    nu, ni, nnz, k = synth.SHAPES[workload]
+    n = int(min(nnz_sample, nnz))
+    rng = np.random.Generator(np.random.PCG64(0))
+    wu, wi = synth.marginals(nu, ni, 0)
+    cu, ci = np.cumsum(wu), np.cumsum(wi)
+    idx = np.empty((n, 2), dtype=np.int32)
+    idx[:, 0] = np.minimum(np.searchsorted(cu, rng.random(n)), nu - 1)
+    idx[:, 1] = np.minimum(np.searchsorted(ci, rng.random(n)), ni - 1)
+    r = rng.integers(1, 6, n).astype(np.float64)
+    u, v = synth.init_factors(nu, ni, k, seed=2)
+    ib, ub = np.zeros(ni), np.zeros(nu)
+    if ref.available():
+        kind = "reference"
+        fn = ref.kmf_train().train_linear_kernel
+        t0 = time.perf_counter()
+        fn(epochs, k, 0.1, HP["lr"], 0.0, 0.0, HP["K_users"], HP["K_items"], HP["K_bias"], 0.0,
+           u, v, idx, r, ib, ub, 1, 1, 0)
+        dt = time.perf_counter() - t0
+    else:
+        kind = "port"
+        t0 = time.perf_counter()
+        cpu.kmf_train("linear", epochs, k, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"], u, v, idx, r, ib, ub)
+        dt = time.perf_counter() - t0
+    return {"value": n * epochs / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d-rating sample of the %s workload, full-size factor matrices (%dx%d, k=%d), %d epoch, %.1f s"
+                      % (n, workload, nu, ni, k, epochs, dt),
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from mfrec_b200 import synth
+    nu, ni, nnz, k = synth.SHAPES[args.workload]
+    vals = []
+    for _ in range(args.warmup):
+        time_reference(args.workload, max(args.cpu_sample // 10, 1000))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(time_reference(args.workload, args.cpu_sample))
+    dt = time.perf_counter() - t0
+    value = float(np.mean([v["value"] for v in vals]))
+    base = dict(vals[-1])
+    base["value"] = value
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "%s-shaped %dx%d k=%d, %d-rating sample per step" % (args.workload, nu, ni, k, args.cpu_sample),
+                       "kernel": "train_linear_kernel", "hyper": HP},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="netflix", choices=["ml100k", "ml20m", "netflix", "yahoo"])
+    ap.add_argument("--nnz", type=int, default=0, help="override the number of ratings (debug)")
+    ap.add_argument("--row-blocks", type=int, default=0)
+    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=5_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        print("bench.py: warmup < 3 breaks the timing rules; using 3", file=sys.stderr)
+        args.warmup = 3
+    out = run_reference(args) if args.impl == "reference" else run_native(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,225 @@
+/*
+ * mfrec_b200.h -- C ABI of libmfrec_b200.so, the B200 (sm_100a) implementation of mfrec's
+ * latent-factor SGD hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only, no torch / numpy / CUDA
+ * types.  Each entry point replaces one native function (or one interpreted inner loop) of
+ * the reference; the file:line it replaces is cited beside it (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stubs that bind these in
+ * mfrec/lib/kmf_train.py and mfrec/lib/gd_estimator.py.
+ *
+ * Array conventions are the reference's own:
+ *   u  : ITEM factors, float64, feature-major [k][ni], C-contiguous, mutated in place
+ *   v  : USER factors, float64, feature-major [k][nu], C-contiguous, mutated in place
+ *   ratings_index : int32 [nnz][2] = (user, item)      ratings : float64 [nnz]
+ *   items_bias float64 [ni], users_bias float64 [nu]
+ * All host pointers are borrowed for the duration of the call only.
+ *
+ * Every function returns MFREC_OK (0) or a negative mfrec_status; mfrec_last_error()
+ * gives the message.  There is no CPU fallback: without a usable CUDA device every
+ * compute entry point fails with MFREC_ERR_CUDA.
+ *
+ * Threading: one in-flight call per mfrec_ctx; different contexts are independent.
+ */
+#ifndef MFREC_B200_H
+#define MFREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFREC_B200_ABI_VERSION 1
+
+typedef enum mfrec_status {
+    MFREC_OK = 0,
+    MFREC_ERR_BAD_ARG = -1,   /* null pointer, negative size, unknown enum value        */
+    MFREC_ERR_INDEX = -2,     /* a user / item index outside [0, nu) / [0, ni)           */
+    MFREC_ERR_OOM = -3,       /* host or device allocation failed                       */
+    MFREC_ERR_CUDA = -4,      /* CUDA runtime error or no sm_100 device                 */
+    MFREC_ERR_UNSUPPORTED = -5 /* e.g. k larger than the kernels are instantiated for   */
+} mfrec_status;
+
+typedef struct mfrec_ctx mfrec_ctx;         /* one device + stream + scratch            */
+typedef struct mfrec_ratings mfrec_ratings; /* ratings packed into HBM (block layout)   */
+typedef struct mfrec_model mfrec_model;     /* factors + biases resident in HBM         */
+
+/* SGD kernels of mfrec/lib/kmf_train.pyx */
+enum { MFREC_KERNEL_LINEAR = 0,    /* train_linear_kernel   kmf_train.pyx:195-277 */
+       MFREC_KERNEL_LOGISTIC = 1   /* train_logistic_kernel kmf_train.pyx:103-189 */ };
+
+/* Funk-SVD per-feature loops of mfrec/lib/gd_estimator.pyx */
+enum { MFREC_FUNK_WITHOUT_BIAS = 0,  /* estimator_loop_without_bias  :691-779 */
+       MFREC_FUNK_WITH_BIAS = 1,     /* estimator_loop_with_bias     :489-582 */
+       MFREC_FUNK_WITH_BIAS_DEV = 2  /* estimator_loop_with_bias_dev :588-685 */ };
+
+/* Predictors (mfrec/recommendation) */
+enum { MFREC_PRED_GD_RATING = 0,       /* gradient_descent.py:621-631  dot + 1.0                   */
+       MFREC_PRED_GD_RATING_BIAS = 1,  /* gradient_descent.py:637-648  dot + mu + b_i + b_u        */
+       MFREC_PRED_KMF_LINEAR = 2,      /* kmf.py:88-94                 dot + b_i + b_u             */
+       MFREC_PRED_KMF_LOGISTIC = 3,    /* kmf.py:79-85                 min + sigma(.)*(max-min)    */
+       MFREC_PRED_KMF_LINEAR_NEG = 4,  /* kmf.py:97-103                min + (.)*(max-min)         */
+       MFREC_PRED_DOT = 5              /* wrmf.py:67-69                dot                         */ };
+
+/* Update schedules */
+enum { MFREC_SCHED_STRATIFIED = 0, /* conflict-free block schedule, fp32, all SMs (default)     */
+       MFREC_SCHED_SEQUENTIAL = 1  /* the reference's exact order, fp64, one thread: bit-exact
+                                      with the reference for the linear / Funk kernels; meant
+                                      for verification and for tiny fold-in calls              */ };
+
+/* Optional knobs; pass NULL for defaults.  Zero in any field means "choose for me". */
+typedef struct mfrec_opts {
+    int32_t schedule;     /* MFREC_SCHED_*                                                  */
+    int32_t row_blocks;   /* B: CTA-level row/column blocks per device (default: from nnz)   */
+    int32_t workers;      /* W: warps per CTA = warp-level row/column groups (default 8)     */
+    int32_t n_slabs;      /* G: item slabs (one per GPU of a DSGD ring); 1 on a single GPU   */
+    int32_t keep_order;   /* keep packed-position -> input-index map for mfrec_ratings_order */
+    int32_t k_hint;       /* number of features the layout will be trained with (sizes the
+                             shared-memory Q tile; 0 = assume the maximum, 256)               */
+    uint64_t seed;        /* tie-break seed of the partitioner                               */
+} mfrec_opts;
+
+/* ---- context ---------------------------------------------------------------------- */
+/* device < 0 means "current device". */
+int mfrec_ctx_create(int device, mfrec_ctx **out);
+void mfrec_ctx_destroy(mfrec_ctx *ctx);
+/* ctx may be NULL: returns the last error raised on this thread without a context. */
+const char *mfrec_last_error(const mfrec_ctx *ctx);
+int mfrec_abi_version(void);
+/* The CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
+void *mfrec_ctx_stream(mfrec_ctx *ctx);
+int mfrec_ctx_sync(mfrec_ctx *ctx);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+int64_t mfrec_ctx_launch_count(const mfrec_ctx *ctx);
+
+/* ---- one-call drop-ins (host buffers in, host buffers out) ----------------------- */
+
+/* Replaces train_linear_kernel / train_logistic_kernel (kmf_train.pyx:195-277, 103-189)
+ * as called by KMFRecommender.train / retrain_user / retrain_item (kmf.py:120-146,197-220).
+ * Copies the inputs to the device, packs the ratings, runs nbr_epochs epochs, writes
+ * u, v, items_bias, users_bias back in place.  rmse_per_epoch: nullable, [nbr_epochs],
+ * receives sqrt(sum err^2 / nnz) of each epoch (the value the reference prints). */
+int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k, double learning_rate,
+                    double K_users, double K_items, double K_bias, double *u, double *v,
+                    const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                    int32_t ni, int32_t nu, double *items_bias, double *users_bias,
+                    int update_users, int update_items, const mfrec_opts *opts,
+                    double *rmse_per_epoch);
+
+/* Replaces estimator_loop_without_bias / _with_bias / _with_bias_dev
+ * (gd_estimator.pyx:691-779, 489-582, 588-685) as called by GDRecommender.feature_training
+ * and retrain_user / retrain_item (gradient_descent.py:506-545, 879-905).
+ * max_epochs is accepted and ignored exactly like the reference does.
+ * feature_epochs (nullable, int32 [k]) and feature_rmse (nullable, [k]) report the passes
+ * run and the last rmse of every feature.  Biases are read-only here. */
+int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int max_epochs,
+                     double min_improvement, int k, double f_init, double learning_rate,
+                     double K, double overall_avg, double *u, double *v,
+                     const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                     int32_t ni, int32_t nu, const double *items_bias,
+                     const double *users_bias, int update_users, int update_items,
+                     const mfrec_opts *opts, int32_t *feature_epochs, double *feature_rmse);
+
+/* Replaces the per-pair Python loop of metrics.test_predict_rating (metrics.py:58-67)
+ * over the predictors above.  pairs: int32 [n][2] = (user, item).  out: float64 [n]. */
+int mfrec_predict_pairs(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,
+                        int32_t ni, int32_t nu, const int32_t *pairs, int64_t n, double mu,
+                        const double *items_bias, const double *users_bias, double min_rating,
+                        double max_rating, double *out);
+
+/* metrics.test_predict_rating (metrics.py:51-82): errors = real - predicted, NaN dropped;
+ * stats = { rmse, mae, var(|e|), n_valid }.  errors_out nullable float64 [n]. */
+int mfrec_rmse_pairs(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,
+                     int32_t ni, int32_t nu, const int32_t *pairs, const double *real,
+                     int64_t n, double mu, const double *items_bias, const double *users_bias,
+                     double min_rating, double max_rating, double *errors_out, double stats[4]);
+
+/* Replaces the per-item loops of MFRecommender.find_recommended_items (mf.py:144-193) and
+ * GDRecommender.find_user_top_match (gradient_descent.py:769-802) for a batch of users:
+ * score items [0, n_candidates), mask the user's rated items and the item whose id equals
+ * the user id (reference quirk), NaN -> 0, drop exact zeros, order by score descending
+ * (ties: ascending item id), keep N.  rated_indptr int64 [n_users+1] / rated_items int32:
+ * CSR of already-rated items per listed user.  out_items int32 [n_users][N] (-1 padded),
+ * out_scores float64 [n_users][N], out_counts int32 [n_users]. */
+int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,
+               int32_t ni, int32_t nu, const int32_t *users, int32_t n_users,
+               int32_t n_candidates, const int64_t *rated_indptr, const int32_t *rated_items,
+               double mu, const double *items_bias, const double *users_bias,
+               double min_rating, double max_rating, int32_t N, int32_t *out_items,
+               double *out_scores, int32_t *out_counts);
+
+/* compute_overall_avg (base.py:504-508), compute_items_bias_bk / compute_users_bias_bk
+ * (mf.py:78-121): mu, b_i = sum(r - mu)/(K3 + n_i), b_u = sum(r - mu - b_i)/(K2 + n_u). */
+int mfrec_bias_stats(mfrec_ctx *ctx, const int32_t *ratings_index, const double *ratings,
+                     int64_t nnz, int32_t ni, int32_t nu, double K2, double K3, double *mu_out,
+                     double *items_bias, double *users_bias);
+
+/* ---- resident objects (what the one-call drop-ins are made of) ------------------- */
+
+/* Ratings layout: COO -> block-bucketed, user-sorted COO in HBM (the GPU counterpart of
+ * BaseRecommender.get_ratings, base.py:1115-1131).  Users and items are relabelled so every
+ * row group / column group is a contiguous id range; ratings are bucketed by
+ * (slab, row block, column block, phase, worker) and sorted by (user, item) inside a bucket.
+ * Either pointer pair may be device memory (is_device != 0) or host memory.
+ * item_degree: nullable int64 [ni], global item degrees when this process holds only a
+ * user-slice of the matrix (multi-GPU); NULL = count from the given ratings. */
+int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, const void *ratings,
+                       int ratings_are_f32, int is_device, int64_t nnz, int32_t ni, int32_t nu,
+                       const int64_t *item_degree, const mfrec_opts *opts,
+                       mfrec_ratings **out);
+void mfrec_ratings_destroy(mfrec_ratings *r);
+/* Shape of the layout: info = { B, W, n_slabs, max column-block items, nnz, kernel launches
+ * per epoch, max bucket nnz, packed bytes }. */
+int mfrec_ratings_info(const mfrec_ratings *r, int64_t info[8]);
+/* Relabelling: user_perm int32 [nu] / item_perm int32 [ni], old id -> packed id. */
+int mfrec_ratings_perm(mfrec_ctx *ctx, const mfrec_ratings *r, int32_t *user_perm,
+                       int32_t *item_perm);
+/* order int64 [packed_len]: input index of the rating stored at each packed position, -1 for
+ * alignment padding (needs opts.keep_order at pack time).  packed_len = info[7]. */
+int mfrec_ratings_order(mfrec_ctx *ctx, const mfrec_ratings *r, int64_t *order);
+/* Buckets in storage order (slab, row block, column block, phase, worker):
+ * offsets int64 [n_buckets + 1] = first packed position, counts int32 [n_buckets];
+ * n_buckets = n_slabs * B * B * W * W.  A one-thread replay that walks
+ * slab, sub-epoch s, row block rb (column block (rb + s) mod B), phase, worker, bucket order
+ * is an equivalent sequential order of the stratified schedule. */
+int mfrec_ratings_offsets(mfrec_ctx *ctx, const mfrec_ratings *r, int64_t *offsets,
+                          int32_t *counts);
+/* The packed triples themselves, [packed_len][3] 32-bit words = (packed user id, packed item
+ * id, float32 rating); padding entries are all-zero. */
+int mfrec_ratings_packed(mfrec_ctx *ctx, const mfrec_ratings *r, void *out);
+/* Item-id range [begin, end) of slab s in packed ids (the Q block a DSGD rank exchanges). */
+int mfrec_ratings_slab_items(const mfrec_ratings *r, int32_t slab, int32_t *begin, int32_t *end);
+
+/* Factors in HBM as row-major [n][kpad] float32 (kpad = k rounded up to 32 * {1,2,4,8}),
+ * rows in packed-id order when `layout` is given, identity order when it is NULL.
+ * Any of u / v / items_bias / users_bias may be NULL (zeros). */
+int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, int k, int32_t ni,
+                       int32_t nu, const double *u, const double *v, const double *items_bias,
+                       const double *users_bias, mfrec_model **out);
+int mfrec_model_read(mfrec_ctx *ctx, const mfrec_model *m, double *u, double *v,
+                     double *items_bias, double *users_bias);
+void mfrec_model_destroy(mfrec_model *m);
+/* Raw device views for a multi-GPU driver that exchanges item blocks itself:
+ * ptrs = { Q float32 [ni][kpad], item bias float32 [ni], P, user bias }, dims = { ni, nu, kpad }. */
+int mfrec_model_device_ptrs(const mfrec_model *m, void *ptrs[4], int64_t dims[3]);
+
+/* One epoch (all B sub-epochs of slab `slab`, or of every slab in order when slab < 0) of
+ * the stratified schedule, asynchronous on the context stream.  sq_err_out: nullable DEVICE
+ * pointer to one double that receives the epoch's sum of squared errors. */
+int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_model *m, int kernel,
+                    double learning_rate, double K_users, double K_items, double K_bias,
+                    int update_users, int update_items, int32_t slab, double *sq_err_out);
+
+/* Batched predict / RMSE on a resident model; pairs and outputs are DEVICE pointers when
+ * is_device != 0.  out float64 [n] nullable; stats_out double[4] (host) nullable
+ * = { sum err^2, sum |err|, sum err^2 of |err| (for var), n_valid } raw sums. */
+int mfrec_model_predict(mfrec_ctx *ctx, const mfrec_model *m, int predictor,
+                        const int32_t *pairs, const void *real, int real_is_f32, int64_t n,
+                        int is_device, double mu, double min_rating, double max_rating,
+                        double *out, double stats_out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFREC_B200_H */

@@ -1,0 +1,142 @@
+// Internal declarations shared by the translation units of libmfrec_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "mfrec_b200.h"
+
+// One packed rating: ids are PACKED (relabelled) user / item ids.
+struct __align__(4) PackedRating {
+    int32_t u;
+    int32_t i;
+    float r;
+};
+static_assert(sizeof(PackedRating) == 12, "rating triple must be 12 bytes");
+
+struct mfrec_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    double *se_scratch = nullptr;  // per-CTA squared-error partials of one epoch
+    size_t se_cap = 0;
+    std::string err;
+};
+
+struct mfrec_ratings {
+    int device = 0;
+    int64_t nnz = 0;
+    int32_t ni = 0, nu = 0;
+    int B = 1, W = 1, G = 1;
+    int64_t n_buckets = 0;
+    int64_t packed_len = 0;        // nnz + alignment padding
+    int32_t max_cb_items = 0;      // widest column block (items) -> shared-memory tile size
+    int64_t max_bucket = 0;
+    // device
+    int32_t *user_perm = nullptr;  // [nu] old -> packed id
+    int32_t *item_perm = nullptr;  // [ni]
+    int32_t *col_start = nullptr;  // [G*B*W + 1] packed item id where each column group begins
+    PackedRating *packed = nullptr;
+    int64_t *bucket_off = nullptr; // [n_buckets] first packed position (multiple of 4)
+    int32_t *bucket_cnt = nullptr; // [n_buckets]
+    int64_t *order = nullptr;      // [packed_len] input index (or -1 for padding), optional
+    // host mirrors
+    std::vector<int32_t> h_row_start;  // [B*W + 1]
+    std::vector<int32_t> h_col_start;  // [G*B*W + 1]
+};
+
+struct mfrec_model {
+    int device = 0;
+    int k = 0, kpad = 0;
+    int32_t ni = 0, nu = 0;
+    float *Q = nullptr;   // [ni][kpad]  item factors
+    float *ib = nullptr;  // [ni]
+    float *P = nullptr;   // [nu][kpad]  user factors
+    float *ub = nullptr;  // [nu]
+    int32_t *user_perm = nullptr;  // own copies (nullptr = identity)
+    int32_t *item_perm = nullptr;
+};
+
+// ---- error plumbing -------------------------------------------------------------------
+int mfrec_set_error(mfrec_ctx *ctx, int code, const char *fmt, ...);
+
+#define MF_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            return mfrec_set_error((ctx),                                                    \
+                                   e__ == cudaErrorMemoryAllocation ? MFREC_ERR_OOM          \
+                                                                    : MFREC_ERR_CUDA,        \
+                                   "%s:%d: %s -> %s", __FILE__, __LINE__, #call,             \
+                                   cudaGetErrorString(e__));                                 \
+        }                                                                                    \
+    } while (0)
+
+#define MF_TRY(call)                      \
+    do {                                  \
+        int rc__ = (call);                \
+        if (rc__ != MFREC_OK) return rc__; \
+    } while (0)
+
+#define MF_LAUNCH_CHECK(ctx)                 \
+    do {                                     \
+        (ctx)->launches += 1;                \
+        MF_CUDA((ctx), cudaGetLastError());  \
+    } while (0)
+
+// Device buffer that frees itself (host-side RAII for scratch allocations).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    T *take()
+    {
+        T *q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
+static inline int mfrec_kpad(int k)
+{
+    if (k <= 32) return 32;
+    if (k <= 64) return 64;
+    if (k <= 128) return 128;
+    if (k <= 256) return 256;
+    return -1;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// layout.cu
+int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
+                        const int32_t *perm_dev, float *dst_nk);
+int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,
+                          const int32_t *perm_dev, double *host_kn);
+int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
+                     float *dst);
+int mfrec_download_vec(mfrec_ctx *ctx, const float *src, int32_t n, const int32_t *perm_dev,
+                       double *host);

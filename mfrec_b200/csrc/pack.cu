@@ -1,0 +1,483 @@
+// Ratings layout: COO -> block-bucketed, user-sorted COO resident in HBM.
+//
+// GPU counterpart of BaseRecommender.get_ratings (reference base.py:1115-1131): instead of one
+// shuffled list walked by one thread, ratings are bucketed so that the SGD kernel can run
+// B * W warps that never touch the same user row or item row at the same time (the DSGD /
+// cuMF_SGD block schedule), see sgd.cu.
+//
+//   users  -> B row blocks      x W row groups      (balanced by degree, LPT)
+//   items  -> G slabs x B column blocks x W column groups
+//   bucket(slab g, row block rb, column block cb, phase p, worker w) holds the ratings of
+//   row group (rb, w) x column group (cb, (w + p) mod W), sorted by (user, item).
+//   Buckets are stored in (g, rb, cb, p, w) order, each starting on a 16-byte boundary so a
+//   CTA can stream them with cp.async.bulk.
+//
+// Users and items are relabelled ("packed ids") so each group is a contiguous id range; the
+// factor matrices live in HBM in packed-id order, which makes every column block's Q tile one
+// contiguous chunk.
+//
+// Steps (all HBM-bound integer work):
+//   1. degree histograms + index validation                 (1 pass over idx)
+//   2. host: hierarchical LPT partition of users / items     (O(n log B), n = nu + ni)
+//   3. 64-bit key = bucket | packed user | packed item       (1 pass)
+//   4. stable LSD radix sort of (key, input position)        (cub::DeviceRadixSort)
+//   5. bucket histogram -> padded offsets                    (1 pass + scan)
+//   6. gather ratings into the packed array                  (1 pass)
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <numeric>
+#include <queue>
+
+#include "common.cuh"
+
+namespace {
+
+__global__ void degree_kernel(const int32_t *__restrict__ idx, int64_t nnz, int32_t ni, int32_t nu,
+                              int32_t *__restrict__ deg_u, int32_t *__restrict__ deg_i,
+                              int32_t *__restrict__ bad)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnz; n += stride) {
+        const int2 ui = reinterpret_cast<const int2 *>(idx)[n];
+        if (ui.x < 0 || ui.x >= nu || ui.y < 0 || ui.y >= ni) {
+            atomicOr(bad, 1);
+            continue;
+        }
+        atomicAdd(&deg_u[ui.x], 1);
+        atomicAdd(&deg_i[ui.y], 1);
+    }
+}
+
+struct KeyLayout {
+    int bits_i, bits_u, bits_b;
+    int W, B;
+};
+
+__global__ void key_kernel(const int32_t *__restrict__ idx, int64_t nnz,
+                           const int32_t *__restrict__ user_perm,
+                           const int32_t *__restrict__ item_perm,
+                           const int32_t *__restrict__ user_group,  // packed row group  [nu]
+                           const int32_t *__restrict__ item_group,  // packed col group  [ni]
+                           KeyLayout kl, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnz; n += stride) {
+        const int2 ui = reinterpret_cast<const int2 *>(idx)[n];
+        const int rg = user_group[ui.x], cg = item_group[ui.y];
+        const int rb = rg / kl.W, wr = rg % kl.W;
+        const int cbg = cg / kl.W, wc = cg % kl.W;   // cbg = slab * B + local column block
+        const int slab = cbg / kl.B, cbl = cbg % kl.B;
+        const int p = (wc - wr + kl.W) % kl.W;
+        const uint64_t bucket =
+            ((((uint64_t)slab * kl.B + rb) * kl.B + cbl) * kl.W + p) * kl.W + wr;
+        keys[n] = (bucket << (kl.bits_u + kl.bits_i)) |
+                  ((uint64_t)(uint32_t)user_perm[ui.x] << kl.bits_i) |
+                  (uint64_t)(uint32_t)item_perm[ui.y];
+        vals[n] = (uint32_t)n;
+    }
+}
+
+__global__ void bucket_hist_kernel(const uint64_t *__restrict__ keys, int64_t nnz, int shift,
+                                   int32_t *__restrict__ cnt)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnz; n += stride)
+        atomicAdd(&cnt[keys[n] >> shift], 1);
+}
+
+__global__ void pad_counts_kernel(const int32_t *__restrict__ cnt, int64_t nb,
+                                  int64_t *__restrict__ raw, int64_t *__restrict__ padded)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) {
+        raw[b] = cnt[b];
+        padded[b] = (cnt[b] + 3) & ~3;
+    }
+}
+
+template <typename RT>
+__global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                              int64_t nnz, const RT *__restrict__ ratings, KeyLayout kl,
+                              const int64_t *__restrict__ raw_off,
+                              const int64_t *__restrict__ pad_off,
+                              PackedRating *__restrict__ packed, int64_t *__restrict__ order)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t mask_i = (1ull << kl.bits_i) - 1, mask_u = (1ull << kl.bits_u) - 1;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nnz; s += stride) {
+        const uint64_t key = keys[s];
+        const uint32_t src = vals[s];
+        const uint64_t b = key >> (kl.bits_u + kl.bits_i);
+        const int64_t dst = pad_off[b] + (s - raw_off[b]);
+        PackedRating pr;
+        pr.u = (int32_t)((key >> kl.bits_i) & mask_u);
+        pr.i = (int32_t)(key & mask_i);
+        pr.r = (float)ratings[src];
+        packed[dst] = pr;
+        if (order) order[dst] = (int64_t)src;
+    }
+}
+
+__global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int bits_for(int64_t n)
+{
+    int b = 1;
+    while ((1ll << b) < n) ++b;
+    return b;
+}
+
+uint64_t mix64(uint64_t x)
+{
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+// Hierarchical longest-processing-time partition: ids -> nblocks blocks -> W groups each,
+// balanced by (degree + 1).  Deterministic for a given seed.  Outputs, for every id, its
+// group (block * W + group-in-block) and its packed id (groups are contiguous id ranges,
+// ascending original id inside a group); start[g] = first packed id of group g.
+void lpt_partition(const std::vector<int32_t> &deg, int nblocks, int W, uint64_t seed,
+                   std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
+                   std::vector<int32_t> &start)
+{
+    const int64_t n = (int64_t)deg.size();
+    std::vector<int32_t> ids(n);
+    std::iota(ids.begin(), ids.end(), 0);
+    std::sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
+        if (deg[a] != deg[b]) return deg[a] > deg[b];
+        const uint64_t ha = mix64(seed ^ (uint64_t)a), hb = mix64(seed ^ (uint64_t)b);
+        if (ha != hb) return ha < hb;
+        return a < b;
+    });
+    typedef std::pair<int64_t, int> Load;  // (load, bin): min-heap, ties -> lowest bin
+    auto lpt = [&](const std::vector<int32_t> &order, int bins, std::vector<int32_t> &bin_of) {
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int b = 0; b < bins; ++b) heap.push(Load(0, b));
+        for (int32_t id : order) {
+            Load top = heap.top();
+            heap.pop();
+            bin_of[id] = top.second;
+            top.first += (int64_t)deg[id] + 1;
+            heap.push(top);
+        }
+    };
+    std::vector<int32_t> block_of(n, 0);
+    lpt(ids, nblocks, block_of);
+    std::vector<std::vector<int32_t>> members(nblocks);
+    for (int32_t id : ids) members[block_of[id]].push_back(id);  // keeps the degree order
+    group_of.assign(n, 0);
+    std::vector<int32_t> sub(n, 0);
+    for (int b = 0; b < nblocks; ++b) {
+        lpt(members[b], W, sub);
+        for (int32_t id : members[b]) group_of[id] = b * W + sub[id];
+    }
+    const int ng = nblocks * W;
+    std::vector<int32_t> count(ng + 1, 0);
+    for (int64_t id = 0; id < n; ++id) count[group_of[id] + 1] += 1;
+    start.assign(ng + 1, 0);
+    for (int g = 0; g < ng; ++g) start[g + 1] = start[g] + count[g + 1];
+    std::vector<int32_t> cursor(start.begin(), start.end() - 1);
+    perm.assign(n, 0);
+    for (int64_t id = 0; id < n; ++id) perm[id] = cursor[group_of[id]]++;
+}
+
+}  // namespace
+
+extern "C" void mfrec_ratings_destroy(mfrec_ratings *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaFree(r->user_perm);
+    cudaFree(r->item_perm);
+    cudaFree(r->col_start);
+    cudaFree(r->packed);
+    cudaFree(r->bucket_off);
+    cudaFree(r->bucket_cnt);
+    cudaFree(r->order);
+    delete r;
+}
+
+extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, const void *ratings,
+                                  int ratings_are_f32, int is_device, int64_t nnz, int32_t ni,
+                                  int32_t nu, const int64_t *item_degree, const mfrec_opts *opts,
+                                  mfrec_ratings **out)
+{
+    if (!ctx || !out) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_pack: NULL argument");
+    *out = nullptr;
+    if (nnz < 0 || ni <= 0 || nu <= 0 || (nnz > 0 && (!ratings_index || !ratings)))
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_pack: nnz=%lld ni=%d nu=%d",
+                               (long long)nnz, ni, nu);
+    if (nnz >= (1ll << 32))
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: nnz >= 2^32 per device");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int G = (opts && opts->n_slabs > 0) ? opts->n_slabs : 1;
+    int W = (opts && opts->workers > 0) ? opts->workers : 8;
+    if (W > 16) W = 16;  // the SGD kernel is built for at most 16 warps per CTA
+    int B = (opts && opts->row_blocks > 0) ? opts->row_blocks : 0;
+    if (B == 0) {
+        // keep ~16+ ratings per bucket, never more row blocks than SMs
+        double per_slab = (double)nnz / G;
+        B = (int)(sqrt(per_slab / 16.0) / W);
+        B = std::max(1, std::min(B, ctx->sm_count));
+    }
+    B = (int)std::max<int64_t>(1, std::min<int64_t>(B, std::min<int64_t>(nu, ni / G) / W));
+    const uint64_t seed = opts ? opts->seed : 0;
+    const bool keep_order = opts && opts->keep_order;
+    int kpad_hint = (opts && opts->k_hint > 0) ? mfrec_kpad(opts->k_hint) : 256;
+    if (kpad_hint < 0) kpad_hint = 256;
+
+    // ---- stage inputs on the device -------------------------------------------------
+    DevBuf<int32_t> idx_stage;
+    DevBuf<char> r_stage;
+    const int32_t *d_idx = ratings_index;
+    const void *d_r = ratings;
+    const size_t rsz = ratings_are_f32 ? 4 : 8;
+    if (!is_device && nnz > 0) {
+        MF_CUDA(ctx, idx_stage.alloc((size_t)nnz * 2));
+        MF_CUDA(ctx, r_stage.alloc((size_t)nnz * rsz));
+        MF_CUDA(ctx, cudaMemcpyAsync(idx_stage.p, ratings_index, (size_t)nnz * 8,
+                                     cudaMemcpyHostToDevice, st));
+        MF_CUDA(ctx, cudaMemcpyAsync(r_stage.p, ratings, (size_t)nnz * rsz, cudaMemcpyHostToDevice, st));
+        d_idx = idx_stage.p;
+        d_r = r_stage.p;
+    }
+    const int grid = ctx->sm_count * 8;
+
+    // ---- 1. degrees + validation ------------------------------------------------------
+    DevBuf<int32_t> deg_u, deg_i, bad;
+    MF_CUDA(ctx, deg_u.alloc(nu));
+    MF_CUDA(ctx, deg_i.alloc(ni));
+    MF_CUDA(ctx, bad.alloc(1));
+    MF_CUDA(ctx, cudaMemsetAsync(deg_u.p, 0, (size_t)nu * 4, st));
+    MF_CUDA(ctx, cudaMemsetAsync(deg_i.p, 0, (size_t)ni * 4, st));
+    MF_CUDA(ctx, cudaMemsetAsync(bad.p, 0, 4, st));
+    if (nnz > 0) {
+        degree_kernel<<<grid, 256, 0, st>>>(d_idx, nnz, ni, nu, deg_u.p, deg_i.p, bad.p);
+        MF_LAUNCH_CHECK(ctx);
+    }
+    std::vector<int32_t> h_deg_u(nu), h_deg_i(ni);
+    int32_t h_bad = 0;
+    MF_CUDA(ctx, cudaMemcpyAsync(h_deg_u.data(), deg_u.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(h_deg_i.data(), deg_i.p, (size_t)ni * 4, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_bad)
+        return mfrec_set_error(ctx, MFREC_ERR_INDEX,
+                               "mfrec_ratings_pack: ratings_index has a user outside [0,%d) or an item outside [0,%d)",
+                               nu, ni);
+    if (item_degree)
+        for (int32_t i = 0; i < ni; ++i)
+            h_deg_i[i] = (int32_t)std::min<int64_t>(item_degree[i], INT32_MAX - 1);
+
+    // ---- 2. partition (host) -----------------------------------------------------------
+    mfrec_ratings *R = new (std::nothrow) mfrec_ratings();
+    if (!R) return mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_ratings_pack: host OOM");
+    struct Guard {
+        mfrec_ratings *r;
+        ~Guard() { if (r) mfrec_ratings_destroy(r); }
+    } guard{R};
+    R->device = ctx->device;
+    R->nnz = nnz;
+    R->ni = ni;
+    R->nu = nu;
+    R->G = G;
+    R->W = W;
+    std::vector<int32_t> ug, up, ig, ip;
+    const size_t ring_bytes = (size_t)W * 2 * 128 * sizeof(PackedRating) + 256;
+    for (;;) {
+        lpt_partition(h_deg_u, B, W, seed, ug, up, R->h_row_start);
+        lpt_partition(h_deg_i, G * B, W, seed ^ 0x5bd1e995u, ig, ip, R->h_col_start);
+        int32_t widest = 0;
+        for (int cb = 0; cb < G * B; ++cb)
+            widest = std::max(widest, R->h_col_start[(cb + 1) * W] - R->h_col_start[cb * W]);
+        R->max_cb_items = widest;
+        // the SGD kernel keeps one column block of Q (kpad floats per row) in shared memory;
+        // grow B until the widest block fits
+        const size_t need = (size_t)widest * (kpad_hint + 1) * 4 + ring_bytes;
+        if (need <= ctx->smem_optin || widest <= 1 || (opts && opts->row_blocks > 0)) break;
+        B *= 2;
+    }
+    R->B = B;
+    R->n_buckets = (int64_t)G * B * B * W * W;
+    KeyLayout kl;
+    kl.bits_i = bits_for(ni);
+    kl.bits_u = bits_for(nu);
+    kl.bits_b = bits_for(R->n_buckets);
+    kl.W = W;
+    kl.B = B;
+    if (kl.bits_i + kl.bits_u + kl.bits_b > 64)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                               "mfrec_ratings_pack: sort key needs %d bits", kl.bits_i + kl.bits_u + kl.bits_b);
+
+    DevBuf<int32_t> d_ug, d_ig;
+    MF_CUDA(ctx, d_ug.alloc(nu));
+    MF_CUDA(ctx, d_ig.alloc(ni));
+    MF_CUDA(ctx, cudaMalloc((void **)&R->user_perm, ((size_t)nu + 1) * 4));
+    MF_CUDA(ctx, cudaMalloc((void **)&R->item_perm, ((size_t)ni + 1) * 4));
+    MF_CUDA(ctx, cudaMalloc((void **)&R->col_start, R->h_col_start.size() * 4));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_ug.p, ug.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_ig.p, ig.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(R->user_perm, up.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(R->item_perm, ip.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(R->col_start, R->h_col_start.data(), R->h_col_start.size() * 4,
+                                 cudaMemcpyHostToDevice, st));
+
+    // ---- 3./4. keys + stable radix sort ------------------------------------------------
+    DevBuf<uint64_t> keys_a, keys_b;
+    DevBuf<uint32_t> vals_a, vals_b;
+    MF_CUDA(ctx, keys_a.alloc(nnz));
+    MF_CUDA(ctx, keys_b.alloc(nnz));
+    MF_CUDA(ctx, vals_a.alloc(nnz));
+    MF_CUDA(ctx, vals_b.alloc(nnz));
+    cub::DoubleBuffer<uint64_t> dkeys(keys_a.p, keys_b.p);
+    cub::DoubleBuffer<uint32_t> dvals(vals_a.p, vals_b.p);
+    if (nnz > 0) {
+        key_kernel<<<grid, 256, 0, st>>>(d_idx, nnz, R->user_perm, R->item_perm, d_ug.p, d_ig.p, kl,
+                                         keys_a.p, vals_a.p);
+        MF_LAUNCH_CHECK(ctx);
+        size_t tmp_bytes = 0;
+        const int end_bit = kl.bits_i + kl.bits_u + kl.bits_b;
+        MF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dkeys, dvals, nnz, 0, end_bit, st));
+        DevBuf<char> tmp;
+        MF_CUDA(ctx, tmp.alloc(tmp_bytes));
+        MF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dkeys, dvals, nnz, 0, end_bit, st));
+        ctx->launches += (end_bit + 7) / 8 * 2 + 1;  // histogram + one onesweep pass per digit
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+
+    // ---- 5. bucket histogram -> offsets ---------------------------------------------------
+    const int64_t nb = R->n_buckets;
+    DevBuf<int64_t> raw_cnt, pad_cnt, raw_off;
+    MF_CUDA(ctx, cudaMalloc((void **)&R->bucket_cnt, (size_t)nb * 4));
+    MF_CUDA(ctx, cudaMalloc((void **)&R->bucket_off, ((size_t)nb + 1) * 8));
+    MF_CUDA(ctx, raw_cnt.alloc(nb + 1));
+    MF_CUDA(ctx, pad_cnt.alloc(nb + 1));
+    MF_CUDA(ctx, raw_off.alloc(nb + 1));
+    MF_CUDA(ctx, cudaMemsetAsync(R->bucket_cnt, 0, (size_t)nb * 4, st));
+    MF_CUDA(ctx, cudaMemsetAsync(raw_cnt.p, 0, ((size_t)nb + 1) * 8, st));
+    MF_CUDA(ctx, cudaMemsetAsync(pad_cnt.p, 0, ((size_t)nb + 1) * 8, st));
+    if (nnz > 0) {
+        bucket_hist_kernel<<<grid, 256, 0, st>>>(dkeys.Current(), nnz, kl.bits_u + kl.bits_i, R->bucket_cnt);
+        MF_LAUNCH_CHECK(ctx);
+    }
+    pad_counts_kernel<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(R->bucket_cnt, nb, raw_cnt.p, pad_cnt.p);
+    MF_LAUNCH_CHECK(ctx);
+    {
+        size_t tmp_bytes = 0;
+        MF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, raw_cnt.p, raw_off.p, nb + 1, st));
+        DevBuf<char> tmp;
+        MF_CUDA(ctx, tmp.alloc(tmp_bytes));
+        MF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, raw_cnt.p, raw_off.p, nb + 1, st));
+        MF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, pad_cnt.p, R->bucket_off, nb + 1, st));
+        ctx->launches += 4;
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    int64_t packed_len = 0;
+    MF_CUDA(ctx, cudaMemcpy(&packed_len, R->bucket_off + nb, 8, cudaMemcpyDeviceToHost));
+    R->packed_len = packed_len;
+
+    // ---- 6. gather ------------------------------------------------------------------------
+    // +16 entries of slack: bulk copies are rounded up to 16 bytes
+    MF_CUDA(ctx, cudaMalloc((void **)&R->packed, ((size_t)packed_len + 16) * sizeof(PackedRating)));
+    MF_CUDA(ctx, cudaMemsetAsync(R->packed, 0, ((size_t)packed_len + 16) * sizeof(PackedRating), st));
+    if (keep_order) {
+        MF_CUDA(ctx, cudaMalloc((void **)&R->order, ((size_t)packed_len + 1) * 8));
+        fill_i64_kernel<<<(unsigned)ceil_div64(packed_len + 1, 256), 256, 0, st>>>(R->order, packed_len, -1);
+        MF_LAUNCH_CHECK(ctx);
+    }
+    if (nnz > 0) {
+        if (ratings_are_f32)
+            gather_kernel<float><<<grid, 256, 0, st>>>(dkeys.Current(), dvals.Current(), nnz,
+                                                       (const float *)d_r, kl, raw_off.p,
+                                                       R->bucket_off, R->packed, R->order);
+        else
+            gather_kernel<double><<<grid, 256, 0, st>>>(dkeys.Current(), dvals.Current(), nnz,
+                                                        (const double *)d_r, kl, raw_off.p,
+                                                        R->bucket_off, R->packed, R->order);
+        MF_LAUNCH_CHECK(ctx);
+    }
+    // widest bucket (diagnostic; bounds the longest serial chain of one phase)
+    {
+        std::vector<int32_t> h_cnt((size_t)nb);
+        MF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), R->bucket_cnt, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+        int32_t mx = 0;
+        for (int32_t c : h_cnt) mx = std::max(mx, c);
+        R->max_bucket = mx;
+    }
+    guard.r = nullptr;
+    *out = R;
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_info(const mfrec_ratings *r, int64_t info[8])
+{
+    if (!r || !info) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ratings_info: NULL argument");
+    info[0] = r->B;
+    info[1] = r->W;
+    info[2] = r->G;
+    info[3] = r->max_cb_items;
+    info[4] = r->nnz;
+    info[5] = (int64_t)r->G * r->B;  // kernel launches per epoch
+    info[6] = r->max_bucket;
+    info[7] = r->packed_len;
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_perm(mfrec_ctx *ctx, const mfrec_ratings *r, int32_t *user_perm,
+                                  int32_t *item_perm)
+{
+    if (!ctx || !r) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_perm: NULL argument");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (user_perm) MF_CUDA(ctx, cudaMemcpy(user_perm, r->user_perm, (size_t)r->nu * 4, cudaMemcpyDeviceToHost));
+    if (item_perm) MF_CUDA(ctx, cudaMemcpy(item_perm, r->item_perm, (size_t)r->ni * 4, cudaMemcpyDeviceToHost));
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_order(mfrec_ctx *ctx, const mfrec_ratings *r, int64_t *order)
+{
+    if (!ctx || !r || !order) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_order: NULL argument");
+    if (!r->order)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_order: pack with opts.keep_order = 1");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    MF_CUDA(ctx, cudaMemcpy(order, r->order, (size_t)r->packed_len * 8, cudaMemcpyDeviceToHost));
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_offsets(mfrec_ctx *ctx, const mfrec_ratings *r, int64_t *offsets,
+                                     int32_t *counts)
+{
+    if (!ctx || !r) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_offsets: NULL argument");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (offsets)
+        MF_CUDA(ctx, cudaMemcpy(offsets, r->bucket_off, ((size_t)r->n_buckets + 1) * 8, cudaMemcpyDeviceToHost));
+    if (counts)
+        MF_CUDA(ctx, cudaMemcpy(counts, r->bucket_cnt, (size_t)r->n_buckets * 4, cudaMemcpyDeviceToHost));
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_packed(mfrec_ctx *ctx, const mfrec_ratings *r, void *out)
+{
+    if (!ctx || !r || !out) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_packed: NULL argument");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    MF_CUDA(ctx, cudaMemcpy(out, r->packed, (size_t)r->packed_len * sizeof(PackedRating), cudaMemcpyDeviceToHost));
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_slab_items(const mfrec_ratings *r, int32_t slab, int32_t *begin, int32_t *end)
+{
+    if (!r || slab < 0 || slab >= r->G || !begin || !end)
+        return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ratings_slab_items: bad argument");
+    *begin = r->h_col_start[(size_t)slab * r->B * r->W];
+    *end = r->h_col_start[(size_t)(slab + 1) * r->B * r->W];
+    return MFREC_OK;
+}

@@ -1,0 +1,331 @@
+// Context, error reporting, resident model and the boundary layout conversion
+// ([k][n] float64 host  <->  [n][kpad] float32 device, optionally row-permuted).
+#include <cstring>
+
+#include "common.cuh"
+
+static thread_local std::string g_tls_error;
+
+int mfrec_set_error(mfrec_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_tls_error = buf;
+    return code;
+}
+
+extern "C" int mfrec_abi_version(void) { return MFREC_B200_ABI_VERSION; }
+
+extern "C" const char *mfrec_last_error(const mfrec_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_tls_error.c_str();
+}
+
+extern "C" int mfrec_ctx_create(int device, mfrec_ctx **out)
+{
+    if (!out) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return mfrec_set_error(nullptr, MFREC_ERR_CUDA,
+                               "mfrec_ctx_create: no CUDA device (%s); this library has no CPU path",
+                               cudaGetErrorString(e));
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count)
+        return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ctx_create: device %d of %d",
+                               device, count);
+    cudaDeviceProp prop;
+    MF_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return mfrec_set_error(nullptr, MFREC_ERR_CUDA,
+                               "mfrec_ctx_create: device %d is sm_%d%d; kernels are built for sm_100a only",
+                               device, prop.major, prop.minor);
+    MF_CUDA(nullptr, cudaSetDevice(device));
+    mfrec_ctx *ctx = new (std::nothrow) mfrec_ctx();
+    if (!ctx) return mfrec_set_error(nullptr, MFREC_ERR_OOM, "mfrec_ctx_create: host OOM");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return mfrec_set_error(nullptr, MFREC_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return MFREC_OK;
+}
+
+extern "C" void mfrec_ctx_destroy(mfrec_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->se_scratch) cudaFree(ctx->se_scratch);
+    delete ctx;
+}
+
+extern "C" void *mfrec_ctx_stream(mfrec_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int mfrec_ctx_sync(mfrec_ctx *ctx)
+{
+    if (!ctx) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ctx_sync: NULL ctx");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFREC_OK;
+}
+
+extern "C" int64_t mfrec_ctx_launch_count(const mfrec_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------
+// Layout conversion kernels.  HBM-bound, one pass: reads are coalesced along n (the
+// contiguous axis of the reference's feature-major arrays), writes along k (the contiguous
+// axis of the device rows), through a padded 32x32 shared tile.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+factor_to_rows_kernel(const double *__restrict__ src_kn, int k, int kpad, int32_t n,
+                      const int32_t *__restrict__ perm, float *__restrict__ dst_nk)
+{
+    __shared__ float tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32;
+    const int f0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int f = f0 + ty + r * 8;
+        const int64_t j = j0 + tx;
+        float val = 0.f;
+        if (f < k && j < n) val = (float)src_kn[(int64_t)f * n + j];
+        tile[ty + r * 8][tx] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t j = j0 + ty + r * 8;
+        const int f = f0 + tx;
+        if (j < n && f < kpad) {
+            const int64_t row = perm ? perm[j] : j;
+            dst_nk[row * kpad + f] = tile[tx][ty + r * 8];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rows_to_factor_kernel(const float *__restrict__ src_nk, int k, int kpad, int32_t n,
+                      const int32_t *__restrict__ perm, double *__restrict__ dst_kn)
+{
+    __shared__ float tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32;
+    const int f0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t j = j0 + ty + r * 8;
+        const int f = f0 + tx;
+        float val = 0.f;
+        if (j < n && f < kpad) {
+            const int64_t row = perm ? perm[j] : j;
+            val = src_nk[row * kpad + f];
+        }
+        tile[ty + r * 8][tx] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int f = f0 + ty + r * 8;
+        const int64_t j = j0 + tx;
+        if (f < k && j < n) dst_kn[(int64_t)f * n + j] = (double)tile[tx][ty + r * 8];
+    }
+}
+
+__global__ void vec_to_dev_kernel(const double *__restrict__ src, int32_t n,
+                                  const int32_t *__restrict__ perm, float *__restrict__ dst)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[perm ? perm[j] : j] = (float)src[j];
+}
+
+__global__ void vec_from_dev_kernel(const float *__restrict__ src, int32_t n,
+                                    const int32_t *__restrict__ perm, double *__restrict__ dst)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[j] = (double)src[perm ? perm[j] : j];
+}
+
+int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
+                        const int32_t *perm_dev, float *dst_nk)
+{
+    if (n == 0) return MFREC_OK;
+    if (!host_kn) {
+        MF_CUDA(ctx, cudaMemsetAsync(dst_nk, 0, (size_t)n * kpad * sizeof(float), ctx->stream));
+        return MFREC_OK;
+    }
+    DevBuf<double> stage;
+    MF_CUDA(ctx, stage.alloc((size_t)k * n));
+    MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host_kn, (size_t)k * n * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
+    factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(stage.p, k, kpad, n, perm_dev, dst_nk);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFREC_OK;
+}
+
+int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,
+                          const int32_t *perm_dev, double *host_kn)
+{
+    if (n == 0 || !host_kn) return MFREC_OK;
+    DevBuf<double> stage;
+    MF_CUDA(ctx, stage.alloc((size_t)k * n));
+    dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
+    rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(src_nk, k, kpad, n, perm_dev, stage.p);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cudaMemcpyAsync(host_kn, stage.p, (size_t)k * n * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFREC_OK;
+}
+
+int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
+                     float *dst)
+{
+    if (n == 0) return MFREC_OK;
+    if (!host) {
+        MF_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)n * sizeof(float), ctx->stream));
+        return MFREC_OK;
+    }
+    DevBuf<double> stage;
+    MF_CUDA(ctx, stage.alloc((size_t)n));
+    MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host, (size_t)n * sizeof(double),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    vec_to_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(stage.p, n, perm_dev, dst);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFREC_OK;
+}
+
+int mfrec_download_vec(mfrec_ctx *ctx, const float *src, int32_t n, const int32_t *perm_dev,
+                       double *host)
+{
+    if (n == 0 || !host) return MFREC_OK;
+    DevBuf<double> stage;
+    MF_CUDA(ctx, stage.alloc((size_t)n));
+    vec_from_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(src, n, perm_dev, stage.p);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cudaMemcpyAsync(host, stage.p, (size_t)n * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MFREC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Resident model
+// ---------------------------------------------------------------------------------------
+extern "C" void mfrec_model_destroy(mfrec_model *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->Q);
+    cudaFree(m->ib);
+    cudaFree(m->P);
+    cudaFree(m->ub);
+    cudaFree(m->user_perm);
+    cudaFree(m->item_perm);
+    delete m;
+}
+
+extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, int k, int32_t ni,
+                                  int32_t nu, const double *u, const double *v,
+                                  const double *items_bias, const double *users_bias,
+                                  mfrec_model **out)
+{
+    if (!ctx || !out) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_model_create: NULL argument");
+    *out = nullptr;
+    if (k <= 0 || ni < 0 || nu < 0)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_model_create: k=%d ni=%d nu=%d", k, ni, nu);
+    const int kpad = mfrec_kpad(k);
+    if (kpad < 0)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_model_create: k=%d > 256 is not instantiated", k);
+    if (layout && (layout->ni != ni || layout->nu != nu))
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG,
+                               "mfrec_model_create: layout is %d x %d, model is %d x %d",
+                               layout->nu, layout->ni, nu, ni);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    mfrec_model *m = new (std::nothrow) mfrec_model();
+    if (!m) return mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_model_create: host OOM");
+    m->device = ctx->device;
+    m->k = k;
+    m->kpad = kpad;
+    m->ni = ni;
+    m->nu = nu;
+    int rc = MFREC_OK;
+    auto fail = [&](int code) {
+        mfrec_model_destroy(m);
+        return code;
+    };
+#define MF_M(call)                                                                        \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(mfrec_set_error(ctx, e__ == cudaErrorMemoryAllocation ? MFREC_ERR_OOM : MFREC_ERR_CUDA, \
+                                        "%s -> %s", #call, cudaGetErrorString(e__)));     \
+    } while (0)
+    // +64 floats of slack so vector loads of the last row never leave the allocation
+    MF_M(cudaMalloc((void **)&m->Q, ((size_t)ni * kpad + 64) * sizeof(float)));
+    MF_M(cudaMalloc((void **)&m->P, ((size_t)nu * kpad + 64) * sizeof(float)));
+    MF_M(cudaMalloc((void **)&m->ib, ((size_t)ni + 64) * sizeof(float)));
+    MF_M(cudaMalloc((void **)&m->ub, ((size_t)nu + 64) * sizeof(float)));
+    if (layout) {
+        MF_M(cudaMalloc((void **)&m->user_perm, ((size_t)nu + 1) * sizeof(int32_t)));
+        MF_M(cudaMalloc((void **)&m->item_perm, ((size_t)ni + 1) * sizeof(int32_t)));
+        MF_M(cudaMemcpyAsync(m->user_perm, layout->user_perm, (size_t)nu * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+        MF_M(cudaMemcpyAsync(m->item_perm, layout->item_perm, (size_t)ni * sizeof(int32_t),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+#undef MF_M
+    if ((rc = mfrec_upload_factor(ctx, u, k, kpad, ni, m->item_perm, m->Q)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_factor(ctx, v, k, kpad, nu, m->user_perm, m->P)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_vec(ctx, items_bias, ni, m->item_perm, m->ib)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_vec(ctx, users_bias, nu, m->user_perm, m->ub)) != MFREC_OK) return fail(rc);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess)
+        return fail(mfrec_set_error(ctx, MFREC_ERR_CUDA, "model upload: %s", cudaGetErrorString(e)));
+    *out = m;
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_model_read(mfrec_ctx *ctx, const mfrec_model *m, double *u, double *v,
+                                double *items_bias, double *users_bias)
+{
+    if (!ctx || !m) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_model_read: NULL argument");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    MF_TRY(mfrec_download_factor(ctx, m->Q, m->k, m->kpad, m->ni, m->item_perm, u));
+    MF_TRY(mfrec_download_factor(ctx, m->P, m->k, m->kpad, m->nu, m->user_perm, v));
+    MF_TRY(mfrec_download_vec(ctx, m->ib, m->ni, m->item_perm, items_bias));
+    MF_TRY(mfrec_download_vec(ctx, m->ub, m->nu, m->user_perm, users_bias));
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_model_device_ptrs(const mfrec_model *m, void *ptrs[4], int64_t dims[3])
+{
+    if (!m || !ptrs || !dims)
+        return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_model_device_ptrs: NULL argument");
+    ptrs[0] = m->Q;
+    ptrs[1] = m->ib;
+    ptrs[2] = m->P;
+    ptrs[3] = m->ub;
+    dims[0] = m->ni;
+    dims[1] = m->nu;
+    dims[2] = m->kpad;
+    return MFREC_OK;
+}

@@ -1,0 +1,582 @@
+// SGD update kernels for the all-k "KMF" loops of the reference
+// (mfrec/lib/kmf_train.pyx:195-277 train_linear_kernel, :103-189 train_logistic_kernel).
+//
+// Stratified schedule (MFREC_SCHED_STRATIFIED)
+// --------------------------------------------
+// Two updates commute iff they share neither the user row nor the item row.  pack.cu cuts the
+// rating matrix into B x B blocks (x G item slabs) and every block into W x W buckets.
+// One epoch = B kernel launches per slab ("sub-epochs").  In sub-epoch s, CTA rb owns
+//   row block rb  x  column block (rb + s) mod B            (a Latin square: no two CTAs share
+//                                                            a row block or a column block)
+// and inside the CTA, in phase p, warp w owns
+//   row group w   x  column group (w + p) mod W             (again a Latin square)
+// with a __syncthreads() between phases.  So at any instant all B*W warps of the grid work on
+// pairwise disjoint users and items: no atomics, no locks, deterministic for a given layout.
+// Any serial replay that visits (sub-epoch, CTA, phase, warp, bucket order) nested in that
+// order is an equivalent sequential SGD order; tests replay exactly that with the CPU oracle.
+//
+// Data movement per CTA
+//   * the column block's Q rows (contiguous in packed-id order) are pulled into shared memory
+//     once with cp.async.bulk (TMA, mbarrier complete_tx) and written back once;
+//   * each warp streams its bucket of 12-byte ratings through a private 2-stage shared-memory
+//     ring filled by cp.async.bulk, so the next chunk lands while the current one is consumed;
+//   * P rows are read with one coalesced 128-bit load per lane, prefetched D ratings ahead
+//     into registers (users inside a bucket are sorted, so the only hazard is "same user as
+//     the previous rating", served from registers), and written back with 128-bit stores;
+//   * the dot product is a 5-step warp-shuffle butterfly; all arithmetic is fp32, the epoch's
+//     sum of squared errors is accumulated in fp64.
+//
+// Sequential schedule (MFREC_SCHED_SEQUENTIAL): one thread, fp64, no FMA contraction, the
+// reference's exact order on the reference's own [k][n] layout.  Bit-exact with the reference
+// for the linear kernel; used for verification and for tiny fold-in calls.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kChunk = 128;   // ratings per TMA chunk (per warp, per stage)
+constexpr int kDepth = 8;     // P rows prefetched ahead, per warp
+static_assert(kChunk % kDepth == 0 && kChunk % 4 == 0, "chunking");
+
+struct SgdParams {
+    const PackedRating *packed;
+    const int64_t *bucket_off;
+    const int32_t *bucket_cnt;
+    const int32_t *col_start;
+    float *Q, *ib, *P, *ub;
+    double *se_part;  // [B] partial sums of this launch
+    int B, W, slab, s;
+    int tile_rows;    // shared-memory rows reserved for the Q tile
+    float lr, Ku, Ki, Kb;
+    int update_users, update_items;
+};
+
+// ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- per-lane row fragment: E floats, as NV vectors of V floats, interleaved over the warp --
+template <int E>
+struct Frag {
+    static constexpr int V = E >= 4 ? 4 : E;
+    static constexpr int NV = E / V;
+    float x[E];
+};
+
+template <int E>
+__device__ __forceinline__ void frag_load(Frag<E> &f, const float *row, int lane)
+{
+    constexpr int V = Frag<E>::V, NV = Frag<E>::NV;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        const float *p = row + (c * 32 + lane) * V;
+        if constexpr (V == 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(p);
+            f.x[c * 4 + 0] = t.x; f.x[c * 4 + 1] = t.y; f.x[c * 4 + 2] = t.z; f.x[c * 4 + 3] = t.w;
+        } else if constexpr (V == 2) {
+            const float2 t = *reinterpret_cast<const float2 *>(p);
+            f.x[0] = t.x; f.x[1] = t.y;
+        } else {
+            f.x[0] = *p;
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void frag_store(const Frag<E> &f, float *row, int lane)
+{
+    constexpr int V = Frag<E>::V, NV = Frag<E>::NV;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        float *p = row + (c * 32 + lane) * V;
+        if constexpr (V == 4)
+            *reinterpret_cast<float4 *>(p) = make_float4(f.x[c * 4], f.x[c * 4 + 1], f.x[c * 4 + 2], f.x[c * 4 + 3]);
+        else if constexpr (V == 2)
+            *reinterpret_cast<float2 *>(p) = make_float2(f.x[0], f.x[1]);
+        else
+            *p = f.x[0];
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// The stratified kernel.  grid = B CTAs, block = W warps.  E = kpad / 32 floats per lane.
+// ------------------------------------------------------------------------------------------
+template <int E, int KERNEL>
+__global__ void __launch_bounds__(512)
+sgd_block_kernel(const SgdParams prm)
+{
+    constexpr int KPAD = E * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int W = prm.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rb = blockIdx.x;
+    const int cbl = (rb + prm.s) % prm.B;
+    const int cbg = prm.slab * prm.B + cbl;
+    const int cs = prm.col_start[cbg * W];
+    const int nq = prm.col_start[(cbg + 1) * W] - cs;
+
+    // shared-memory carve-up
+    float *Qs = reinterpret_cast<float *>(smem_raw);
+    float *ibs = Qs + (size_t)prm.tile_rows * KPAD;
+    PackedRating *ring_all = reinterpret_cast<PackedRating *>(ibs + ((prm.tile_rows + 3) & ~3));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring_all + (size_t)W * 2 * kChunk);
+    int64_t *boff = reinterpret_cast<int64_t *>(bars + 1 + 2 * W);
+    int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W);
+    double *se_s = reinterpret_cast<double *>(bcnt + ((W * W + 1) & ~1));
+
+    PackedRating *ring = ring_all + (size_t)warp * 2 * kChunk;
+    uint64_t *tile_bar = bars;
+    uint64_t *my_bar = bars + 1 + 2 * warp;
+
+    if (threadIdx.x == 0) {
+        mbar_init(tile_bar, 1);
+        for (int i = 0; i < 2 * W; ++i) mbar_init(bars + 1 + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // this CTA's W*W bucket descriptors
+    const int64_t bucket_base = (((int64_t)prm.slab * prm.B + rb) * prm.B + cbl) * W * W;
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x) {
+        boff[i] = prm.bucket_off[bucket_base + i];
+        bcnt[i] = prm.bucket_cnt[bucket_base + i];
+    }
+    __syncthreads();
+
+    // Q tile: one elected thread issues the bulk copies, everyone waits on the mbarrier
+    if (threadIdx.x == 0 && nq > 0) {
+        const uint32_t total = (uint32_t)nq * KPAD * 4u;
+        mbar_expect_tx(tile_bar, total);
+        const char *src = reinterpret_cast<const char *>(prm.Q + (size_t)cs * KPAD);
+        char *dst = reinterpret_cast<char *>(Qs);
+        for (uint32_t o = 0; o < total; o += 32768u)
+            bulk_g2s(dst + o, src + o, min(32768u, total - o), tile_bar);
+    }
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) ibs[i] = prm.ib[cs + i];
+    if (nq > 0) mbar_wait(tile_bar, 0);
+    __syncthreads();
+
+    const float lr = prm.lr, Ku = prm.Ku, Ki = prm.Ki, Kb = prm.Kb;
+    const bool upd_u = prm.update_users != 0, upd_i = prm.update_items != 0;
+    uint32_t uses0 = 0, uses1 = 0;  // completed waits per ring stage (parity tracking)
+    double se = 0.0;                // fp64 total; fp32 partials of kDepth ratings feed it
+
+    for (int p = 0; p < W; ++p) {
+        const int64_t a = boff[p * W + warp];
+        const int n = bcnt[p * W + warp];
+        if (n > 0) {
+            const PackedRating *src = prm.packed + a;
+            const int nch = (n + kChunk - 1) / kChunk;
+            auto issue = [&](int j) {
+                if (lane == 0) {
+                    const int cnt = min(kChunk, n - j * kChunk);
+                    const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 12u;
+                    uint64_t *bar = my_bar + (j & 1);
+                    mbar_expect_tx(bar, bytes);
+                    bulk_g2s(ring + (j & 1) * kChunk, src + (size_t)j * kChunk, bytes, bar);
+                }
+            };
+            auto wait = [&](int j) {
+                if (j & 1) { mbar_wait(my_bar + 1, uses1 & 1); ++uses1; }
+                else       { mbar_wait(my_bar + 0, uses0 & 1); ++uses0; }
+            };
+            issue(0);
+            if (nch > 1) issue(1);
+            wait(0);
+
+            Frag<E> pre[kDepth];
+            float pre_b[kDepth];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                if (d < n) {
+                    const int up = ring[d].u;
+                    frag_load<E>(pre[d], prm.P + (size_t)up * KPAD, lane);
+                    pre_b[d] = (lane == 0) ? prm.ub[up] : 0.f;
+                }
+            }
+            Frag<E> cp, cq;          // current user row / item row (post-update values)
+            float cbu = 0.f, cbi = 0.f;
+            int prev_u = -1, prev_i = -1;
+
+            for (int tb = 0; tb < n; tb += kDepth) {
+                if (tb > 0 && (tb % kChunk) == 0) {
+                    __syncwarp();
+                    const int j = tb / kChunk;
+                    if (j + 1 < nch) issue(j + 1);
+                }
+                const int tp0 = tb + kDepth;
+                if (tp0 < n && (tp0 % kChunk) == 0) wait(tp0 / kChunk);
+                float se_f = 0.f;
+#pragma unroll
+                for (int d = 0; d < kDepth; ++d) {
+                    const int t = tb + d;
+                    if (t < n) {
+                        const PackedRating rt = ring[t % (2 * kChunk)];
+                        Frag<E> pu = pre[d];
+                        float bu = pre_b[d];
+                        const int tp = t + kDepth;
+                        if (tp < n) {
+                            const int up = ring[tp % (2 * kChunk)].u;
+                            frag_load<E>(pre[d], prm.P + (size_t)up * KPAD, lane);
+                            pre_b[d] = (lane == 0) ? prm.ub[up] : 0.f;
+                        }
+                        if (rt.u == prev_u) { pu = cp; bu = cbu; }
+                        Frag<E> qi;
+                        float bi;
+                        float *qrow = Qs + (size_t)(rt.i - cs) * KPAD;
+                        if (rt.i == prev_i) { qi = cq; bi = cbi; }
+                        else {
+                            frag_load<E>(qi, qrow, lane);
+                            bi = (lane == 0) ? ibs[rt.i - cs] : 0.f;
+                        }
+                        float part = 0.f;
+#pragma unroll
+                        for (int e = 0; e < E; ++e) part = fmaf(pu.x[e], qi.x[e], part);
+                        const float dot = warp_sum(part);
+                        // lane 0 owns the biases; broadcast their sum
+                        const float bsum = __shfl_sync(0xffffffffu, bi + bu, 0);
+                        const float s = bsum + dot;
+                        float err, grad;
+                        if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
+                            err = rt.r - s;
+                            grad = err;
+                        } else {
+                            const float sig = 1.f / (1.f + expf(-s));
+                            err = rt.r - (1.f + 4.f * sig);
+                            grad = err * sig * (1.f - sig) * 4.f;
+                        }
+                        se_f = fmaf(err, err, se_f);
+                        if (KERNEL == MFREC_KERNEL_LINEAR || upd_u) bu += lr * (grad - Kb * bu);
+                        if (KERNEL == MFREC_KERNEL_LINEAR || upd_i) bi += lr * (grad - Kb * bi);
+#pragma unroll
+                        for (int e = 0; e < E; ++e) {
+                            const float cf = pu.x[e], mf = qi.x[e];
+                            if (upd_i) qi.x[e] = mf + lr * (grad * cf - Ki * mf);
+                            if (upd_u) pu.x[e] = cf + lr * (grad * mf - Ku * cf);
+                        }
+                        cp = pu; cq = qi; cbu = bu; cbi = bi;
+                        prev_u = rt.u; prev_i = rt.i;
+                        frag_store<E>(qi, qrow, lane);
+                        frag_store<E>(pu, prm.P + (size_t)rt.u * KPAD, lane);
+                        if (lane == 0) {
+                            ibs[rt.i - cs] = bi;
+                            prm.ub[rt.u] = bu;
+                        }
+                    }
+                }
+                se += (double)se_f;
+            }
+            __syncwarp();  // ring reads done before the next bucket's copies land
+        }
+        __syncthreads();  // phase boundary: column groups change hands
+    }
+
+    // write the Q tile back
+    {
+        const int nvec = nq * KPAD / 4;
+        float4 *dst = reinterpret_cast<float4 *>(prm.Q + (size_t)cs * KPAD);
+        const float4 *srcv = reinterpret_cast<const float4 *>(Qs);
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.ib[cs + i] = ibs[i];
+    }
+    if (lane == 0) se_s[warp] = se;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < W; ++w) tot += se_s[w];
+        prm.se_part[rb] = tot;
+    }
+}
+
+// fixed-order sum of the per-CTA partials of one epoch
+__global__ void __launch_bounds__(1024) se_reduce_kernel(const double *__restrict__ part, int64_t n,
+                                                         double *__restrict__ out)
+{
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += part[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// Sequential schedule: the reference's loop verbatim (kmf_train.pyx:241-273), one thread,
+// fp64, round-to-nearest multiplies and adds kept separate (the reference build has no FMA).
+// ------------------------------------------------------------------------------------------
+__global__ void kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, double lr, double K_users,
+                                      double K_items, double K_bias, double *u, double *v,
+                                      const int32_t *idx, const double *ratings, int64_t nnz,
+                                      int64_t ni, int64_t nu, double *ib, double *ub,
+                                      int update_users, int update_items, double *rmse_out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int epoch = 0; epoch < nbr_epochs; ++epoch) {
+        double se = 0.0;
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int user = idx[2 * n], item = idx[2 * n + 1];
+            const double rating = ratings[n];
+            double s = __dadd_rn(__dadd_rn(0.0, ib[item]), ub[user]);
+            for (int f = 0; f < dim; ++f)
+                s = __dadd_rn(s, __dmul_rn(u[(int64_t)f * ni + item], v[(int64_t)f * nu + user]));
+            double err, grad;
+            if (kernel == MFREC_KERNEL_LINEAR) {
+                err = __dadd_rn(rating, -s);
+                grad = err;
+            } else {
+                const double sig = 1.0 / __dadd_rn(1.0, exp(-s));
+                const double p = __dadd_rn(1.0, __dmul_rn(sig, 4.0));
+                err = __dadd_rn(rating, -p);
+                grad = __dmul_rn(__dmul_rn(__dmul_rn(err, sig), __dadd_rn(1.0, -sig)), 4.0);
+            }
+            se = __dadd_rn(se, __dmul_rn(err, err));
+            if (kernel == MFREC_KERNEL_LINEAR || update_users)
+                ub[user] = __dadd_rn(ub[user], __dmul_rn(lr, __dadd_rn(grad, -__dmul_rn(K_bias, ub[user]))));
+            if (kernel == MFREC_KERNEL_LINEAR || update_items)
+                ib[item] = __dadd_rn(ib[item], __dmul_rn(lr, __dadd_rn(grad, -__dmul_rn(K_bias, ib[item]))));
+            for (int f = 0; f < dim; ++f) {
+                double *pu = &u[(int64_t)f * ni + item], *pv = &v[(int64_t)f * nu + user];
+                const double cf = *pv, mf = *pu;
+                if (update_items)
+                    *pu = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, cf), -__dmul_rn(K_items, mf))));
+                if (update_users)
+                    *pv = __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, mf), -__dmul_rn(K_users, cf))));
+            }
+        }
+        if (rmse_out) rmse_out[epoch] = sqrt(se / (double)nnz);
+    }
+}
+
+size_t sgd_smem_bytes(int tile_rows, int kpad, int W)
+{
+    size_t b = (size_t)tile_rows * kpad * 4;               // Q tile
+    b += (size_t)((tile_rows + 3) & ~3) * 4;               // item biases
+    b += (size_t)W * 2 * kChunk * sizeof(PackedRating);    // rating rings
+    b += (size_t)(1 + 2 * W) * 8;                          // mbarriers
+    b += (size_t)W * W * 8;                                // bucket offsets
+    b += (size_t)((W * W + 1) & ~1) * 4;                   // bucket counts
+    b += (size_t)W * 8;                                    // per-warp squared error
+    return b + 128;
+}
+
+template <int E>
+int launch_sgd(mfrec_ctx *ctx, int kernel, const SgdParams &prm, size_t smem)
+{
+    auto fn = kernel == MFREC_KERNEL_LINEAR ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR>
+                                            : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC>;
+    static size_t configured[2] = {0, 0};  // per instantiation (E) and kernel
+    if (configured[kernel] < smem) {
+        MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[kernel] = smem;
+    }
+    fn<<<prm.B, prm.W * 32, smem, ctx->stream>>>(prm);
+    MF_LAUNCH_CHECK(ctx);
+    return MFREC_OK;
+}
+
+}  // namespace
+
+extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_model *m, int kernel,
+                               double learning_rate, double K_users, double K_items, double K_bias,
+                               int update_users, int update_items, int32_t slab, double *sq_err_out)
+{
+    if (!ctx || !r || !m) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: NULL argument");
+    if (kernel != MFREC_KERNEL_LINEAR && kernel != MFREC_KERNEL_LOGISTIC)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: kernel=%d", kernel);
+    if (m->ni != r->ni || m->nu != r->nu || !m->user_perm)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: model was not created with this layout");
+    if (slab >= r->G) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: slab=%d of %d", slab, r->G);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int s_lo = slab < 0 ? 0 : slab, s_hi = slab < 0 ? r->G : slab + 1;
+    const int64_t nparts = (int64_t)(s_hi - s_lo) * r->B * r->B;
+    if (ctx->se_cap < (size_t)nparts) {
+        if (ctx->se_scratch) cudaFree(ctx->se_scratch);
+        ctx->se_scratch = nullptr;
+        ctx->se_cap = 0;
+        MF_CUDA(ctx, cudaMalloc((void **)&ctx->se_scratch, (size_t)nparts * 8));
+        ctx->se_cap = (size_t)nparts;
+    }
+    SgdParams prm;
+    prm.packed = r->packed;
+    prm.bucket_off = r->bucket_off;
+    prm.bucket_cnt = r->bucket_cnt;
+    prm.col_start = r->col_start;
+    prm.Q = m->Q; prm.ib = m->ib; prm.P = m->P; prm.ub = m->ub;
+    prm.B = r->B; prm.W = r->W;
+    prm.tile_rows = r->max_cb_items;
+    prm.lr = (float)learning_rate; prm.Ku = (float)K_users; prm.Ki = (float)K_items; prm.Kb = (float)K_bias;
+    prm.update_users = update_users; prm.update_items = update_items;
+    const size_t smem = sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
+    if (smem > ctx->smem_optin)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                               "mfrec_sgd_epoch: Q tile of %d rows x %d needs %zu B shared memory (> %zu); pack with more row_blocks",
+                               r->max_cb_items, m->kpad, smem, ctx->smem_optin);
+    int64_t part = 0;
+    for (int g = s_lo; g < s_hi; ++g) {
+        for (int s = 0; s < r->B; ++s) {
+            prm.slab = g;
+            prm.s = s;
+            prm.se_part = ctx->se_scratch + part;
+            part += r->B;
+            int rc;
+            switch (m->kpad) {
+            case 32: rc = launch_sgd<1>(ctx, kernel, prm, smem); break;
+            case 64: rc = launch_sgd<2>(ctx, kernel, prm, smem); break;
+            case 128: rc = launch_sgd<4>(ctx, kernel, prm, smem); break;
+            case 256: rc = launch_sgd<8>(ctx, kernel, prm, smem); break;
+            default: rc = mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", m->kpad);
+            }
+            MF_TRY(rc);
+        }
+    }
+    if (sq_err_out) {
+        se_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->se_scratch, nparts, sq_err_out);
+        MF_LAUNCH_CHECK(ctx);
+    }
+    return MFREC_OK;
+}
+
+static int train_kmf_sequential(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k, double lr,
+                                double K_users, double K_items, double K_bias, double *u, double *v,
+                                const int32_t *idx, const double *ratings, int64_t nnz, int32_t ni,
+                                int32_t nu, double *ib, double *ub, int update_users,
+                                int update_items, double *rmse_per_epoch)
+{
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> du, dv, dr, dib, dub, drm;
+    DevBuf<int32_t> didx;
+    MF_CUDA(ctx, du.alloc((size_t)k * ni));
+    MF_CUDA(ctx, dv.alloc((size_t)k * nu));
+    MF_CUDA(ctx, dr.alloc((size_t)nnz));
+    MF_CUDA(ctx, didx.alloc((size_t)nnz * 2));
+    MF_CUDA(ctx, dib.alloc(ni));
+    MF_CUDA(ctx, dub.alloc(nu));
+    MF_CUDA(ctx, drm.alloc(nbr_epochs > 0 ? nbr_epochs : 1));
+    MF_CUDA(ctx, cudaMemcpyAsync(du.p, u, (size_t)k * ni * 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(dv.p, v, (size_t)k * nu * 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(dr.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(didx.p, idx, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(dib.p, ib, (size_t)ni * 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(dub.p, ub, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
+    kmf_sequential_kernel<<<1, 1, 0, st>>>(kernel, nbr_epochs, k, lr, K_users, K_items, K_bias, du.p,
+                                           dv.p, didx.p, dr.p, nnz, ni, nu, dib.p, dub.p,
+                                           update_users, update_items, drm.p);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cudaMemcpyAsync(u, du.p, (size_t)k * ni * 8, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(v, dv.p, (size_t)k * nu * 8, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(ib, dib.p, (size_t)ni * 8, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(ub, dub.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, st));
+    if (rmse_per_epoch && nbr_epochs > 0)
+        MF_CUDA(ctx, cudaMemcpyAsync(rmse_per_epoch, drm.p, (size_t)nbr_epochs * 8, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaStreamSynchronize(st));
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k, double learning_rate,
+                               double K_users, double K_items, double K_bias, double *u, double *v,
+                               const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                               int32_t ni, int32_t nu, double *items_bias, double *users_bias,
+                               int update_users, int update_items, const mfrec_opts *opts,
+                               double *rmse_per_epoch)
+{
+    if (!ctx) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_train_kmf: NULL ctx");
+    if (!u || !v || !items_bias || !users_bias || (nnz > 0 && (!ratings_index || !ratings)))
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_train_kmf: NULL array");
+    if (kernel != MFREC_KERNEL_LINEAR && kernel != MFREC_KERNEL_LOGISTIC)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_train_kmf: kernel=%d", kernel);
+    if (k <= 0 || ni <= 0 || nu <= 0 || nnz < 0 || nbr_epochs < 0)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_train_kmf: k=%d ni=%d nu=%d nnz=%lld epochs=%d",
+                               k, ni, nu, (long long)nnz, nbr_epochs);
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nbr_epochs == 0) return MFREC_OK;
+    if (nnz == 0) {
+        // the reference divides 0/0 -> rmse = NaN and leaves the model untouched
+        if (rmse_per_epoch)
+            for (int e = 0; e < nbr_epochs; ++e) rmse_per_epoch[e] = NAN;
+        return MFREC_OK;
+    }
+    if (opts && opts->schedule == MFREC_SCHED_SEQUENTIAL) {
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int32_t a = ratings_index[2 * n], b = ratings_index[2 * n + 1];
+            if (a < 0 || a >= nu || b < 0 || b >= ni)
+                return mfrec_set_error(ctx, MFREC_ERR_INDEX, "mfrec_train_kmf: rating %lld has (user,item)=(%d,%d)",
+                                       (long long)n, a, b);
+        }
+        return train_kmf_sequential(ctx, kernel, nbr_epochs, k, learning_rate, K_users, K_items, K_bias,
+                                    u, v, ratings_index, ratings, nnz, ni, nu, items_bias, users_bias,
+                                    update_users, update_items, rmse_per_epoch);
+    }
+    if (mfrec_kpad(k) < 0)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_train_kmf: k=%d > 256 is not instantiated", k);
+    mfrec_opts o;
+    if (opts) o = *opts; else memset(&o, 0, sizeof(o));
+    o.n_slabs = 1;
+    if (o.k_hint == 0) o.k_hint = k;
+    mfrec_ratings *R = nullptr;
+    mfrec_model *M = nullptr;
+    MF_TRY(mfrec_ratings_pack(ctx, ratings_index, ratings, 0, 0, nnz, ni, nu, nullptr, &o, &R));
+    int rc = mfrec_model_create(ctx, R, k, ni, nu, u, v, items_bias, users_bias, &M);
+    DevBuf<double> d_se;
+    if (rc == MFREC_OK && d_se.alloc(nbr_epochs) != cudaSuccess)
+        rc = mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_train_kmf: device OOM");
+    for (int e = 0; rc == MFREC_OK && e < nbr_epochs; ++e)
+        rc = mfrec_sgd_epoch(ctx, R, M, kernel, learning_rate, K_users, K_items, K_bias, update_users,
+                             update_items, -1, d_se.p + e);
+    if (rc == MFREC_OK) {
+        std::vector<double> h_se(nbr_epochs);
+        cudaError_t ce = cudaMemcpyAsync(h_se.data(), d_se.p, (size_t)nbr_epochs * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) rc = mfrec_set_error(ctx, MFREC_ERR_CUDA, "mfrec_train_kmf: %s", cudaGetErrorString(ce));
+        else if (rmse_per_epoch)
+            for (int e = 0; e < nbr_epochs; ++e) rmse_per_epoch[e] = sqrt(h_se[e] / (double)nnz);
+    }
+    if (rc == MFREC_OK) rc = mfrec_model_read(ctx, M, u, v, items_bias, users_bias);
+    mfrec_model_destroy(M);
+    mfrec_ratings_destroy(R);
+    return rc;
+}
