@@ -170,6 +170,18 @@ def run_native(args):
                         nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
                         workers=args.workers)
     M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
+    layout_desc = ("stratified B=%d W=%d launches/epoch=%d max_bucket=%d widest_column_block=%d items"
+                   % (R.B, R.W, R.launches_per_epoch, R.max_bucket, R.max_cb_items))
+    # schedule balance: the serial chain of one epoch = sum over launches of the slowest CTA,
+    # a CTA = sum over phases of its fullest bucket; ideal = nnz / (B * W)
+    _, cnt = R.offsets()
+    c4 = cnt.reshape(R.G, R.B, R.B, R.W, R.W).astype(np.int64)   # [g, rb, cb, w, phase]
+    cta = c4.max(axis=3).sum(axis=3)                              # [g, rb, cb]
+    rbs = np.arange(R.B)
+    crit = sum(int(cta[g, rbs, (rbs + s) % R.B].max()) for g in range(R.G) for s in range(R.B))
+    balance = {"critical_path_ratings": crit, "ideal": nnz / float(R.B * R.W),
+               "efficiency": nnz / float(R.B * R.W) / max(crit, 1)}
+    del cnt, c4, cta
     se = torch.zeros(args.steps + args.warmup, device=dev, dtype=torch.float64)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     launches0 = ctx.launch_count
@@ -249,7 +261,7 @@ def run_native(args):
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "%s-shaped %dx%d nnz=%d k=%d (BASELINE configs[2])" % (args.workload, nu, ni, nnz, k),
-                      "kernel": "train_linear_kernel", "schedule": "stratified B=%d W=%d" % (R_B_W[0], R_B_W[1]) if False else None,
+                      "kernel": "train_linear_kernel", "schedule": layout_desc, "balance": balance,
                       "l2": "inputs (1.2 GB ratings + 255 MB factors) exceed the 126 MB L2",
                       "hyper": HP},
            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,

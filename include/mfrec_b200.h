@@ -178,7 +178,7 @@ int mfrec_ratings_perm(mfrec_ctx *ctx, const mfrec_ratings *r, int32_t *user_per
 /* order int64 [packed_len]: input index of the rating stored at each packed position, -1 for
  * alignment padding (needs opts.keep_order at pack time).  packed_len = info[7]. */
 int mfrec_ratings_order(mfrec_ctx *ctx, const mfrec_ratings *r, int64_t *order);
-/* Buckets in storage order (slab, row block, column block, phase, worker):
+/* Buckets in storage order (slab, row block, column block, worker, phase):
  * offsets int64 [n_buckets + 1] = first packed position, counts int32 [n_buckets];
  * n_buckets = n_slabs * B * B * W * W.  A one-thread replay that walks
  * slab, sub-epoch s, row block rb (column block (rb + s) mod B), phase, worker, bucket order

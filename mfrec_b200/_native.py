@@ -346,10 +346,11 @@ class Ratings(object):
             for s in range(B):
                 for rb in range(B):
                     cb = (rb + s) % B
-                    for q in range(W * W):
-                        a, n = off[g, rb, cb, q], cnt[g, rb, cb, q]
-                        if n:
-                            out.append(order[a:a + n])
+                    for ph in range(W):
+                        for w in range(W):   # buckets are stored worker-major: index w * W + phase
+                            a, n = off[g, rb, cb, w * W + ph], cnt[g, rb, cb, w * W + ph]
+                            if n:
+                                out.append(order[a:a + n])
         return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
 
 

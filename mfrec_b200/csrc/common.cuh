@@ -131,7 +131,10 @@ static inline int mfrec_kpad(int k)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// layout.cu
+// sgd.cu
+size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W);
+
+// runtime.cu
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
                         const int32_t *perm_dev, float *dst_nk);
 int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,

@@ -9,8 +9,9 @@
 //   items  -> G slabs x B column blocks x W column groups
 //   bucket(slab g, row block rb, column block cb, phase p, worker w) holds the ratings of
 //   row group (rb, w) x column group (cb, (w + p) mod W), sorted by (user, item).
-//   Buckets are stored in (g, rb, cb, p, w) order, each starting on a 16-byte boundary so a
-//   CTA can stream them with cp.async.bulk.
+//   Buckets are stored in (g, rb, cb, w, p) order -- worker-major, so the W buckets one warp
+//   walks through are one contiguous stream -- each starting on a 16-byte boundary so the
+//   warp can pull the stream through shared memory with cp.async.bulk.
 //
 // Users and items are relabelled ("packed ids") so each group is a contiguous id range; the
 // factor matrices live in HBM in packed-id order, which makes every column block's Q tile one
@@ -70,7 +71,7 @@ __global__ void key_kernel(const int32_t *__restrict__ idx, int64_t nnz,
         const int slab = cbg / kl.B, cbl = cbg % kl.B;
         const int p = (wc - wr + kl.W) % kl.W;
         const uint64_t bucket =
-            ((((uint64_t)slab * kl.B + rb) * kl.B + cbl) * kl.W + p) * kl.W + wr;
+            ((((uint64_t)slab * kl.B + rb) * kl.B + cbl) * kl.W + wr) * kl.W + p;
         keys[n] = (bucket << (kl.bits_u + kl.bits_i)) |
                   ((uint64_t)(uint32_t)user_perm[ui.x] << kl.bits_i) |
                   (uint64_t)(uint32_t)item_perm[ui.y];
@@ -292,7 +293,6 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     R->G = G;
     R->W = W;
     std::vector<int32_t> ug, up, ig, ip;
-    const size_t ring_bytes = (size_t)W * 2 * 128 * sizeof(PackedRating) + 256;
     for (;;) {
         lpt_partition(h_deg_u, B, W, seed, ug, up, R->h_row_start);
         lpt_partition(h_deg_i, G * B, W, seed ^ 0x5bd1e995u, ig, ip, R->h_col_start);
@@ -302,7 +302,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         R->max_cb_items = widest;
         // the SGD kernel keeps one column block of Q (kpad floats per row) in shared memory;
         // grow B until the widest block fits
-        const size_t need = (size_t)widest * (kpad_hint + 1) * 4 + ring_bytes;
+        const size_t need = mfrec_sgd_smem_bytes(widest, kpad_hint, W);
         if (need <= ctx->smem_optin || widest <= 1 || (opts && opts->row_blocks > 0)) break;
         B *= 2;
     }

@@ -18,11 +18,12 @@
 // Data movement per CTA
 //   * the column block's Q rows (contiguous in packed-id order) are pulled into shared memory
 //     once with cp.async.bulk (TMA, mbarrier complete_tx) and written back once;
-//   * each warp streams its bucket of 12-byte ratings through a private 2-stage shared-memory
-//     ring filled by cp.async.bulk, so the next chunk lands while the current one is consumed;
-//   * P rows are read with one coalesced 128-bit load per lane, prefetched D ratings ahead
-//     into registers (users inside a bucket are sorted, so the only hazard is "same user as
-//     the previous rating", served from registers), and written back with 128-bit stores;
+//   * each warp's W buckets are stored back to back, so the warp streams ONE contiguous run of
+//     12-byte ratings through a private 4-stage shared-memory ring filled by cp.async.bulk;
+//   * P rows are fetched with cp.async (16 bytes per lane, coalesced 512 B per row at k = 128)
+//     into an 8-deep shared-memory ring, 8 ratings ahead of the consumer and across phase
+//     boundaries; they are tracked by cp.async groups, not by the register scoreboard, so a
+//     wait never stalls on the newest request; updated rows go back with 128-bit stores;
 //   * the dot product is a 5-step warp-shuffle butterfly; all arithmetic is fp32, the epoch's
 //     sum of squared errors is accumulated in fp64.
 //
@@ -35,9 +36,12 @@
 
 namespace {
 
-constexpr int kChunk = 128;   // ratings per TMA chunk (per warp, per stage)
-constexpr int kDepth = 8;     // P rows prefetched ahead, per warp
-static_assert(kChunk % kDepth == 0 && kChunk % 4 == 0, "chunking");
+constexpr int kChunk = 64;    // ratings per TMA chunk
+constexpr int kStages = 4;    // chunks in flight per warp (ring of kStages * kChunk ratings)
+constexpr int kDepth = 8;     // P rows in flight per warp (cp.async ring)
+constexpr int kRing = kChunk * kStages;
+static_assert(kChunk % 4 == 0, "chunks must be 16-byte multiples");
+static_assert(4 * kDepth <= kChunk, "the prefetch cursor may run at most one chunk ahead");
 
 struct SgdParams {
     const PackedRating *packed;
@@ -52,7 +56,7 @@ struct SgdParams {
     int update_users, update_items;
 };
 
-// ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) ----------------------
+// ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) + cp.async ------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -90,6 +94,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src_gmem)
+{
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- per-lane row fragment: E floats, as NV vectors of V floats, interleaved over the warp --
 template <int E>
@@ -134,6 +149,16 @@ __device__ __forceinline__ void frag_store(const Frag<E> &f, float *row, int lan
     }
 }
 
+// asynchronous global -> shared copy of one row, same lane <-> column mapping as frag_load
+template <int E>
+__device__ __forceinline__ void row_cp_async(float *dst_row, const float *src_row, int lane)
+{
+    constexpr int V = Frag<E>::V, NV = Frag<E>::NV;
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+        cp_async<V * 4>(dst_row + (c * 32 + lane) * V, src_row + (c * 32 + lane) * V);
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
@@ -143,6 +168,19 @@ __device__ __forceinline__ float warp_sum(float v)
 
 // ------------------------------------------------------------------------------------------
 // The stratified kernel.  grid = B CTAs, block = W warps.  E = kpad / 32 floats per lane.
+//
+// Every warp walks ONE contiguous stream of packed ratings (its W buckets, stored
+// back to back) with three cursors:
+//   load cursor     : cp.async.bulk chunks of kChunk ratings into a kStages-deep ring
+//   prefetch cursor : kDepth ratings ahead of the consumer, cp.async of the P row (and user
+//                     bias) of each upcoming rating into a kDepth-deep shared-memory ring;
+//                     P rows of a row group belong to this warp for the whole launch, so the
+//                     cursor may run across phase boundaries
+//   consume cursor  : the update itself; __syncthreads() at every bucket (= phase) end
+// Stale-prefetch hazard: the row of rating x is fetched while ratings x-kDepth .. x-1 are still
+// being applied.  Inside a bucket equal users are adjacent (sorted) and are served from
+// registers; across a bucket boundary a lane-distributed history of the last kDepth users
+// detects the rare repeat and re-reads the row from global memory.
 // ------------------------------------------------------------------------------------------
 template <int E, int KERNEL>
 __global__ void __launch_bounds__(512)
@@ -158,29 +196,33 @@ sgd_block_kernel(const SgdParams prm)
     const int cs = prm.col_start[cbg * W];
     const int nq = prm.col_start[(cbg + 1) * W] - cs;
 
-    // shared-memory carve-up
+    // shared-memory carve-up (every section is a multiple of 16 bytes)
     float *Qs = reinterpret_cast<float *>(smem_raw);
     float *ibs = Qs + (size_t)prm.tile_rows * KPAD;
-    PackedRating *ring_all = reinterpret_cast<PackedRating *>(ibs + ((prm.tile_rows + 3) & ~3));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring_all + (size_t)W * 2 * kChunk);
-    int64_t *boff = reinterpret_cast<int64_t *>(bars + 1 + 2 * W);
-    int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W);
+    float *prow_all = ibs + ((prm.tile_rows + 3) & ~3);
+    float *pbias_all = prow_all + (size_t)W * kDepth * KPAD;
+    PackedRating *ring_all = reinterpret_cast<PackedRating *>(pbias_all + (size_t)W * kDepth);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring_all + (size_t)W * kRing);
+    int64_t *boff = reinterpret_cast<int64_t *>(bars + 1 + kStages * W);
+    int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
     double *se_s = reinterpret_cast<double *>(bcnt + ((W * W + 1) & ~1));
 
-    PackedRating *ring = ring_all + (size_t)warp * 2 * kChunk;
+    float *prow = prow_all + (size_t)warp * kDepth * KPAD;
+    float *pbias = pbias_all + warp * kDepth;
+    PackedRating *ring = ring_all + (size_t)warp * kRing;
     uint64_t *tile_bar = bars;
-    uint64_t *my_bar = bars + 1 + 2 * warp;
+    uint64_t *my_bar = bars + 1 + kStages * warp;
 
     if (threadIdx.x == 0) {
         mbar_init(tile_bar, 1);
-        for (int i = 0; i < 2 * W; ++i) mbar_init(bars + 1 + i, 1);
+        for (int i = 0; i < kStages * W; ++i) mbar_init(bars + 1 + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // this CTA's W*W bucket descriptors
+    // this CTA's W*W bucket descriptors (worker-major: index w * W + phase) + end sentinel
     const int64_t bucket_base = (((int64_t)prm.slab * prm.B + rb) * prm.B + cbl) * W * W;
-    for (int i = threadIdx.x; i < W * W; i += blockDim.x) {
+    for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
         boff[i] = prm.bucket_off[bucket_base + i];
-        bcnt[i] = prm.bucket_cnt[bucket_base + i];
+        if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
     }
     __syncthreads();
 
@@ -194,124 +236,150 @@ sgd_block_kernel(const SgdParams prm)
             bulk_g2s(dst + o, src + o, min(32768u, total - o), tile_bar);
     }
     for (int i = threadIdx.x; i < nq; i += blockDim.x) ibs[i] = prm.ib[cs + i];
+
+    // ---- this warp's stream ---------------------------------------------------------------
+    const int64_t S0 = boff[warp * W];
+    const uint32_t slen = (uint32_t)(boff[warp * W + W] - S0);   // multiple of 4 (padded buckets)
+    const uint32_t nchunks = (slen + kChunk - 1) / kChunk;
+    const PackedRating *stream = prm.packed + S0;
+    const int32_t *cnt_w = bcnt + warp * W;
+    const int64_t *off_w = boff + warp * W;
+    uint32_t issued = 0;
+
+    auto issue_chunk = [&](uint32_t c) {
+        if (lane == 0) {
+            const uint32_t cnt = min((uint32_t)kChunk, slen - c * kChunk);
+            uint64_t *bar = my_bar + (c % kStages);
+            mbar_expect_tx(bar, cnt * 12u);
+            bulk_g2s(ring + (c % kStages) * kChunk, stream + (size_t)c * kChunk, cnt * 12u, bar);
+        }
+    };
+    while (issued < nchunks && issued < (uint32_t)kStages) issue_chunk(issued++);
+
+    // Prefetch cursor: walks stream POSITIONS (padding entries included: they name packed user 0,
+    // a valid row, and are never consumed), one cp.async group per position, so that group
+    // index == position and cp.async.wait_group<kDepth-1> at position x guarantees row x landed
+    // once the cursor stands at x + kDepth.  Positions past the end commit empty groups.
+    uint32_t pfpos = 0;
+    auto prefetch_to = [&](uint32_t target) {
+        while (pfpos < target) {
+            if (pfpos < slen) {
+                if ((pfpos % kChunk) == 0) {   // first touch of a chunk: wait for its bulk copy
+                    const uint32_t c = pfpos / kChunk;
+                    mbar_wait(my_bar + (c % kStages), (c / kStages) & 1u);
+                }
+                const int up = ring[pfpos % kRing].u;
+                const uint32_t slot = pfpos % kDepth;
+                row_cp_async<E>(prow + slot * KPAD, prm.P + (size_t)up * KPAD, lane);
+                if (lane == 0) cp_async<4>(pbias + slot, prm.ub + up);
+            }
+            cp_async_commit();
+            ++pfpos;
+        }
+    };
+    prefetch_to(kDepth);
+
     if (nq > 0) mbar_wait(tile_bar, 0);
     __syncthreads();
 
-    const float lr = prm.lr, Ku = prm.Ku, Ki = prm.Ki, Kb = prm.Kb;
+    const float lr = prm.lr, Kb = prm.Kb;
     const bool upd_u = prm.update_users != 0, upd_i = prm.update_items != 0;
-    uint32_t uses0 = 0, uses1 = 0;  // completed waits per ring stage (parity tracking)
-    double se = 0.0;                // fp64 total; fp32 partials of kDepth ratings feed it
+    // q' = q + lr (g p - Ki q) = (1 - lr Ki) q + (lr g) p, likewise for p (frozen side: a = 1, gl = 0)
+    const float a_i = upd_i ? 1.f - prm.lr * prm.Ki : 1.f;
+    const float a_u = upd_u ? 1.f - prm.lr * prm.Ku : 1.f;
+    const float a_b = 1.f - lr * Kb;
+    const bool upd_bu = (KERNEL == MFREC_KERNEL_LINEAR) || upd_u;
+    const bool upd_bi = (KERNEL == MFREC_KERNEL_LINEAR) || upd_i;
+    double se = 0.0;       // fp64 total of fp32 per-bucket partials
+    Frag<E> cp, cq;        // current user row / item row (post-update values)
+#pragma unroll
+    for (int e = 0; e < E; ++e) { cp.x[e] = 0.f; cq.x[e] = 0.f; }
+    float cbu = 0.f, cbi = 0.f;
+    int prev_u = -1, prev_i = -1, hist = -1;
+    uint32_t cons_chunk = 0;
 
     for (int p = 0; p < W; ++p) {
-        const int64_t a = boff[p * W + warp];
-        const int n = bcnt[p * W + warp];
-        if (n > 0) {
-            const PackedRating *src = prm.packed + a;
-            const int nch = (n + kChunk - 1) / kChunk;
-            auto issue = [&](int j) {
-                if (lane == 0) {
-                    const int cnt = min(kChunk, n - j * kChunk);
-                    const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 12u;
-                    uint64_t *bar = my_bar + (j & 1);
-                    mbar_expect_tx(bar, bytes);
-                    bulk_g2s(ring + (j & 1) * kChunk, src + (size_t)j * kChunk, bytes, bar);
-                }
-            };
-            auto wait = [&](int j) {
-                if (j & 1) { mbar_wait(my_bar + 1, uses1 & 1); ++uses1; }
-                else       { mbar_wait(my_bar + 0, uses0 & 1); ++uses0; }
-            };
-            issue(0);
-            if (nch > 1) issue(1);
-            wait(0);
-
-            Frag<E> pre[kDepth];
-            float pre_b[kDepth];
-#pragma unroll
-            for (int d = 0; d < kDepth; ++d) {
-                if (d < n) {
-                    const int up = ring[d].u;
-                    frag_load<E>(pre[d], prm.P + (size_t)up * KPAD, lane);
-                    pre_b[d] = (lane == 0) ? prm.ub[up] : 0.f;
-                }
+        const uint32_t n = (uint32_t)cnt_w[p];
+        const uint32_t rel0 = (uint32_t)(off_w[p] - S0);
+        float se_f = 0.f;
+        PackedRating rt_next;
+        if (n > 0) rt_next = ring[rel0 % kRing];
+#pragma unroll 1
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t rel = rel0 + i;
+            const PackedRating rt = rt_next;
+            if (rel / kChunk != cons_chunk) {
+                cons_chunk = rel / kChunk;   // every earlier chunk's stage is free again
+                __syncwarp();
+                while (issued < nchunks && issued < cons_chunk + kStages) issue_chunk(issued++);
             }
-            Frag<E> cp, cq;          // current user row / item row (post-update values)
-            float cbu = 0.f, cbi = 0.f;
-            int prev_u = -1, prev_i = -1;
-
-            for (int tb = 0; tb < n; tb += kDepth) {
-                if (tb > 0 && (tb % kChunk) == 0) {
-                    __syncwarp();
-                    const int j = tb / kChunk;
-                    if (j + 1 < nch) issue(j + 1);
-                }
-                const int tp0 = tb + kDepth;
-                if (tp0 < n && (tp0 % kChunk) == 0) wait(tp0 / kChunk);
-                float se_f = 0.f;
-#pragma unroll
-                for (int d = 0; d < kDepth; ++d) {
-                    const int t = tb + d;
-                    if (t < n) {
-                        const PackedRating rt = ring[t % (2 * kChunk)];
-                        Frag<E> pu = pre[d];
-                        float bu = pre_b[d];
-                        const int tp = t + kDepth;
-                        if (tp < n) {
-                            const int up = ring[tp % (2 * kChunk)].u;
-                            frag_load<E>(pre[d], prm.P + (size_t)up * KPAD, lane);
-                            pre_b[d] = (lane == 0) ? prm.ub[up] : 0.f;
-                        }
-                        if (rt.u == prev_u) { pu = cp; bu = cbu; }
-                        Frag<E> qi;
-                        float bi;
-                        float *qrow = Qs + (size_t)(rt.i - cs) * KPAD;
-                        if (rt.i == prev_i) { qi = cq; bi = cbi; }
-                        else {
-                            frag_load<E>(qi, qrow, lane);
-                            bi = (lane == 0) ? ibs[rt.i - cs] : 0.f;
-                        }
-                        float part = 0.f;
-#pragma unroll
-                        for (int e = 0; e < E; ++e) part = fmaf(pu.x[e], qi.x[e], part);
-                        const float dot = warp_sum(part);
-                        // lane 0 owns the biases; broadcast their sum
-                        const float bsum = __shfl_sync(0xffffffffu, bi + bu, 0);
-                        const float s = bsum + dot;
-                        float err, grad;
-                        if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
-                            err = rt.r - s;
-                            grad = err;
-                        } else {
-                            const float sig = 1.f / (1.f + expf(-s));
-                            err = rt.r - (1.f + 4.f * sig);
-                            grad = err * sig * (1.f - sig) * 4.f;
-                        }
-                        se_f = fmaf(err, err, se_f);
-                        if (KERNEL == MFREC_KERNEL_LINEAR || upd_u) bu += lr * (grad - Kb * bu);
-                        if (KERNEL == MFREC_KERNEL_LINEAR || upd_i) bi += lr * (grad - Kb * bi);
-#pragma unroll
-                        for (int e = 0; e < E; ++e) {
-                            const float cf = pu.x[e], mf = qi.x[e];
-                            if (upd_i) qi.x[e] = mf + lr * (grad * cf - Ki * mf);
-                            if (upd_u) pu.x[e] = cf + lr * (grad * mf - Ku * cf);
-                        }
-                        cp = pu; cq = qi; cbu = bu; cbi = bi;
-                        prev_u = rt.u; prev_i = rt.i;
-                        frag_store<E>(qi, qrow, lane);
-                        frag_store<E>(pu, prm.P + (size_t)rt.u * KPAD, lane);
-                        if (lane == 0) {
-                            ibs[rt.i - cs] = bi;
-                            prm.ub[rt.u] = bu;
-                        }
-                    }
-                }
-                se += (double)se_f;
+            prefetch_to(rel + kDepth);
+            cp_async_wait<kDepth - 1>();
+            // next rating of this bucket (garbage past the end, never used)
+            rt_next = ring[(rel + 1) % kRing];
+            const bool last = (i + 1 == n);
+            const uint32_t slot = rel % kDepth;
+            Frag<E> pu, qi;
+            frag_load<E>(pu, prow + slot * KPAD, lane);
+            float bu = (lane == 0) ? pbias[slot] : 0.f;   // lane 0 owns both biases
+            float *qrow = Qs + (size_t)(rt.i - cs) * KPAD;
+            frag_load<E>(qi, qrow, lane);
+            float bi = (lane == 0) ? ibs[rt.i - cs] : 0.f;
+            const bool same_u = (rt.u == prev_u), same_i = (rt.i == prev_i);
+            if (__any_sync(0xffffffffu, hist == rt.u) && !same_u) {
+                // the row was updated after its prefetch was issued (user repeats across a bucket
+                // boundary within the prefetch window): re-read it from global memory
+                frag_load<E>(pu, prm.P + (size_t)rt.u * KPAD, lane);
+                bu = (lane == 0) ? prm.ub[rt.u] : 0.f;
             }
-            __syncwarp();  // ring reads done before the next bucket's copies land
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                pu.x[e] = same_u ? cp.x[e] : pu.x[e];
+                qi.x[e] = same_i ? cq.x[e] : qi.x[e];
+            }
+            bu = same_u ? cbu : bu;
+            bi = same_i ? cbi : bi;
+            const float bsum = __shfl_sync(0xffffffffu, bi + bu, 0);
+            float part = 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) part = fmaf(pu.x[e], qi.x[e], part);
+            const float s = warp_sum(part) + bsum;
+            float err, grad;
+            if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
+                err = rt.r - s;
+                grad = err;
+            } else {
+                const float sig = 1.f / (1.f + expf(-s));
+                err = rt.r - (1.f + 4.f * sig);
+                grad = err * sig * (1.f - sig) * 4.f;
+            }
+            se_f = fmaf(err, err, se_f);
+            const float gl = lr * grad;
+            cbu = upd_bu ? fmaf(a_b, bu, gl) : bu;
+            cbi = upd_bi ? fmaf(a_b, bi, gl) : bi;
+            const float gl_i = upd_i ? gl : 0.f, gl_u = upd_u ? gl : 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                cq.x[e] = fmaf(gl_i, pu.x[e], a_i * qi.x[e]);
+                cp.x[e] = fmaf(gl_u, qi.x[e], a_u * pu.x[e]);
+            }
+            prev_u = rt.u; prev_i = rt.i;
+            if (lane == (int)slot) hist = rt.u;
+            // rows go back unless the very next rating of the bucket continues the same row
+            if (last || rt_next.i != rt.i) {
+                frag_store<E>(cq, qrow, lane);
+                if (lane == 0) ibs[rt.i - cs] = cbi;
+            }
+            if (last || rt_next.u != rt.u) {
+                frag_store<E>(cp, prm.P + (size_t)rt.u * KPAD, lane);
+                if (lane == 0) prm.ub[rt.u] = cbu;
+            }
         }
-        __syncthreads();  // phase boundary: column groups change hands
+        se += (double)se_f;
+        prev_i = -1;       // the column group changes hands: never forward Q across a phase
+        __syncthreads();   // phase boundary
     }
-
+    cp_async_wait<0>();
     // write the Q tile back
     {
         const int nvec = nq * KPAD / 4;
@@ -392,17 +460,24 @@ __global__ void kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, doubl
     }
 }
 
-size_t sgd_smem_bytes(int tile_rows, int kpad, int W)
+}  // namespace
+
+// shared memory one CTA of the stratified kernel needs (also used by pack.cu to size blocks)
+size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W)
 {
     size_t b = (size_t)tile_rows * kpad * 4;               // Q tile
     b += (size_t)((tile_rows + 3) & ~3) * 4;               // item biases
-    b += (size_t)W * 2 * kChunk * sizeof(PackedRating);    // rating rings
-    b += (size_t)(1 + 2 * W) * 8;                          // mbarriers
-    b += (size_t)W * W * 8;                                // bucket offsets
+    b += (size_t)W * kDepth * kpad * 4;                    // P-row rings
+    b += (size_t)W * kDepth * 4;                           // user-bias rings
+    b += (size_t)W * kRing * sizeof(PackedRating);         // rating rings
+    b += (size_t)(1 + kStages * W) * 8;                    // mbarriers
+    b += (size_t)(W * W + 1) * 8;                          // bucket offsets
     b += (size_t)((W * W + 1) & ~1) * 4;                   // bucket counts
     b += (size_t)W * 8;                                    // per-warp squared error
     return b + 128;
 }
+
+namespace {
 
 template <int E>
 int launch_sgd(mfrec_ctx *ctx, int kernel, const SgdParams &prm, size_t smem)
@@ -451,7 +526,7 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     prm.tile_rows = r->max_cb_items;
     prm.lr = (float)learning_rate; prm.Ku = (float)K_users; prm.Ki = (float)K_items; prm.Kb = (float)K_bias;
     prm.update_users = update_users; prm.update_items = update_items;
-    const size_t smem = sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
+    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
     if (smem > ctx->smem_optin)
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
                                "mfrec_sgd_epoch: Q tile of %d rows x %d needs %zu B shared memory (> %zu); pack with more row_blocks",

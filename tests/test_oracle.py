@@ -1,0 +1,139 @@
+"""CPU tests (no GPU): the C oracle against the committed golden vectors (outputs of the
+reference's own kernels, tests/golden/make_golden.py) and, where oracle/_ref is built, against
+the reference kernels executed live on fresh seeded inputs."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from mfrec_b200 import synth
+from oracle import cpu, ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def g(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "kmf_*.npz"))))
+def test_kmf_golden(path):
+    d = dict(np.load(path))
+    kernel = "linear" if "linear" in os.path.basename(path) else "logistic"
+    u, v = d["u0"].copy(), d["v0"].copy()
+    ib, ub = np.zeros(u.shape[1]), np.zeros(v.shape[1])
+    cpu.kmf_train(kernel, int(d["nbr_epochs"]), int(d["k"]), float(d["lr"]), float(d["K_users"]),
+                  float(d["K_items"]), float(d["K_bias"]), u, v, d["idx"], d["r"], ib, ub,
+                  int(d["update_users"]), int(d["update_items"]))
+    for a, b in ((u, d["u"]), (v, d["v"]), (ib, d["ib"]), (ub, d["ub"])):
+        assert np.array_equal(a, b), "C oracle must be bit-exact with the reference kernel"
+
+
+def test_funk_golden():
+    d = g("funk_without_bias.npz")
+    k, ni, nu = int(d["k"]), d["u"].shape[1], d["v"].shape[1]
+    u = np.zeros((k, ni)) + float(d["f_init"])
+    v = np.zeros((k, nu)) + float(d["f_init"])
+    cpu.funk_train("without_bias", int(d["min_epochs"]), float(d["min_improvement"]), k,
+                   float(d["f_init"]), float(d["lr"]), float(d["K"]), u, v, d["idx"], d["r"])
+    assert np.array_equal(u, d["u"]) and np.array_equal(v, d["v"])
+
+    d = g("funk_with_bias.npz")
+    u = np.zeros((k, ni)) + float(d["f_init"])
+    v = np.zeros((k, nu)) + float(d["f_init"])
+    cpu.funk_train("with_bias", int(d["min_epochs"]), float(d["min_improvement"]), k,
+                   float(d["f_init"]), float(d["lr"]), float(d["K"]), u, v, d["idx"], d["r"],
+                   float(d["mu"]), d["bi"], d["bu"])
+    assert np.array_equal(u, d["u"]) and np.array_equal(v, d["v"])
+
+    for tag in ("u1_i0", "u0_i1"):
+        d = g("funk_with_bias_dev_%s.npz" % tag)
+        u, v = d["u0"].copy(), d["v0"].copy()
+        cpu.funk_train("with_bias_dev", int(d["min_epochs"]), float(d["min_improvement"]), k,
+                       float(d["f_init"]), float(d["lr"]), float(d["K"]), u, v, d["idx"], d["r"],
+                       float(d["mu"]), d["bi"], d["bu"], int(d["update_users"]), int(d["update_items"]))
+        assert np.array_equal(u, d["u"]) and np.array_equal(v, d["v"])
+        if tag == "u1_i0":
+            assert np.array_equal(u, d["u0"])  # items frozen
+        else:
+            assert np.array_equal(v, d["v0"])
+
+
+def test_predictors_and_rmse_golden():
+    d = g("predictors.npz")
+    for name in cpu.PREDICTORS:
+        out = cpu.predict_pairs(name, d["u"], d["v"], d["pairs"], float(d["mu"]), d["ib"], d["ub"])
+        np.testing.assert_allclose(out, d["pred_" + name], rtol=1e-13, atol=1e-14)
+        stats, errs = cpu.rmse_pairs(name, d["u"], d["v"], d["pairs"], d["real"], float(d["mu"]),
+                                     d["ib"], d["ub"])
+        np.testing.assert_allclose(stats, d["stats_" + name], rtol=1e-12)
+        assert stats[3] == d["pairs"].shape[0] - 1 and np.isnan(errs[17])
+
+
+def test_topn_golden():
+    d = g("topn.npz")
+    N = int(d["N"])
+    for tag, predictor, ncand in (("gd_all", "predict_rating", d["u"].shape[1]),
+                                  ("mf_first25", "predict_logistic", 25)):
+        for row, user in enumerate(d["users"]):
+            a, b = d["rated_indptr"][row], d["rated_indptr"][row + 1]
+            items, scores = cpu.topn_user(predictor, d["u"], d["v"], int(user), int(ncand),
+                                          d["rated_items"][a:b], N, float(d["mu"]), d["ib"], d["ub"])
+            want = d["items_" + tag][row]
+            assert np.array_equal(items, want[want >= 0])
+            np.testing.assert_allclose(scores, d["scores_" + tag][row][: len(items)], rtol=1e-13)
+            # quirk: the item whose id equals the user id is never recommended
+            assert int(user) not in items.tolist()
+
+
+def test_bias_stats_against_numpy():
+    nu, ni, nnz = 80, 60, 1500
+    d = synth.make_ratings(nu, ni, nnz, seed=4, shuffle_seed=None)
+    idx, r = d["idx"], d["r"]
+    mu, ib, ub = cpu.bias_stats(idx, r, ni, nu, 0.02, 0.03)
+    assert abs(mu - r.mean()) < 1e-14
+    for i in range(ni):
+        m = idx[:, 1] == i
+        want = (r[m] - mu).sum() / (0.03 + m.sum()) if m.any() else 0.0
+        assert abs(ib[i] - want) < 1e-12
+    for j in range(nu):
+        m = idx[:, 0] == j
+        want = (r[m] - mu - ib[idx[m, 1]]).sum() / (0.02 + m.sum()) if m.any() else 0.0
+        assert abs(ub[j] - want) < 1e-12
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_equals_reference_live(seed):
+    """Fresh inputs, reference kernels executed here: bit-equality for every loop."""
+    nu, ni, nnz, k = 120, 90, 3000, 10
+    d = synth.make_ratings(nu, ni, nnz, seed=seed, shuffle_seed=seed + 7)
+    idx, r = d["idx"], d["r"]
+    for kernel in ("linear", "logistic"):
+        for gates in ((1, 1), (0, 1), (1, 0)):
+            u, v = synth.init_factors(nu, ni, k, seed=seed)
+            ib, ub = np.zeros(ni), np.zeros(nu)
+            u2, v2, ib2, ub2 = u.copy(), v.copy(), ib.copy(), ub.copy()
+            fn = getattr(ref.kmf_train(), "train_%s_kernel" % kernel)
+            fn(3, k, 0.1, 0.01, 0.0, 0.0, 0.04, 0.06, 0.007, 2.0, u, v, idx, r, ib, ub, gates[0], gates[1], 0)
+            cpu.kmf_train(kernel, 3, k, 0.01, 0.04, 0.06, 0.007, u2, v2, idx, r, ib2, ub2, *gates)
+            assert np.array_equal(u, u2) and np.array_equal(v, v2)
+            assert np.array_equal(ib, ib2) and np.array_equal(ub, ub2)
+    mu, bi, bu = cpu.bias_stats(idx, r, ni, nu)
+    u = np.zeros((4, ni)) + 0.1
+    v = np.zeros((4, nu)) + 0.1
+    u2, v2 = u.copy(), v.copy()
+    ref.gd_estimator().estimator_loop_with_bias(5, 9, 0.001, 4, 0.1, 0.002, 0, 0, 0.05, mu, u, v, idx, r,
+                                                bi, bu, nu, ni, 0)
+    cpu.funk_train("with_bias", 5, 0.001, 4, 0.1, 0.002, 0.05, u2, v2, idx, r, mu, bi, bu)
+    assert np.array_equal(u, u2) and np.array_equal(v, v2)
+
+
+def test_synth_is_deterministic_and_unique():
+    a = synth.make_ratings(200, 150, 4000, seed=0)
+    b = synth.make_ratings(200, 150, 4000, seed=0)
+    assert np.array_equal(a["idx"], b["idx"]) and np.array_equal(a["r"], b["r"])
+    keys = a["idx"][:, 0].astype(np.int64) * 150 + a["idx"][:, 1]
+    assert np.unique(keys).shape[0] == 4000
+    assert a["r"].min() >= 1 and a["r"].max() <= 5
