@@ -39,6 +39,7 @@ struct mfrec_ratings {
     int64_t packed_len = 0;        // nnz + alignment padding
     int32_t max_cb_items = 0;      // widest column block (items) -> shared-memory tile size
     int64_t max_bucket = 0;
+    float max_abs_rating = 0.f;    // sizes the fixed-point scale of the warp reduction
     // device
     int32_t *user_perm = nullptr;  // [nu] old -> packed id
     int32_t *item_perm = nullptr;  // [ni]

@@ -8,7 +8,8 @@
 //   users  -> B row blocks      x W row groups      (balanced by degree, LPT)
 //   items  -> G slabs x B column blocks x W column groups
 //   bucket(slab g, row block rb, column block cb, phase p, worker w) holds the ratings of
-//   row group (rb, w) x column group (cb, (w + p) mod W), sorted by (user, item).
+//   row group (rb, w) x column group (cb, (w + p) mod W), sorted by (user, item) so that
+//   ratings of one user are adjacent (sgd.cu keeps that user's row in registers).
 //   Buckets are stored in (g, rb, cb, w, p) order -- worker-major, so the W buckets one warp
 //   walks through are one contiguous stream -- each starting on a 16-byte boundary so the
 //   warp can pull the stream through shared memory with cp.async.bulk.
@@ -25,6 +26,7 @@
 //   5. bucket histogram -> padded offsets                    (1 pass + scan)
 //   6. gather ratings into the packed array                  (1 pass)
 #include <algorithm>
+#include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <numeric>
@@ -74,7 +76,7 @@ __global__ void key_kernel(const int32_t *__restrict__ idx, int64_t nnz,
             ((((uint64_t)slab * kl.B + rb) * kl.B + cbl) * kl.W + wr) * kl.W + p;
         keys[n] = (bucket << (kl.bits_u + kl.bits_i)) |
                   ((uint64_t)(uint32_t)user_perm[ui.x] << kl.bits_i) |
-                  (uint64_t)(uint32_t)item_perm[ui.y];
+                  (uint64_t)(uint32_t)item_perm[ui.y];   // bucket, then user, then item
         vals[n] = (uint32_t)n;
     }
 }
@@ -118,6 +120,18 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
         packed[dst] = pr;
         if (order) order[dst] = (int64_t)src;
     }
+}
+
+// max |rating| over the packed array (non-negative floats order like their bit patterns)
+__global__ void max_abs_rating_kernel(const PackedRating *__restrict__ packed, int64_t n,
+                                      int32_t *__restrict__ out_bits)
+{
+    int32_t mx = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        mx = max(mx, __float_as_int(fabsf(packed[j].r)));
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, mx);
 }
 
 __global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v)
@@ -404,6 +418,20 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
                                                         (const double *)d_r, kl, raw_off.p,
                                                         R->bucket_off, R->packed, R->order);
         MF_LAUNCH_CHECK(ctx);
+    }
+    // largest |rating| (sizes the fixed-point reduction scale of the SGD kernel)
+    {
+        DevBuf<int32_t> d_mx;
+        MF_CUDA(ctx, d_mx.alloc(1));
+        MF_CUDA(ctx, cudaMemsetAsync(d_mx.p, 0, 4, st));
+        if (packed_len > 0) {
+            max_abs_rating_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len, d_mx.p);
+            MF_LAUNCH_CHECK(ctx);
+        }
+        int32_t bits = 0;
+        MF_CUDA(ctx, cudaMemcpyAsync(&bits, d_mx.p, 4, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+        memcpy(&R->max_abs_rating, &bits, 4);
     }
     // widest bucket (diagnostic; bounds the longest serial chain of one phase)
     {

@@ -31,6 +31,8 @@
 // reference's exact order on the reference's own [k][n] layout.  Bit-exact with the reference
 // for the linear kernel; used for verification and for tiny fold-in calls.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -38,7 +40,8 @@ namespace {
 
 constexpr int kChunk = 64;    // ratings per TMA chunk
 constexpr int kStages = 4;    // chunks in flight per warp (ring of kStages * kChunk ratings)
-constexpr int kDepth = 8;     // P rows in flight per warp (cp.async ring)
+constexpr int kDepth = 16;    // P rows in flight per warp (cp.async ring), in stream positions
+constexpr int kQuadsAhead = kDepth / 4;
 constexpr int kRing = kChunk * kStages;
 static_assert(kChunk % 4 == 0, "chunks must be 16-byte multiples");
 static_assert(4 * kDepth <= kChunk, "the prefetch cursor may run at most one chunk ahead");
@@ -54,6 +57,8 @@ struct SgdParams {
     int tile_rows;    // shared-memory rows reserved for the Q tile
     float lr, Ku, Ki, Kb;
     int update_users, update_items;
+    float fx_scale, fx_inv;       // fixed-point scale of the warp reduction (power of two)
+    unsigned long long *timing;   // debug (MFREC_SGD_TIMING=1): [B][W][8] cycle counters, or null
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) + cp.async ------------
@@ -241,6 +246,7 @@ sgd_block_kernel(const SgdParams prm)
     const int64_t S0 = boff[warp * W];
     const uint32_t slen = (uint32_t)(boff[warp * W + W] - S0);   // multiple of 4 (padded buckets)
     const uint32_t nchunks = (slen + kChunk - 1) / kChunk;
+    const uint32_t nquads = slen / 4;
     const PackedRating *stream = prm.packed + S0;
     const int32_t *cnt_w = bcnt + warp * W;
     const int64_t *off_w = boff + warp * W;
@@ -256,130 +262,166 @@ sgd_block_kernel(const SgdParams prm)
     };
     while (issued < nchunks && issued < (uint32_t)kStages) issue_chunk(issued++);
 
-    // Prefetch cursor: walks stream POSITIONS (padding entries included: they name packed user 0,
-    // a valid row, and are never consumed), one cp.async group per position, so that group
-    // index == position and cp.async.wait_group<kDepth-1> at position x guarantees row x landed
-    // once the cursor stands at x + kDepth.  Positions past the end commit empty groups.
-    uint32_t pfpos = 0;
-    auto prefetch_to = [&](uint32_t target) {
-        while (pfpos < target) {
-            if (pfpos < slen) {
-                if ((pfpos % kChunk) == 0) {   // first touch of a chunk: wait for its bulk copy
-                    const uint32_t c = pfpos / kChunk;
+    // Prefetch cursor: walks the stream one QUAD (4 positions = 48 bytes, 16-byte aligned) at a
+    // time, padding entries included (they name packed user 0, a valid row, and are never
+    // consumed).  One cp.async group per quad, so group index == quad index and
+    // cp.async.wait_group<kQuadsAhead-1> at quad x guarantees its four rows have landed once
+    // the cursor stands at x + kQuadsAhead.  Quads past the end commit empty groups.
+    uint32_t pfq = 0;
+    auto prefetch_quads_to = [&](uint32_t target) {
+#pragma unroll 1
+        while (pfq < target) {
+            if (pfq < nquads) {
+                const uint32_t pos = pfq * 4;
+                if ((pos % kChunk) == 0) {   // first touch of a chunk: wait for its bulk copy
+                    const uint32_t c = pos / kChunk;
                     mbar_wait(my_bar + (c % kStages), (c / kStages) & 1u);
                 }
-                const int up = ring[pfpos % kRing].u;
-                const uint32_t slot = pfpos % kDepth;
-                row_cp_async<E>(prow + slot * KPAD, prm.P + (size_t)up * KPAD, lane);
-                if (lane == 0) cp_async<4>(pbias + slot, prm.ub + up);
+                const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (pos % kRing));
+                const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
+                const int us[4] = {a.x, a.w, b.z, c2.y};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t slot = (pos + t) % kDepth;
+                    row_cp_async<E>(prow + slot * KPAD, prm.P + (size_t)us[t] * KPAD, lane);
+                    if (lane == 0) cp_async<4>(pbias + slot, prm.ub + us[t]);
+                }
             }
             cp_async_commit();
-            ++pfpos;
+            ++pfq;
         }
     };
-    prefetch_to(kDepth);
+    prefetch_quads_to(kQuadsAhead);
 
     if (nq > 0) mbar_wait(tile_bar, 0);
     __syncthreads();
 
-    const float lr = prm.lr, Kb = prm.Kb;
+    const float lr = prm.lr;
     const bool upd_u = prm.update_users != 0, upd_i = prm.update_items != 0;
     // q' = q + lr (g p - Ki q) = (1 - lr Ki) q + (lr g) p, likewise for p (frozen side: a = 1, gl = 0)
     const float a_i = upd_i ? 1.f - prm.lr * prm.Ki : 1.f;
     const float a_u = upd_u ? 1.f - prm.lr * prm.Ku : 1.f;
-    const float a_b = 1.f - lr * Kb;
+    const float a_b = 1.f - prm.lr * prm.Kb;
     const bool upd_bu = (KERNEL == MFREC_KERNEL_LINEAR) || upd_u;
     const bool upd_bi = (KERNEL == MFREC_KERNEL_LINEAR) || upd_i;
+    const float fx_scale = prm.fx_scale, fx_inv = prm.fx_inv;
     double se = 0.0;       // fp64 total of fp32 per-bucket partials
+    // opt-in section timer (cycles per warp): 0 bookkeeping + prefetch issue, 1 cp.async wait,
+    // 2 quad load, 3 updates, 6 phase barrier
+    unsigned long long tsec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool timing = prm.timing != nullptr;
+    long long tmark = timing ? clock64() : 0;
+    auto lap = [&](int k) {
+        if (timing) {
+            const long long now = clock64();
+            tsec[k] += (unsigned long long)(now - tmark);
+            tmark = now;
+        }
+    };
     Frag<E> cp, cq;        // current user row / item row (post-update values)
 #pragma unroll
     for (int e = 0; e < E; ++e) { cp.x[e] = 0.f; cq.x[e] = 0.f; }
-    float cbu = 0.f, cbi = 0.f;
+    float cbu = 0.f, cbi = 0.f, se_f = 0.f;
     int prev_u = -1, prev_i = -1, hist = -1;
     uint32_t cons_chunk = 0;
+
+    // one rating: pos = stream position, (u, i, r) the triple
+    auto update_one = [&](uint32_t pos, int u, int it, float r) {
+        const uint32_t slot = pos % kDepth;
+        const bool same_u = (u == prev_u);
+        Frag<E> pu;
+        float bu;
+        if (!same_u && __any_sync(0xffffffffu, hist == u)) {
+            // the row was updated after its prefetch was issued (the user repeats across a bucket
+            // boundary inside the prefetch window): re-read it from global memory
+            frag_load<E>(pu, prm.P + (size_t)u * KPAD, lane);
+            bu = prm.ub[u];
+        } else {
+            frag_load<E>(pu, prow + slot * KPAD, lane);
+            bu = pbias[slot];
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) pu.x[e] = same_u ? cp.x[e] : pu.x[e];
+        bu = same_u ? cbu : bu;
+        float *qrow = Qs + (size_t)(it - cs) * KPAD;
+        if (it != prev_i) {   // otherwise the item row is still in registers
+            frag_load<E>(cq, qrow, lane);
+            cbi = ibs[it - cs];
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) part = fmaf(pu.x[e], cq.x[e], part);
+        // deterministic warp reduction in 32-bit fixed point: one REDUX instead of a 5-level
+        // shuffle butterfly; integer addition is associative, so the result does not depend on
+        // lane order.  fx_scale is a power of two chosen from max |rating| (see sgd_epoch).
+        const float dot = (float)__reduce_add_sync(0xffffffffu, __float2int_rn(part * fx_scale)) * fx_inv;
+        const float pred = cbi + bu + dot;
+        float err, grad;
+        if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
+            err = r - pred;
+            grad = err;
+        } else {
+            const float sig = 1.f / (1.f + expf(-pred));
+            err = r - (1.f + 4.f * sig);
+            grad = err * sig * (1.f - sig) * 4.f;
+        }
+        se_f = fmaf(err, err, se_f);
+        const float gl = lr * grad;
+        cbu = upd_bu ? fmaf(a_b, bu, gl) : bu;
+        cbi = upd_bi ? fmaf(a_b, cbi, gl) : cbi;
+        const float gli = upd_i ? gl : 0.f, glu = upd_u ? gl : 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float pe = pu.x[e], qe = cq.x[e];
+            cp.x[e] = fmaf(glu, qe, a_u * pe);
+            cq.x[e] = fmaf(gli, pe, a_i * qe);
+        }
+        prev_u = u;
+        prev_i = it;
+        if (lane == (int)slot) hist = u;
+        frag_store<E>(cq, qrow, lane);
+        frag_store<E>(cp, prm.P + (size_t)u * KPAD, lane);
+        if (lane == 0) {
+            ibs[it - cs] = cbi;
+            prm.ub[u] = cbu;
+        }
+    };
 
     for (int p = 0; p < W; ++p) {
         const uint32_t n = (uint32_t)cnt_w[p];
         const uint32_t rel0 = (uint32_t)(off_w[p] - S0);
-        float se_f = 0.f;
-        PackedRating rt_next;
-        if (n > 0) rt_next = ring[rel0 % kRing];
+        se_f = 0.f;
 #pragma unroll 1
-        for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t rel = rel0 + i;
-            const PackedRating rt = rt_next;
+        for (uint32_t i = 0; i < n; i += 4) {
+            const uint32_t rel = rel0 + i;   // quad aligned
             if (rel / kChunk != cons_chunk) {
                 cons_chunk = rel / kChunk;   // every earlier chunk's stage is free again
                 __syncwarp();
                 while (issued < nchunks && issued < cons_chunk + kStages) issue_chunk(issued++);
             }
-            prefetch_to(rel + kDepth);
-            cp_async_wait<kDepth - 1>();
-            // next rating of this bucket (garbage past the end, never used)
-            rt_next = ring[(rel + 1) % kRing];
-            const bool last = (i + 1 == n);
-            const uint32_t slot = rel % kDepth;
-            Frag<E> pu, qi;
-            frag_load<E>(pu, prow + slot * KPAD, lane);
-            float bu = (lane == 0) ? pbias[slot] : 0.f;   // lane 0 owns both biases
-            float *qrow = Qs + (size_t)(rt.i - cs) * KPAD;
-            frag_load<E>(qi, qrow, lane);
-            float bi = (lane == 0) ? ibs[rt.i - cs] : 0.f;
-            const bool same_u = (rt.u == prev_u), same_i = (rt.i == prev_i);
-            if (__any_sync(0xffffffffu, hist == rt.u) && !same_u) {
-                // the row was updated after its prefetch was issued (user repeats across a bucket
-                // boundary within the prefetch window): re-read it from global memory
-                frag_load<E>(pu, prm.P + (size_t)rt.u * KPAD, lane);
-                bu = (lane == 0) ? prm.ub[rt.u] : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                pu.x[e] = same_u ? cp.x[e] : pu.x[e];
-                qi.x[e] = same_i ? cq.x[e] : qi.x[e];
-            }
-            bu = same_u ? cbu : bu;
-            bi = same_i ? cbi : bi;
-            const float bsum = __shfl_sync(0xffffffffu, bi + bu, 0);
-            float part = 0.f;
-#pragma unroll
-            for (int e = 0; e < E; ++e) part = fmaf(pu.x[e], qi.x[e], part);
-            const float s = warp_sum(part) + bsum;
-            float err, grad;
-            if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
-                err = rt.r - s;
-                grad = err;
-            } else {
-                const float sig = 1.f / (1.f + expf(-s));
-                err = rt.r - (1.f + 4.f * sig);
-                grad = err * sig * (1.f - sig) * 4.f;
-            }
-            se_f = fmaf(err, err, se_f);
-            const float gl = lr * grad;
-            cbu = upd_bu ? fmaf(a_b, bu, gl) : bu;
-            cbi = upd_bi ? fmaf(a_b, bi, gl) : bi;
-            const float gl_i = upd_i ? gl : 0.f, gl_u = upd_u ? gl : 0.f;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                cq.x[e] = fmaf(gl_i, pu.x[e], a_i * qi.x[e]);
-                cp.x[e] = fmaf(gl_u, qi.x[e], a_u * pu.x[e]);
-            }
-            prev_u = rt.u; prev_i = rt.i;
-            if (lane == (int)slot) hist = rt.u;
-            // rows go back unless the very next rating of the bucket continues the same row
-            if (last || rt_next.i != rt.i) {
-                frag_store<E>(cq, qrow, lane);
-                if (lane == 0) ibs[rt.i - cs] = cbi;
-            }
-            if (last || rt_next.u != rt.u) {
-                frag_store<E>(cp, prm.P + (size_t)rt.u * KPAD, lane);
-                if (lane == 0) prm.ub[rt.u] = cbu;
-            }
+            prefetch_quads_to(rel / 4 + kQuadsAhead);
+            lap(0);
+            cp_async_wait<kQuadsAhead - 1>();   // the four rows of this quad have landed
+            __syncwarp();                       // ... and lane 0's bias copies / stores are visible
+            lap(1);
+            const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (rel % kRing));
+            const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
+            const uint32_t nv = n - i;   // valid ratings in this quad (>= 1; >= 4 means all)
+            lap(2);
+            update_one(rel, a.x, a.y, __int_as_float(a.z));
+            if (nv > 1) update_one(rel + 1, a.w, b.x, __int_as_float(b.y));
+            if (nv > 2) update_one(rel + 2, b.z, b.w, __int_as_float(c2.x));
+            if (nv > 3) update_one(rel + 3, c2.y, c2.z, __int_as_float(c2.w));
+            lap(3);
         }
         se += (double)se_f;
         prev_i = -1;       // the column group changes hands: never forward Q across a phase
         __syncthreads();   // phase boundary
+        lap(6);
     }
     cp_async_wait<0>();
+    if (timing && lane == 0)
+        for (int k2 = 0; k2 < 8; ++k2) prm.timing[((size_t)rb * W + warp) * 8 + k2] = tsec[k2];
     // write the Q tile back
     {
         const int nvec = nq * KPAD / 4;
@@ -526,11 +568,31 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     prm.tile_rows = r->max_cb_items;
     prm.lr = (float)learning_rate; prm.Ku = (float)K_users; prm.Ki = (float)K_items; prm.Kb = (float)K_bias;
     prm.update_users = update_users; prm.update_items = update_items;
+    {
+        // The dot product's cross-lane sum runs in 32-bit fixed point (REDUX).  Predictions live
+        // on the rating scale, so allow |dot| up to 16 x max|rating| (at least 16) before the
+        // integer sum wraps; the resolution is then <= 2^-23 of that range (fp32-like).
+        const float range = 16.f * fmaxf(r->max_abs_rating, 1.f);
+        int ex = 0;
+        frexpf(range, &ex);              // range <= 2^ex
+        prm.fx_scale = ldexpf(1.f, 30 - ex);
+        prm.fx_inv = ldexpf(1.f, ex - 30);
+    }
     const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
     if (smem > ctx->smem_optin)
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
                                "mfrec_sgd_epoch: Q tile of %d rows x %d needs %zu B shared memory (> %zu); pack with more row_blocks",
                                r->max_cb_items, m->kpad, smem, ctx->smem_optin);
+    // debug: MFREC_SGD_TIMING=1 prints per-section cycle counts of the first launch to stderr
+    static int timing_env = -1;
+    if (timing_env < 0) timing_env = getenv("MFREC_SGD_TIMING") ? 1 : 0;
+    DevBuf<unsigned long long> d_timing;
+    prm.timing = nullptr;
+    if (timing_env) {
+        MF_CUDA(ctx, d_timing.alloc((size_t)r->B * r->W * 8));
+        MF_CUDA(ctx, cudaMemsetAsync(d_timing.p, 0, (size_t)r->B * r->W * 64, ctx->stream));
+        prm.timing = d_timing.p;
+    }
     int64_t part = 0;
     for (int g = s_lo; g < s_hi; ++g) {
         for (int s = 0; s < r->B; ++s) {
@@ -547,6 +609,25 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
             default: rc = mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", m->kpad);
             }
             MF_TRY(rc);
+            if (timing_env) {
+                std::vector<unsigned long long> h((size_t)r->B * r->W * 8);
+                MF_CUDA(ctx, cudaMemcpyAsync(h.data(), d_timing.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                double avg[8] = {0}, mx[8] = {0};
+                double worst_tot = 0; int worst = 0;
+                for (int c = 0; c < r->B * r->W; ++c) {
+                    double tot = 0;
+                    for (int k2 = 0; k2 < 7; ++k2) { avg[k2] += (double)h[(size_t)c * 8 + k2]; tot += (double)h[(size_t)c * 8 + k2]; }
+                    if (tot - (double)h[(size_t)c * 8 + 6] > worst_tot) { worst_tot = tot - (double)h[(size_t)c * 8 + 6]; worst = c; }
+                }
+                fprintf(stderr, "[sgd timing] slab %d sub-epoch %d: avg cycles/warp by section:", g, s);
+                for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %.0f", avg[k2] / (r->B * r->W));
+                fprintf(stderr, " | busiest warp (cta %d warp %d):", worst / r->W, worst % r->W);
+                for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %llu", h[(size_t)worst * 8 + k2]);
+                fprintf(stderr, "\n");
+                (void)mx;
+                if (s >= 2) timing_env = 0;   // three launches are enough
+            }
         }
     }
     if (sq_err_out) {
