@@ -94,13 +94,17 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------------
 # synthetic data on the GPU (torch is plumbing here: RNG, sort/unique, host pinning)
 # --------------------------------------------------------------------------------------------
-def gpu_synth(torch, dev, nu, ni, nnz, seed, user_offset=0):
+def gpu_synth(torch, dev, nu, ni, nnz, seed, user_offset=0, item_tiles=1, item_seed=None):
     """Netflix-shaped unique (user, item, rating) triples in shuffled order (see
-    mfrec_b200/synth.py for the model; this is the same recipe with torch's generator)."""
+    mfrec_b200/synth.py for the model; this is the same recipe with torch's generator).
+    item_tiles > 1: the ni items are `item_tiles` copies of one item-popularity profile (the
+    multi-GPU weak-scaling workload); item_seed fixes that profile across ranks."""
     from mfrec_b200 import synth
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    wu, wi = synth.marginals(nu, ni, seed)
+    ni_tile = ni // item_tiles
+    wu, _ = synth.marginals(nu, ni_tile, seed)
+    _, wi = synth.marginals(nu, ni_tile, seed if item_seed is None else item_seed)
     cu = torch.from_numpy(np.cumsum(wu)).to(dev)
     ci = torch.from_numpy(np.cumsum(wi)).to(dev)
     keys = None
@@ -108,7 +112,9 @@ def gpu_synth(torch, dev, nu, ni, nnz, seed, user_offset=0):
         need = nnz - (0 if keys is None else keys.numel())
         m = int(need * 1.12) + 4096
         us = torch.searchsorted(cu, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=nu - 1)
-        it = torch.searchsorted(ci, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=ni - 1)
+        it = torch.searchsorted(ci, torch.rand(m, device=dev, dtype=torch.float64, generator=g)).clamp_(max=ni_tile - 1)
+        if item_tiles > 1:
+            it += torch.randint(0, item_tiles, (m,), device=dev, generator=g) * ni_tile
         new = us * ni + it
         del us, it
         keys = torch.unique(new if keys is None else torch.cat([keys, new]))

@@ -231,3 +231,29 @@ def test_empty_and_tiny_inputs(native):
     kmf_train.train_logistic_kernel(7, k, 0.1, 0.01, 0, 0, 0.05, 0.05, 0.007, 0.0, u, v, idx, r, ib, ub, 1, 0)
     assert np.array_equal(u, u3), "items must stay frozen when update_items = 0"
     assert not np.array_equal(v, v3)
+
+
+def test_item_slabs_on_one_device(native, small_problem):
+    """G = 3 item slabs processed back to back on one GPU (what one rank of a 3-GPU ring does over
+    an epoch, minus the exchange) must equal the oracle replay of the same block order."""
+    from oracle import cpu
+    p = small_problem
+    k = 24
+    R = native.Ratings(p["idx"], p["r"], p["ni"], p["nu"], row_blocks=2, workers=4, n_slabs=3,
+                       keep_order=1, k_hint=k)
+    assert R.G == 3 and R.launches_per_epoch == 6
+    bounds = [R.slab_items(c) for c in range(3)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == p["ni"]
+    assert all(bounds[c][1] == bounds[c + 1][0] for c in range(2))
+    rep = R.replay_order()
+    u0, v0, ib0, ub0 = _fresh(p["nu"], p["ni"], k)
+    M = native.Model(k, p["ni"], p["nu"], u0, v0, ib0, ub0, layout=R)
+    for _ in range(2):
+        for c in range(3):           # slab by slab, like the ring driver
+            M.sgd_epoch(R, native.KERNEL_LINEAR, LR, KU, KI, KB, slab=c)
+    M.ctx.sync()
+    u1, v1, ib1, ub1 = M.read()
+    cpu.kmf_train("linear", 2, k, LR, KU, KI, KB, u0, v0, np.ascontiguousarray(p["idx"][rep]),
+                  np.ascontiguousarray(p["r"][rep]), ib0, ub0)
+    for a, b in ((u0, u1), (v0, v1), (ib0, ib1), (ub0, ub1)):
+        np.testing.assert_allclose(b, a, rtol=2e-4, atol=2e-5)
