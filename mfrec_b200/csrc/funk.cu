@@ -1,10 +1,371 @@
-// Funk-SVD per-feature SGD (gd_estimator.pyx) -- placeholder until the kernel lands.
+// Funk-SVD per-feature SGD: estimator_loop_without_bias / _with_bias / _with_bias_dev of the
+// reference (mfrec/lib/gd_estimator.pyx:691-779, 489-582, 588-685), as driven by
+// GDRecommender.feature_training and retrain_user / retrain_item
+// (mfrec/recommendation/gradient_descent.py:506-545, 879-905).
+//
+// One feature f is trained at a time: every rating touches ONE scalar of the item row and ONE of
+// the user row plus a cached partial prediction, so a training pass is a pure stream:
+//   12 B rating triple + 8 B cache read + 2 x (8 B read + 8 B write) scalars  (fp64 on device)
+// Everything is kept in float64 with unfused multiplies and adds, so the stratified schedule is
+// BIT-IDENTICAL to the CPU oracle replaying the same block order, and the sequential schedule is
+// bit-identical to the reference order.
+//
+// Stratified schedule: the same B x B x W x W layout as the KMF kernel (pack.cu).  A warp owns a
+// bucket; its 32 lanes stage 32 ratings (triple, cache value, user scalar) with coalesced loads
+// and then replay them in order through warp shuffles, all lanes computing the (scalar) update
+// redundantly.  The item scalars of the column block live in shared memory.  The
+// `while rmse <= rmse_last - min_improvement` control of the reference (rmse carried across
+// features, max_epochs ignored) runs on the host, one device reduction per pass.
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 
-extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int, int, int, double, int, double, double, double, double,
-                                double *, double *, const int32_t *, const double *, int64_t, int32_t,
-                                int32_t, const double *, const double *, int, int, const mfrec_opts *,
-                                int32_t *, double *)
+namespace {
+
+__device__ __forceinline__ double clamp15(double x)
 {
-    return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_train_funk: not implemented yet");
+    if (x > 5.0) x = 5.0;
+    if (x < 1.0) x = 1.0;
+    return x;
+}
+
+// gd_estimator.pyx:38-73 with unfused arithmetic
+__device__ __forceinline__ double funk_estimate(double uf, double vf, double cache, double base,
+                                                double trail, int trailing)
+{
+    double s = cache > 0 ? cache : base;
+    s = __dadd_rn(s, __dmul_rn(uf, vf));
+    s = clamp15(s);
+    if (trailing) {
+        s = __dadd_rn(s, trail);
+        s = clamp15(s);
+    }
+    return s;
+}
+
+struct FunkParams {
+    const PackedRating *packed;
+    const int64_t *bucket_off;
+    const int32_t *bucket_cnt;
+    const int32_t *col_start;
+    double *uf;          // [ni] item scalars of feature f, packed order
+    double *vf;          // [nu] user scalars
+    const double *ibp;   // [ni] item biases, packed order (variant > 0)
+    const double *ubp;   // [nu]
+    const double *cache; // [packed_len]
+    double *se_part;     // [B]
+    int B, W, s;
+    int tile_rows;
+    int variant;
+    double lr, K, overall, trail;
+    int update_users, update_items;
+};
+
+__global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W = prm.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rb = blockIdx.x;
+    const int cbl = (rb + prm.s) % prm.B;
+    const int cs = prm.col_start[cbl * W];
+    const int nq = prm.col_start[(cbl + 1) * W] - cs;
+    double *ufs = reinterpret_cast<double *>(smem_raw);
+    double *ibs = ufs + prm.tile_rows;
+    double *se_s = ibs + prm.tile_rows;
+    int64_t *boff = reinterpret_cast<int64_t *>(se_s + W);
+    int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
+
+    const int64_t bucket_base = ((int64_t)rb * prm.B + cbl) * W * W;
+    for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
+        boff[i] = prm.bucket_off[bucket_base + i];
+        if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
+    }
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+        ufs[i] = prm.uf[cs + i];
+        ibs[i] = prm.variant ? prm.ibp[cs + i] : 0.0;
+    }
+    __syncthreads();
+
+    const double lr = prm.lr, K = prm.K;
+    double se = 0.0;
+    for (int p = 0; p < W; ++p) {
+        const int64_t a = boff[warp * W + p];
+        const int n = bcnt[warp * W + p];
+        int prev_u = -1;
+        double vf_cur = 0.0;
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            PackedRating rt;
+            rt.u = 0; rt.i = cs; rt.r = 0.f;
+            double c = 0.0, vfu = 0.0, bb = 1.0;
+            if (j < n) {
+                rt = prm.packed[a + j];
+                c = prm.cache[a + j];
+                vfu = prm.vf[rt.u];
+                // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
+                bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[rt.i - cs]), prm.ubp[rt.u])
+                                 : 1.0;
+            }
+            const int cnt = min(32, n - base);
+            for (int t = 0; t < cnt; ++t) {
+                const int u_t = __shfl_sync(0xffffffffu, rt.u, t);
+                const int i_t = __shfl_sync(0xffffffffu, rt.i, t);
+                const double r_t = (double)__shfl_sync(0xffffffffu, rt.r, t);
+                const double c_t = __shfl_sync(0xffffffffu, c, t);
+                double v_t = __shfl_sync(0xffffffffu, vfu, t);
+                const double b_t = __shfl_sync(0xffffffffu, bb, t);
+                if (u_t == prev_u) v_t = vf_cur;                   // same user as the last rating
+                else if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
+                const double mf = ufs[i_t - cs];
+                const double pr = funk_estimate(mf, v_t, c_t, b_t, prm.trail, 1);
+                const double err = __dadd_rn(r_t, -pr);
+                se = __dadd_rn(se, __dmul_rn(err, err));
+                const double cf = v_t;
+                if (prm.update_items)
+                    ufs[i_t - cs] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
+                vf_cur = prm.update_users
+                             ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
+                             : cf;
+                prev_u = u_t;
+            }
+        }
+        if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
+        __syncthreads();   // phase boundary (also orders lane 0's stores before the next loads)
+    }
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.uf[cs + i] = ufs[i];
+    if (lane == 0) se_s[warp] = se;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < W; ++w) tot = __dadd_rn(tot, se_s[w]);
+        prm.se_part[rb] = tot;
+    }
+}
+
+// cache refresh after a feature is trained (:771-777): embarrassingly parallel
+__global__ void funk_cache_kernel(const PackedRating *__restrict__ packed, int64_t n,
+                                  const double *__restrict__ uf, const double *__restrict__ vf,
+                                  const double *__restrict__ ibp, const double *__restrict__ ubp,
+                                  int variant, double overall, double *__restrict__ cache)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const PackedRating rt = packed[j];
+        const double bb = variant ? __dadd_rn(__dadd_rn(overall, ibp[rt.i]), ubp[rt.u]) : 1.0;
+        cache[j] = funk_estimate(uf[rt.i], vf[rt.u], cache[j], bb, 0.0, 0);
+    }
+}
+
+__global__ void gather_row_kernel(const double *__restrict__ row, int32_t n,
+                                  const int32_t *__restrict__ perm, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[perm[i]] = row ? row[i] : 0.0;
+}
+
+__global__ void scatter_row_kernel(const double *__restrict__ in, int32_t n,
+                                   const int32_t *__restrict__ perm, double *__restrict__ row)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) row[i] = in[perm[i]];
+}
+
+__global__ void __launch_bounds__(1024) sum_parts_kernel(const double *__restrict__ part, int n,
+                                                         double *__restrict__ out)
+{
+    // fixed order: one thread, partials are few (B * B per pass)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < n; ++i) tot = __dadd_rn(tot, part[i]);
+        *out = tot;
+    }
+}
+
+// ---- sequential schedule: the reference loop verbatim, one thread ---------------------------
+__global__ void funk_sequential_kernel(int variant, int min_epochs, double min_improvement, int dim,
+                                       double f_init, double lr, double K, double overall,
+                                       double *u, double *v, const int32_t *idx, const double *ratings,
+                                       int64_t nnz, int64_t ni, int64_t nu, const double *ib,
+                                       const double *ub, int update_users, int update_items,
+                                       double *cache, int32_t *feature_epochs, double *feature_rmse)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double rmse = 2.0, rmse_last = 0.0;
+    for (int64_t n = 0; n < nnz; ++n) cache[n] = 0.0;
+    for (int f = 0; f < dim; ++f) {
+        double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
+        const double trail = __dmul_rn(__dmul_rn((double)(dim - f - 1), f_init), f_init);
+        int epoch = 0;
+        while (epoch < min_epochs || rmse <= __dadd_rn(rmse_last, -min_improvement)) {
+            double se = 0.0;
+            rmse_last = rmse;
+            for (int64_t n = 0; n < nnz; ++n) {
+                const int user = idx[2 * n], item = idx[2 * n + 1];
+                const double bb = variant ? __dadd_rn(__dadd_rn(overall, ib[item]), ub[user]) : 1.0;
+                const double pr = funk_estimate(uf[item], vf[user], cache[n], bb, trail, 1);
+                const double err = __dadd_rn(ratings[n], -pr);
+                se = __dadd_rn(se, __dmul_rn(err, err));
+                const double cf = vf[user], mf = uf[item];
+                if (update_items)
+                    uf[item] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
+                if (update_users)
+                    vf[user] = __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))));
+            }
+            rmse = sqrt(se / (double)nnz);
+            ++epoch;
+        }
+        feature_epochs[f] = epoch;
+        feature_rmse[f] = rmse;
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int user = idx[2 * n], item = idx[2 * n + 1];
+            const double bb = variant ? __dadd_rn(__dadd_rn(overall, ib[item]), ub[user]) : 1.0;
+            cache[n] = funk_estimate(uf[item], vf[user], cache[n], bb, 0.0, 0);
+        }
+    }
+}
+
+size_t funk_smem_bytes(int tile_rows, int W)
+{
+    return (size_t)tile_rows * 16 + (size_t)W * 8 + (size_t)(W * W + 1) * 8 + (size_t)(W * W + 2) * 4 + 64;
+}
+
+}  // namespace
+
+extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int max_epochs,
+                                double min_improvement, int k, double f_init, double learning_rate,
+                                double K, double overall_avg, double *u, double *v,
+                                const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                                int32_t ni, int32_t nu, const double *items_bias,
+                                const double *users_bias, int update_users, int update_items,
+                                const mfrec_opts *opts, int32_t *feature_epochs, double *feature_rmse)
+{
+    (void)max_epochs;  // ignored by the reference too (CYTHON_UNUSED, gd_estimator.c:1272)
+    if (!ctx) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_train_funk: NULL ctx");
+    if (variant < MFREC_FUNK_WITHOUT_BIAS || variant > MFREC_FUNK_WITH_BIAS_DEV)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_train_funk: variant=%d", variant);
+    if (!u || !v || (nnz > 0 && (!ratings_index || !ratings)) || k <= 0 || ni <= 0 || nu <= 0 || nnz < 0)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_train_funk: bad argument");
+    if (variant != MFREC_FUNK_WITHOUT_BIAS && (!items_bias || !users_bias))
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_train_funk: bias arrays are required");
+    if (variant != MFREC_FUNK_WITH_BIAS_DEV) { update_users = 1; update_items = 1; }
+    if (nnz == 0)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG,
+                               "mfrec_train_funk: no ratings (the reference loops forever on 0/0)");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> h_fe(k, 0);
+    std::vector<double> h_fr(k, 0.0);
+
+    DevBuf<double> du, dv, dib, dub;
+    MF_CUDA(ctx, du.alloc((size_t)k * ni));
+    MF_CUDA(ctx, dv.alloc((size_t)k * nu));
+    MF_CUDA(ctx, cudaMemcpyAsync(du.p, u, (size_t)k * ni * 8, cudaMemcpyHostToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(dv.p, v, (size_t)k * nu * 8, cudaMemcpyHostToDevice, st));
+    if (variant) {
+        MF_CUDA(ctx, dib.alloc(ni));
+        MF_CUDA(ctx, dub.alloc(nu));
+        MF_CUDA(ctx, cudaMemcpyAsync(dib.p, items_bias, (size_t)ni * 8, cudaMemcpyHostToDevice, st));
+        MF_CUDA(ctx, cudaMemcpyAsync(dub.p, users_bias, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
+    }
+
+    if (opts && opts->schedule == MFREC_SCHED_SEQUENTIAL) {
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int32_t a = ratings_index[2 * n], b = ratings_index[2 * n + 1];
+            if (a < 0 || a >= nu || b < 0 || b >= ni)
+                return mfrec_set_error(ctx, MFREC_ERR_INDEX, "mfrec_train_funk: rating %lld has (user,item)=(%d,%d)",
+                                       (long long)n, a, b);
+        }
+        DevBuf<int32_t> didx, dfe;
+        DevBuf<double> dr, dcache, dfr;
+        MF_CUDA(ctx, didx.alloc((size_t)nnz * 2));
+        MF_CUDA(ctx, dr.alloc(nnz));
+        MF_CUDA(ctx, dcache.alloc(nnz));
+        MF_CUDA(ctx, dfe.alloc(k));
+        MF_CUDA(ctx, dfr.alloc(k));
+        MF_CUDA(ctx, cudaMemcpyAsync(didx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        MF_CUDA(ctx, cudaMemcpyAsync(dr.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
+        funk_sequential_kernel<<<1, 1, 0, st>>>(variant, min_epochs, min_improvement, k, f_init,
+                                                learning_rate, K, overall_avg, du.p, dv.p, didx.p, dr.p,
+                                                nnz, ni, nu, dib.p, dub.p, update_users, update_items,
+                                                dcache.p, dfe.p, dfr.p);
+        MF_LAUNCH_CHECK(ctx);
+        MF_CUDA(ctx, cudaMemcpyAsync(h_fe.data(), dfe.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(ctx, cudaMemcpyAsync(h_fr.data(), dfr.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        mfrec_opts o;
+        if (opts) o = *opts; else memset(&o, 0, sizeof(o));
+        o.n_slabs = 1;
+        o.k_hint = 4;   // the tile holds 16 B per item here, far below any factor-row tile
+        mfrec_ratings *R = nullptr;
+        MF_TRY(mfrec_ratings_pack(ctx, ratings_index, ratings, 0, 0, nnz, ni, nu, nullptr, &o, &R));
+        struct Guard { mfrec_ratings *r; ~Guard() { mfrec_ratings_destroy(r); } } guard{R};
+        const size_t smem = funk_smem_bytes(R->max_cb_items, R->W);
+        if (smem > ctx->smem_optin)
+            return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_train_funk: tile needs %zu B shared memory", smem);
+        MF_CUDA(ctx, cudaFuncSetAttribute(funk_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DevBuf<double> cache, ufp, vfp, ibp, ubp, se_part, se_tot;
+        MF_CUDA(ctx, cache.alloc((size_t)R->packed_len + 1));
+        MF_CUDA(ctx, cudaMemsetAsync(cache.p, 0, ((size_t)R->packed_len + 1) * 8, st));
+        MF_CUDA(ctx, ufp.alloc(ni));
+        MF_CUDA(ctx, vfp.alloc(nu));
+        MF_CUDA(ctx, ibp.alloc(ni));
+        MF_CUDA(ctx, ubp.alloc(nu));
+        MF_CUDA(ctx, se_part.alloc((size_t)R->B * R->B));
+        MF_CUDA(ctx, se_tot.alloc(1));
+        const int gi = (ni + 255) / 256, gu = (nu + 255) / 256;
+        gather_row_kernel<<<gi, 256, 0, st>>>(variant ? dib.p : nullptr, ni, R->item_perm, ibp.p);
+        MF_LAUNCH_CHECK(ctx);
+        gather_row_kernel<<<gu, 256, 0, st>>>(variant ? dub.p : nullptr, nu, R->user_perm, ubp.p);
+        MF_LAUNCH_CHECK(ctx);
+        FunkParams prm;
+        prm.packed = R->packed; prm.bucket_off = R->bucket_off; prm.bucket_cnt = R->bucket_cnt;
+        prm.col_start = R->col_start;
+        prm.uf = ufp.p; prm.vf = vfp.p; prm.ibp = ibp.p; prm.ubp = ubp.p; prm.cache = cache.p;
+        prm.B = R->B; prm.W = R->W; prm.tile_rows = R->max_cb_items; prm.variant = variant;
+        prm.lr = learning_rate; prm.K = K; prm.overall = overall_avg;
+        prm.update_users = update_users; prm.update_items = update_items;
+        double rmse = 2.0, rmse_last = 0.0;
+        for (int f = 0; f < k; ++f) {
+            gather_row_kernel<<<gi, 256, 0, st>>>(du.p + (size_t)f * ni, ni, R->item_perm, ufp.p);
+            MF_LAUNCH_CHECK(ctx);
+            gather_row_kernel<<<gu, 256, 0, st>>>(dv.p + (size_t)f * nu, nu, R->user_perm, vfp.p);
+            MF_LAUNCH_CHECK(ctx);
+            prm.trail = (double)(k - f - 1) * f_init * f_init;
+            int epoch = 0;
+            while (epoch < min_epochs || rmse <= rmse_last - min_improvement) {
+                rmse_last = rmse;
+                for (int s = 0; s < R->B; ++s) {
+                    prm.s = s;
+                    prm.se_part = se_part.p + (size_t)s * R->B;
+                    funk_train_kernel<<<R->B, R->W * 32, smem, st>>>(prm);
+                    MF_LAUNCH_CHECK(ctx);
+                }
+                sum_parts_kernel<<<1, 32, 0, st>>>(se_part.p, R->B * R->B, se_tot.p);
+                MF_LAUNCH_CHECK(ctx);
+                double se = 0.0;
+                MF_CUDA(ctx, cudaMemcpyAsync(&se, se_tot.p, 8, cudaMemcpyDeviceToHost, st));
+                MF_CUDA(ctx, cudaStreamSynchronize(st));
+                rmse = sqrt(se / (double)nnz);
+                ++epoch;
+            }
+            h_fe[f] = epoch;
+            h_fr[f] = rmse;
+            funk_cache_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(R->packed, R->packed_len, ufp.p, vfp.p,
+                                                                 ibp.p, ubp.p, variant, overall_avg, cache.p);
+            MF_LAUNCH_CHECK(ctx);
+            scatter_row_kernel<<<gi, 256, 0, st>>>(ufp.p, ni, R->item_perm, du.p + (size_t)f * ni);
+            MF_LAUNCH_CHECK(ctx);
+            scatter_row_kernel<<<gu, 256, 0, st>>>(vfp.p, nu, R->user_perm, dv.p + (size_t)f * nu);
+            MF_LAUNCH_CHECK(ctx);
+        }
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    MF_CUDA(ctx, cudaMemcpyAsync(u, du.p, (size_t)k * ni * 8, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(v, dv.p, (size_t)k * nu * 8, cudaMemcpyDeviceToHost, st));
+    MF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (feature_epochs) memcpy(feature_epochs, h_fe.data(), (size_t)k * 4);
+    if (feature_rmse) memcpy(feature_rmse, h_fr.data(), (size_t)k * 8);
+    return MFREC_OK;
 }
