@@ -34,6 +34,18 @@ def algorithmic_bytes_per_update(k, elem_bytes=4):
     return 4 * k * elem_bytes + 12 + 16
 
 
+def captured_traffic(kernel, updates_per_launch):
+    """DRAM bytes per launch of the dominant kernel from the latest committed `ncu --set full`
+    capture (profiles/traffic.json), rescaled to this run's updates per launch."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)[kernel]
+        return t["dram_bytes_per_launch"] * updates_per_launch / t["updates_per_launch"], t["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -176,7 +188,7 @@ def run_native(args):
                         nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
                         workers=args.workers)
     M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
-    layout_desc = ("stratified B=%d W=%d launches/epoch=%d max_bucket=%d widest_column_block=%d items"
+    layout_desc = ("stratified B=%d W=%d sub-epochs/epoch=%d max_bucket=%d widest_column_block=%d items"
                    % (R.B, R.W, R.launches_per_epoch, R.max_bucket, R.max_cb_items))
     # schedule balance: the serial chain of one epoch = sum over launches of the slowest CTA,
     # a CTA = sum over phases of its fullest bucket; ideal = nnz / (B * W)
@@ -219,10 +231,14 @@ def run_native(args):
     # figures: algorithmic bytes of one launch / its average duration
     n_sgd = launches_timed - args.steps
     achieved = value * bpu / 1e9
+    upl = nnz * args.steps / max(n_sgd, 1)
+    traffic, traffic_src = captured_traffic("sgd_block_kernel", upl)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "kernel": "sgd_block_kernel", "algorithmic_bytes_per_update": bpu,
-                "updates_per_launch": nnz * args.steps / max(n_sgd, 1),
+                "algorithmic_bytes_per_launch": bpu * upl,
+                "updates_per_launch": upl,
                 "avg_launch_us": ms * 1e3 / max(n_sgd, 1)}
 
     # ---------------- end-to-end arm: the public drop-in call with host buffers -----------------

@@ -22,11 +22,15 @@ static_assert(sizeof(PackedRating) == 12, "rating triple must be 12 bytes");
 struct mfrec_ctx {
     int device = 0;
     int sm_count = 0;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0;         // largest dynamic shared memory one CTA may ask for
+    size_t smem_per_sm = 0;
+    int coop_launch = 0;           // cudaDevAttrCooperativeLaunch
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     double *se_scratch = nullptr;  // per-CTA squared-error partials of one epoch
     size_t se_cap = 0;
+    int32_t *ticks = nullptr;      // per column block hand-over counters of the running SGD launch
+    size_t ticks_cap = 0;
     std::string err;
 };
 

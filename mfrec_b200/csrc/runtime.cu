@@ -53,6 +53,8 @@ extern "C" int mfrec_ctx_create(int device, mfrec_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    ctx->coop_launch = prop.cooperativeLaunch;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
@@ -71,6 +73,7 @@ extern "C" void mfrec_ctx_destroy(mfrec_ctx *ctx)
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->se_scratch) cudaFree(ctx->se_scratch);
+    if (ctx->ticks) cudaFree(ctx->ticks);
     delete ctx;
 }
 

@@ -5,27 +5,32 @@
 // --------------------------------------------
 // Two updates commute iff they share neither the user row nor the item row.  pack.cu cuts the
 // rating matrix into B x B blocks (x G item slabs) and every block into W x W buckets.
-// One epoch = B kernel launches per slab ("sub-epochs").  In sub-epoch s, CTA rb owns
+// One epoch = B sub-epochs per slab.  In sub-epoch s, CTA rb owns
 //   row block rb  x  column block (rb + s) mod B            (a Latin square: no two CTAs share
 //                                                            a row block or a column block)
 // and inside the CTA, in phase p, warp w owns
 //   row group w   x  column group (w + p) mod W             (again a Latin square)
-// with a __syncthreads() between phases.  So at any instant all B*W warps of the grid work on
-// pairwise disjoint users and items: no atomics, no locks, deterministic for a given layout.
-// Any serial replay that visits (sub-epoch, CTA, phase, warp, bucket order) nested in that
-// order is an equivalent sequential SGD order; tests replay exactly that with the CPU oracle.
+// So at any instant all B*W warps of the grid work on pairwise disjoint users and items: no
+// atomics, no locks, deterministic for a given layout.  Any serial replay that visits
+// (sub-epoch, CTA, phase, warp, bucket order) nested in that order is an equivalent sequential
+// SGD order; tests replay exactly that with the CPU oracle.
 //
-// Data movement per CTA
+// One persistent cooperative launch runs all B sub-epochs of a slab: column blocks pass from CTA
+// to CTA through release/acquire counters in global memory, column groups from warp to warp
+// through counters in shared memory (see sgd_block_kernel), so there is no grid-wide or
+// CTA-wide barrier on the critical path.
+//
+// Data movement per CTA and sub-epoch
 //   * the column block's Q rows (contiguous in packed-id order) are pulled into shared memory
 //     once with cp.async.bulk (TMA, mbarrier complete_tx) and written back once;
 //   * each warp's W buckets are stored back to back, so the warp streams ONE contiguous run of
 //     12-byte ratings through a private 4-stage shared-memory ring filled by cp.async.bulk;
 //   * P rows are fetched with cp.async (16 bytes per lane, coalesced 512 B per row at k = 128)
-//     into an 8-deep shared-memory ring, 8 ratings ahead of the consumer and across phase
+//     into a 16-deep shared-memory ring, 16 ratings ahead of the consumer and across phase
 //     boundaries; they are tracked by cp.async groups, not by the register scoreboard, so a
 //     wait never stalls on the newest request; updated rows go back with 128-bit stores;
-//   * the dot product is a 5-step warp-shuffle butterfly; all arithmetic is fp32, the epoch's
-//     sum of squared errors is accumulated in fp64.
+//   * the dot product's cross-lane sum is one REDUX in 32-bit fixed point; all other arithmetic
+//     is fp32, the epoch's sum of squared errors is accumulated in fp64.
 //
 // Sequential schedule (MFREC_SCHED_SEQUENTIAL): one thread, fp64, no FMA contraction, the
 // reference's exact order on the reference's own [k][n] layout.  Bit-exact with the reference
@@ -52,8 +57,10 @@ struct SgdParams {
     const int32_t *bucket_cnt;
     const int32_t *col_start;
     float *Q, *ib, *P, *ub;
-    double *se_part;  // [B] partial sums of this launch
-    int B, W, slab, s;
+    double *se_part;  // [B] per-CTA sums of this launch
+    int32_t *ticks;   // [B] sub-epochs finished on each column block in this launch, or null
+                      // (null: no hand-over, the launch must cover exactly one sub-epoch)
+    int B, W, slab, s_begin, s_end;
     int tile_rows;    // shared-memory rows reserved for the Q tile
     float lr, Ku, Ki, Kb;
     int update_users, update_items;
@@ -171,35 +178,56 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
-// The stratified kernel.  grid = B CTAs, block = W warps.  E = kpad / 32 floats per lane.
+// The stratified kernel.  grid = B CTAs (one per SM, cooperative launch), block = W warps,
+// E = kpad / 32 floats per lane.  One launch runs sub-epochs [s_begin, s_end) of one item slab.
 //
-// Every warp walks ONE contiguous stream of packed ratings (its W buckets, stored
+// CTA level: in sub-epoch s CTA rb owns column block cb = (rb + s) mod B.  Its previous owner was
+// CTA rb + 1 in sub-epoch s - 1, so instead of a grid-wide barrier (a kernel boundary) between
+// sub-epochs the column block is handed over through a per-block counter in global memory:
+// the owner writes its Q tile back, fences, and releases ticks[cb] = s + 1; the next owner
+// acquires ticks[cb] == s before it pulls the tile.  The result is the same as with one launch per
+// sub-epoch (the serial replay order is unchanged), but a slow CTA only delays the two CTAs that
+// depend on it, not the whole grid.
+//
+// Warp level: the same hand-over inside the CTA.  In phase p warp w owns column group
+// (w + p) mod W, last used by warp w + 1 in phase p - 1; a shared-memory counter per warp
+// replaces the CTA-wide barrier between phases.
+//
+// Every warp walks ONE contiguous stream of packed ratings per sub-epoch (its W buckets, stored
 // back to back) with three cursors:
 //   load cursor     : cp.async.bulk chunks of kChunk ratings into a kStages-deep ring
 //   prefetch cursor : kDepth ratings ahead of the consumer, cp.async of the P row (and user
 //                     bias) of each upcoming rating into a kDepth-deep shared-memory ring;
 //                     P rows of a row group belong to this warp for the whole launch, so the
-//                     cursor may run across phase boundaries
-//   consume cursor  : the update itself; __syncthreads() at every bucket (= phase) end
-// Stale-prefetch hazard: the row of rating x is fetched while ratings x-kDepth .. x-1 are still
-// being applied.  Inside a bucket equal users are adjacent (sorted) and are served from
-// registers; across a bucket boundary a lane-distributed history of the last kDepth users
-// detects the rare repeat and re-reads the row from global memory.
+//                     cursor runs across phase boundaries
+//   consume cursor  : the update itself
+// Stale-prefetch hazard: the row of rating x is fetched while up to kDepth + 3 earlier ratings are
+// still being applied.  Equal adjacent users are served from registers; otherwise a
+// lane-distributed history of the users of the last 32 stream positions detects a repeat inside
+// the window and the row is re-read from global memory.
 // ------------------------------------------------------------------------------------------
-template <int E, int KERNEL>
-__global__ void __launch_bounds__(512)
+template <int E, int KERNEL, bool TIMING>
+__global__ void __launch_bounds__(512, 1)
 sgd_block_kernel(const SgdParams prm)
 {
     constexpr int KPAD = E * 32;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = prm.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = blockIdx.x;
-    const int cbl = (rb + prm.s) % prm.B;
-    const int cbg = prm.slab * prm.B + cbl;
-    const int cs = prm.col_start[cbg * W];
-    const int nq = prm.col_start[(cbg + 1) * W] - cs;
 
     // shared-memory carve-up (every section is a multiple of 16 bytes)
     float *Qs = reinterpret_cast<float *>(smem_raw);
@@ -211,6 +239,7 @@ sgd_block_kernel(const SgdParams prm)
     int64_t *boff = reinterpret_cast<int64_t *>(bars + 1 + kStages * W);
     int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
     double *se_s = reinterpret_cast<double *>(bcnt + ((W * W + 1) & ~1));
+    volatile int32_t *phase_done = reinterpret_cast<volatile int32_t *>(se_s + W);
 
     float *prow = prow_all + (size_t)warp * kDepth * KPAD;
     float *pbias = pbias_all + warp * kDepth;
@@ -221,80 +250,9 @@ sgd_block_kernel(const SgdParams prm)
     if (threadIdx.x == 0) {
         mbar_init(tile_bar, 1);
         for (int i = 0; i < kStages * W; ++i) mbar_init(bars + 1 + i, 1);
+        for (int i = 0; i < W; ++i) phase_done[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // this CTA's W*W bucket descriptors (worker-major: index w * W + phase) + end sentinel
-    const int64_t bucket_base = (((int64_t)prm.slab * prm.B + rb) * prm.B + cbl) * W * W;
-    for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
-        boff[i] = prm.bucket_off[bucket_base + i];
-        if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
-    }
-    __syncthreads();
-
-    // Q tile: one elected thread issues the bulk copies, everyone waits on the mbarrier
-    if (threadIdx.x == 0 && nq > 0) {
-        const uint32_t total = (uint32_t)nq * KPAD * 4u;
-        mbar_expect_tx(tile_bar, total);
-        const char *src = reinterpret_cast<const char *>(prm.Q + (size_t)cs * KPAD);
-        char *dst = reinterpret_cast<char *>(Qs);
-        for (uint32_t o = 0; o < total; o += 32768u)
-            bulk_g2s(dst + o, src + o, min(32768u, total - o), tile_bar);
-    }
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) ibs[i] = prm.ib[cs + i];
-
-    // ---- this warp's stream ---------------------------------------------------------------
-    const int64_t S0 = boff[warp * W];
-    const uint32_t slen = (uint32_t)(boff[warp * W + W] - S0);   // multiple of 4 (padded buckets)
-    const uint32_t nchunks = (slen + kChunk - 1) / kChunk;
-    const uint32_t nquads = slen / 4;
-    const PackedRating *stream = prm.packed + S0;
-    const int32_t *cnt_w = bcnt + warp * W;
-    const int64_t *off_w = boff + warp * W;
-    uint32_t issued = 0;
-
-    auto issue_chunk = [&](uint32_t c) {
-        if (lane == 0) {
-            const uint32_t cnt = min((uint32_t)kChunk, slen - c * kChunk);
-            uint64_t *bar = my_bar + (c % kStages);
-            mbar_expect_tx(bar, cnt * 12u);
-            bulk_g2s(ring + (c % kStages) * kChunk, stream + (size_t)c * kChunk, cnt * 12u, bar);
-        }
-    };
-    while (issued < nchunks && issued < (uint32_t)kStages) issue_chunk(issued++);
-
-    // Prefetch cursor: walks the stream one QUAD (4 positions = 48 bytes, 16-byte aligned) at a
-    // time, padding entries included (they name packed user 0, a valid row, and are never
-    // consumed).  One cp.async group per quad, so group index == quad index and
-    // cp.async.wait_group<kQuadsAhead-1> at quad x guarantees its four rows have landed once
-    // the cursor stands at x + kQuadsAhead.  Quads past the end commit empty groups.
-    uint32_t pfq = 0;
-    auto prefetch_quads_to = [&](uint32_t target) {
-#pragma unroll 1
-        while (pfq < target) {
-            if (pfq < nquads) {
-                const uint32_t pos = pfq * 4;
-                if ((pos % kChunk) == 0) {   // first touch of a chunk: wait for its bulk copy
-                    const uint32_t c = pos / kChunk;
-                    mbar_wait(my_bar + (c % kStages), (c / kStages) & 1u);
-                }
-                const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (pos % kRing));
-                const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
-                const int us[4] = {a.x, a.w, b.z, c2.y};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint32_t slot = (pos + t) % kDepth;
-                    row_cp_async<E>(prow + slot * KPAD, prm.P + (size_t)us[t] * KPAD, lane);
-                    if (lane == 0) cp_async<4>(pbias + slot, prm.ub + us[t]);
-                }
-            }
-            cp_async_commit();
-            ++pfq;
-        }
-    };
-    prefetch_quads_to(kQuadsAhead);
-
-    if (nq > 0) mbar_wait(tile_bar, 0);
-    __syncthreads();
 
     const float lr = prm.lr;
     const bool upd_u = prm.update_users != 0, upd_i = prm.update_items != 0;
@@ -305,130 +263,258 @@ sgd_block_kernel(const SgdParams prm)
     const bool upd_bu = (KERNEL == MFREC_KERNEL_LINEAR) || upd_u;
     const bool upd_bi = (KERNEL == MFREC_KERNEL_LINEAR) || upd_i;
     const float fx_scale = prm.fx_scale, fx_inv = prm.fx_inv;
-    double se = 0.0;       // fp64 total of fp32 per-bucket partials
+    float *const P_lane = prm.P + lane * Frag<E>::V;   // this lane's column of every P row
+
+    double se = 0.0;          // fp64 total of fp32 per-bucket partials, over the whole launch
+    uint32_t chunk_seq = 0;   // chunks this warp has pulled so far (ring stage + mbarrier parity)
+    int hist = -1;            // user consumed at the stream position == lane (mod 32)
     // opt-in section timer (cycles per warp): 0 bookkeeping + prefetch issue, 1 cp.async wait,
-    // 2 quad load, 3 updates, 6 phase barrier
+    // 2 quad load, 3 updates, 4 phase hand-over wait, 5 sub-epoch set-up (ticket + tile), 6 tail
     unsigned long long tsec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool timing = prm.timing != nullptr;
-    long long tmark = timing ? clock64() : 0;
+    long long tmark = 0;
+    if constexpr (TIMING) tmark = clock64();
     auto lap = [&](int k) {
-        if (timing) {
+        if constexpr (TIMING) {
             const long long now = clock64();
             tsec[k] += (unsigned long long)(now - tmark);
             tmark = now;
         }
     };
-    Frag<E> cp, cq;        // current user row / item row (post-update values)
-#pragma unroll
-    for (int e = 0; e < E; ++e) { cp.x[e] = 0.f; cq.x[e] = 0.f; }
-    float cbu = 0.f, cbi = 0.f, se_f = 0.f;
-    int prev_u = -1, prev_i = -1, hist = -1;
-    uint32_t cons_chunk = 0;
 
-    // one rating: pos = stream position, (u, i, r) the triple
-    auto update_one = [&](uint32_t pos, int u, int it, float r) {
-        const uint32_t slot = pos % kDepth;
-        const bool same_u = (u == prev_u);
-        Frag<E> pu;
-        float bu;
-        if (!same_u && __any_sync(0xffffffffu, hist == u)) {
-            // the row was updated after its prefetch was issued (the user repeats across a bucket
-            // boundary inside the prefetch window): re-read it from global memory
-            frag_load<E>(pu, prm.P + (size_t)u * KPAD, lane);
-            bu = prm.ub[u];
-        } else {
-            frag_load<E>(pu, prow + slot * KPAD, lane);
-            bu = pbias[slot];
-        }
-#pragma unroll
-        for (int e = 0; e < E; ++e) pu.x[e] = same_u ? cp.x[e] : pu.x[e];
-        bu = same_u ? cbu : bu;
-        float *qrow = Qs + (size_t)(it - cs) * KPAD;
-        if (it != prev_i) {   // otherwise the item row is still in registers
-            frag_load<E>(cq, qrow, lane);
-            cbi = ibs[it - cs];
-        }
-        float part = 0.f;
-#pragma unroll
-        for (int e = 0; e < E; ++e) part = fmaf(pu.x[e], cq.x[e], part);
-        // deterministic warp reduction in 32-bit fixed point: one REDUX instead of a 5-level
-        // shuffle butterfly; integer addition is associative, so the result does not depend on
-        // lane order.  fx_scale is a power of two chosen from max |rating| (see sgd_epoch).
-        const float dot = (float)__reduce_add_sync(0xffffffffu, __float2int_rn(part * fx_scale)) * fx_inv;
-        const float pred = cbi + bu + dot;
-        float err, grad;
-        if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
-            err = r - pred;
-            grad = err;
-        } else {
-            const float sig = 1.f / (1.f + expf(-pred));
-            err = r - (1.f + 4.f * sig);
-            grad = err * sig * (1.f - sig) * 4.f;
-        }
-        se_f = fmaf(err, err, se_f);
-        const float gl = lr * grad;
-        cbu = upd_bu ? fmaf(a_b, bu, gl) : bu;
-        cbi = upd_bi ? fmaf(a_b, cbi, gl) : cbi;
-        const float gli = upd_i ? gl : 0.f, glu = upd_u ? gl : 0.f;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const float pe = pu.x[e], qe = cq.x[e];
-            cp.x[e] = fmaf(glu, qe, a_u * pe);
-            cq.x[e] = fmaf(gli, pe, a_i * qe);
-        }
-        prev_u = u;
-        prev_i = it;
-        if (lane == (int)slot) hist = u;
-        frag_store<E>(cq, qrow, lane);
-        frag_store<E>(cp, prm.P + (size_t)u * KPAD, lane);
-        if (lane == 0) {
-            ibs[it - cs] = cbi;
-            prm.ub[u] = cbu;
-        }
-    };
+    for (int s = prm.s_begin; s < prm.s_end; ++s) {
+        const int step = s - prm.s_begin;
+        const int cbl = (rb + s) % prm.B;
+        const int cbg = prm.slab * prm.B + cbl;
+        const int cs = prm.col_start[cbg * W];
+        const int nq = prm.col_start[(cbg + 1) * W] - cs;
 
-    for (int p = 0; p < W; ++p) {
-        const uint32_t n = (uint32_t)cnt_w[p];
-        const uint32_t rel0 = (uint32_t)(off_w[p] - S0);
-        se_f = 0.f;
-#pragma unroll 1
-        for (uint32_t i = 0; i < n; i += 4) {
-            const uint32_t rel = rel0 + i;   // quad aligned
-            if (rel / kChunk != cons_chunk) {
-                cons_chunk = rel / kChunk;   // every earlier chunk's stage is free again
-                __syncwarp();
-                while (issued < nchunks && issued < cons_chunk + kStages) issue_chunk(issued++);
+        // this CTA's W*W bucket descriptors (worker-major: index w * W + phase) + end sentinel
+        const int64_t bucket_base = (((int64_t)prm.slab * prm.B + rb) * prm.B + cbl) * W * W;
+        for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
+            boff[i] = prm.bucket_off[bucket_base + i];
+            if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
+        }
+        // Q tile: one elected thread takes the column block over and issues the bulk copies
+        if (threadIdx.x == 0) {
+            if (prm.ticks) {
+                while (ld_acquire_gpu(prm.ticks + cbl) < s) __nanosleep(64);
+                // order the acquire (generic proxy) before the bulk reads (async proxy)
+                asm volatile("fence.proxy.async;" ::: "memory");
             }
-            prefetch_quads_to(rel / 4 + kQuadsAhead);
-            lap(0);
-            cp_async_wait<kQuadsAhead - 1>();   // the four rows of this quad have landed
-            __syncwarp();                       // ... and lane 0's bias copies / stores are visible
-            lap(1);
-            const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (rel % kRing));
-            const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
-            const uint32_t nv = n - i;   // valid ratings in this quad (>= 1; >= 4 means all)
-            lap(2);
-            update_one(rel, a.x, a.y, __int_as_float(a.z));
-            if (nv > 1) update_one(rel + 1, a.w, b.x, __int_as_float(b.y));
-            if (nv > 2) update_one(rel + 2, b.z, b.w, __int_as_float(c2.x));
-            if (nv > 3) update_one(rel + 3, c2.y, c2.z, __int_as_float(c2.w));
-            lap(3);
+            if (nq > 0) {
+                const uint32_t total = (uint32_t)nq * KPAD * 4u;
+                mbar_expect_tx(tile_bar, total);
+                const char *src = reinterpret_cast<const char *>(prm.Q + (size_t)cs * KPAD);
+                char *dst = reinterpret_cast<char *>(Qs);
+                for (uint32_t o = 0; o < total; o += 32768u)
+                    bulk_g2s(dst + o, src + o, min(32768u, total - o), tile_bar);
+            }
         }
-        se += (double)se_f;
-        prev_i = -1;       // the column group changes hands: never forward Q across a phase
-        __syncthreads();   // phase boundary
+        __syncthreads();   // descriptors visible; mbarrier init visible (first step)
+
+        // ---- this warp's stream ---------------------------------------------------------------
+        const int64_t S0 = boff[warp * W];
+        const uint32_t slen = (uint32_t)(boff[warp * W + W] - S0);   // multiple of 4 (padded buckets)
+        const uint32_t nchunks = (slen + kChunk - 1) / kChunk;
+        const uint32_t nquads = slen / 4;
+        const PackedRating *stream = prm.packed + S0;
+        const int32_t *cnt_w = bcnt + warp * W;
+        const int64_t *off_w = boff + warp * W;
+        uint32_t issued = 0;
+
+        auto issue_chunk = [&](uint32_t c) {
+            if (lane == 0) {
+                const uint32_t cnt = min((uint32_t)kChunk, slen - c * kChunk);
+                const uint32_t g = chunk_seq + c;
+                uint64_t *bar = my_bar + (g % kStages);
+                mbar_expect_tx(bar, cnt * 12u);
+                bulk_g2s(ring + (g % kStages) * kChunk, stream + (size_t)c * kChunk, cnt * 12u, bar);
+            }
+        };
+        while (issued < nchunks && issued < (uint32_t)kStages) issue_chunk(issued++);
+
+        // Prefetch cursor: walks the stream one QUAD (4 positions = 48 bytes, 16-byte aligned) at a
+        // time, padding entries included (they name packed user 0, a valid row, and are never
+        // consumed).  One cp.async group per quad, so group index == quad index and
+        // cp.async.wait_group<kQuadsAhead-1> at quad x guarantees its four rows have landed once
+        // the cursor stands at x + kQuadsAhead.  Quads past the end commit empty groups.
+        uint32_t pfq = 0;
+        auto prefetch_quads_to = [&](uint32_t target) {
+#pragma unroll 1
+            while (pfq < target) {
+                if (pfq < nquads) {
+                    const uint32_t pos = pfq * 4;
+                    const uint32_t g = chunk_seq + pos / kChunk;
+                    if ((pos % kChunk) == 0)   // first touch of a chunk: wait for its bulk copy
+                        mbar_wait(my_bar + (g % kStages), (g / kStages) & 1u);
+                    const PackedRating *src = ring + (g % kStages) * kChunk + (pos % kChunk);
+                    const int4 *qsrc = reinterpret_cast<const int4 *>(src);
+                    const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
+                    const int us[4] = {a.x, a.w, b.z, c2.y};
+                    const uint32_t slot0 = pos % kDepth;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float *dst = prow + (slot0 + t) * KPAD + lane * Frag<E>::V;
+                        const float *gsrc = P_lane + (size_t)us[t] * KPAD;
+#pragma unroll
+                        for (int c = 0; c < Frag<E>::NV; ++c)
+                            cp_async<Frag<E>::V * 4>(dst + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
+                    }
+                    if (lane < 4) cp_async<4>(pbias + slot0 + lane, prm.ub + src[lane].u);
+                }
+                cp_async_commit();
+                ++pfq;
+            }
+        };
+        prefetch_quads_to(kQuadsAhead);
+
+        if (nq > 0) mbar_wait(tile_bar, step & 1);
+        // item biases of the block: L2 loads (another SM wrote them; L1 may hold a stale line)
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) ibs[i] = __ldcg(prm.ib + cs + i);
+        __syncthreads();   // tile + biases in place
+        lap(5);
+
+        Frag<E> cp, cq;        // current user row / item row (post-update values)
+#pragma unroll
+        for (int e = 0; e < E; ++e) { cp.x[e] = 0.f; cq.x[e] = 0.f; }
+        float cbu = 0.f, cbi = 0.f, se_f = 0.f;
+        int prev_u = -1, prev_i = -1;
+
+        // one rating: pos = stream position, (u, it, r) the triple
+        auto update_one = [&](uint32_t pos, int u, int it, float r) {
+            const uint32_t slot = pos % kDepth;
+            Frag<E> pu;
+            float bu;
+            const bool stale = __any_sync(FULL, hist == u);
+            if (u == prev_u) {                 // adjacent ratings of one user: row is in registers
+#pragma unroll
+                for (int e = 0; e < E; ++e) pu.x[e] = cp.x[e];
+                bu = cbu;
+            } else if (stale) {
+                // the row was updated after its prefetch was issued: re-read it from global memory
+                frag_load<E>(pu, prm.P + (size_t)u * KPAD, lane);
+                bu = prm.ub[u];
+            } else {
+                frag_load<E>(pu, prow + slot * KPAD, lane);
+                bu = pbias[slot];
+            }
+            float *qrow = Qs + (size_t)(it - cs) * KPAD;
+            if (it != prev_i) {   // otherwise the item row is still in registers
+                frag_load<E>(cq, qrow, lane);
+                cbi = ibs[it - cs];
+            }
+            float part = pu.x[0] * cq.x[0];
+#pragma unroll
+            for (int e = 1; e < E; ++e) part = fmaf(pu.x[e], cq.x[e], part);
+            // deterministic warp reduction in 32-bit fixed point: one REDUX instead of a 5-level
+            // shuffle butterfly; integer addition is associative, so the result does not depend on
+            // lane order.  fx_scale is a power of two chosen from max |rating| (see sgd_epoch).
+            const float dot = (float)__reduce_add_sync(FULL, __float2int_rn(part * fx_scale)) * fx_inv;
+            const float pred = dot + (cbi + bu);
+            float err, grad;
+            if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
+                err = r - pred;
+                grad = err;
+            } else {
+                const float sig = 1.f / (1.f + expf(-pred));
+                err = r - (1.f + 4.f * sig);
+                grad = err * sig * (1.f - sig) * 4.f;
+            }
+            se_f = fmaf(err, err, se_f);
+            const float gl = lr * grad;
+            cbu = upd_bu ? fmaf(a_b, bu, gl) : bu;
+            cbi = upd_bi ? fmaf(a_b, cbi, gl) : cbi;
+            const float gli = upd_i ? gl : 0.f, glu = upd_u ? gl : 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const float pe = pu.x[e], qe = cq.x[e];
+                cp.x[e] = fmaf(glu, qe, a_u * pe);
+                cq.x[e] = fmaf(gli, pe, a_i * qe);
+            }
+            prev_u = u;
+            prev_i = it;
+            if (lane == (int)(pos & 31u)) hist = u;
+            frag_store<E>(cq, qrow, lane);
+            frag_store<E>(cp, prm.P + (size_t)u * KPAD, lane);
+            if (lane == 0) {
+                ibs[it - cs] = cbi;
+                prm.ub[u] = cbu;
+            }
+        };
+
+        const int32_t done_base = step * W;
+        for (int p = 0; p < W; ++p) {
+            const uint32_t n = (uint32_t)cnt_w[p];
+            const uint32_t rel0 = (uint32_t)(off_w[p] - S0);
+            if (p > 0) {
+                // column group (warp + p) mod W comes from warp + 1, which used it in phase p - 1
+                const volatile int32_t *flag = phase_done + (warp + 1 == W ? 0 : warp + 1);
+                if (lane == 0) {
+                    while (*flag < done_base + p) { }
+                    __threadfence_block();
+                }
+                __syncwarp();
+                lap(4);
+            }
+            se_f = 0.f;
+#pragma unroll 1
+            for (uint32_t i = 0; i < n; i += 4) {
+                const uint32_t rel = rel0 + i;   // quad aligned
+                const uint32_t c_here = rel / kChunk;
+                if (c_here + kStages > issued && issued < nchunks) {
+                    // every chunk before c_here has been consumed: its stage is free again
+                    __syncwarp();
+                    while (issued < nchunks && issued < c_here + kStages) issue_chunk(issued++);
+                }
+                prefetch_quads_to(rel / 4 + kQuadsAhead);
+                lap(0);
+                cp_async_wait<kQuadsAhead - 1>();   // the four rows of this quad have landed
+                __syncwarp();                       // ... and the bias copies / lane 0's stores are visible
+                lap(1);
+                const uint32_t g = chunk_seq + c_here;
+                const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (g % kStages) * kChunk + (rel % kChunk));
+                const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
+                const uint32_t nv = n - i;   // valid ratings in this quad (>= 1; >= 4 means all)
+                lap(2);
+                update_one(rel, a.x, a.y, __int_as_float(a.z));
+                if (nv > 1) update_one(rel + 1, a.w, b.x, __int_as_float(b.y));
+                if (nv > 2) update_one(rel + 2, b.z, b.w, __int_as_float(c2.x));
+                if (nv > 3) update_one(rel + 3, c2.y, c2.z, __int_as_float(c2.w));
+                lap(3);
+            }
+            se += (double)se_f;
+            prev_i = -1;       // the column group changes hands: never forward Q across a phase
+            // hand the column group over: Q rows / item biases written above, then the counter
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                phase_done[warp] = done_base + p + 1;
+            }
+        }
+        cp_async_wait<0>();
+        chunk_seq += nchunks;
+        __syncthreads();   // every warp is done with the tile
+        lap(4);
+        // write the Q tile back and pass the column block on
+        {
+            const int nvec = nq * KPAD / 4;
+            float4 *dst = reinterpret_cast<float4 *>(prm.Q + (size_t)cs * KPAD);
+            const float4 *srcv = reinterpret_cast<const float4 *>(Qs);
+            for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
+            for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.ib[cs + i] = ibs[i];
+        }
+        if (prm.ticks) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_gpu(prm.ticks + cbl, s + 1);
+        } else {
+            __syncthreads();
+        }
         lap(6);
     }
-    cp_async_wait<0>();
-    if (timing && lane == 0)
-        for (int k2 = 0; k2 < 8; ++k2) prm.timing[((size_t)rb * W + warp) * 8 + k2] = tsec[k2];
-    // write the Q tile back
-    {
-        const int nvec = nq * KPAD / 4;
-        float4 *dst = reinterpret_cast<float4 *>(prm.Q + (size_t)cs * KPAD);
-        const float4 *srcv = reinterpret_cast<const float4 *>(Qs);
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
-        for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.ib[cs + i] = ibs[i];
+    if constexpr (TIMING) {
+        if (prm.timing && lane == 0)
+            for (int k2 = 0; k2 < 8; ++k2) prm.timing[((size_t)rb * W + warp) * 8 + k2] = tsec[k2];
     }
     if (lane == 0) se_s[warp] = se;
     __syncthreads();
@@ -516,24 +602,59 @@ size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W)
     b += (size_t)(W * W + 1) * 8;                          // bucket offsets
     b += (size_t)((W * W + 1) & ~1) * 4;                   // bucket counts
     b += (size_t)W * 8;                                    // per-warp squared error
+    b += (size_t)((W + 3) & ~3) * 4;                       // per-warp phase counters
     return b + 128;
 }
 
 namespace {
 
-template <int E>
-int launch_sgd(mfrec_ctx *ctx, int kernel, const SgdParams &prm, size_t smem)
+template <int E, bool TIMING>
+int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative)
 {
-    auto fn = kernel == MFREC_KERNEL_LINEAR ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR>
-                                            : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC>;
-    static size_t configured[2] = {0, 0};  // per instantiation (E) and kernel
+    auto fn = kernel == MFREC_KERNEL_LINEAR ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING>
+                                            : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING>;
+    static size_t configured[2] = {0, 0};  // per instantiation (E, TIMING) and kernel
     if (configured[kernel] < smem) {
         MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[kernel] = smem;
     }
-    fn<<<prm.B, prm.W * 32, smem, ctx->stream>>>(prm);
-    MF_LAUNCH_CHECK(ctx);
+    if (cooperative) {
+        // all B CTAs must be resident at once: they wait on one another's column blocks
+        void *args[] = {(void *)&prm};
+        MF_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fn, dim3(prm.B), dim3(prm.W * 32), args, smem,
+                                                 ctx->stream));
+        ctx->launches += 1;
+    } else {
+        fn<<<prm.B, prm.W * 32, smem, ctx->stream>>>(prm);
+        MF_LAUNCH_CHECK(ctx);
+    }
     return MFREC_OK;
+}
+
+template <bool TIMING>
+int launch_sgd_kpad(mfrec_ctx *ctx, int kpad, int kernel, SgdParams &prm, size_t smem, bool cooperative)
+{
+    switch (kpad) {
+    case 32: return launch_sgd<1, TIMING>(ctx, kernel, prm, smem, cooperative);
+    case 64: return launch_sgd<2, TIMING>(ctx, kernel, prm, smem, cooperative);
+    case 128: return launch_sgd<4, TIMING>(ctx, kernel, prm, smem, cooperative);
+    case 256: return launch_sgd<8, TIMING>(ctx, kernel, prm, smem, cooperative);
+    default: return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", kpad);
+    }
+}
+
+// can B CTAs of W warps with `smem` bytes each be co-resident (one wave)?
+bool sgd_fits_one_wave(mfrec_ctx *ctx, int B, int W, size_t smem)
+{
+    // one CTA per SM is always possible when the shared memory fits (<= 512 threads, <= 128
+    // registers per thread by __launch_bounds__); more than sm_count CTAs would need two per SM
+    if (B <= ctx->sm_count) return smem <= ctx->smem_optin;
+    const size_t per_sm = ctx->smem_per_sm;
+    const int by_smem = (int)(per_sm / (smem + 1024));
+    const int by_threads = 2048 / (W * 32);
+    const int by_regs = 65536 / (128 * W * 32);
+    const int per = std::min(by_smem, std::min(by_threads, by_regs));
+    return (int64_t)per * ctx->sm_count >= B;
 }
 
 }  // namespace
@@ -550,13 +671,30 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     if (slab >= r->G) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: slab=%d of %d", slab, r->G);
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     const int s_lo = slab < 0 ? 0 : slab, s_hi = slab < 0 ? r->G : slab + 1;
-    const int64_t nparts = (int64_t)(s_hi - s_lo) * r->B * r->B;
+    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
+    if (smem > ctx->smem_optin)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                               "mfrec_sgd_epoch: Q tile of %d rows x %d needs %zu B shared memory (> %zu); pack with more row_blocks",
+                               r->max_cb_items, m->kpad, smem, ctx->smem_optin);
+    // MFREC_SGD_LAUNCH_PER_SUBEPOCH=1 forces the fallback (one launch per sub-epoch, no hand-over)
+    static int per_subepoch_env = -1;
+    if (per_subepoch_env < 0) per_subepoch_env = getenv("MFREC_SGD_LAUNCH_PER_SUBEPOCH") ? 1 : 0;
+    const bool persistent = !per_subepoch_env && ctx->coop_launch && sgd_fits_one_wave(ctx, r->B, r->W, smem);
+    const int64_t launches = (int64_t)(s_hi - s_lo) * (persistent ? 1 : r->B);
+    const int64_t nparts = launches * r->B;
     if (ctx->se_cap < (size_t)nparts) {
         if (ctx->se_scratch) cudaFree(ctx->se_scratch);
         ctx->se_scratch = nullptr;
         ctx->se_cap = 0;
         MF_CUDA(ctx, cudaMalloc((void **)&ctx->se_scratch, (size_t)nparts * 8));
         ctx->se_cap = (size_t)nparts;
+    }
+    if (persistent && ctx->ticks_cap < (size_t)r->B) {
+        if (ctx->ticks) cudaFree(ctx->ticks);
+        ctx->ticks = nullptr;
+        ctx->ticks_cap = 0;
+        MF_CUDA(ctx, cudaMalloc((void **)&ctx->ticks, (size_t)r->B * 4));
+        ctx->ticks_cap = (size_t)r->B;
     }
     SgdParams prm;
     prm.packed = r->packed;
@@ -578,55 +716,49 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
         prm.fx_scale = ldexpf(1.f, 30 - ex);
         prm.fx_inv = ldexpf(1.f, ex - 30);
     }
-    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
-    if (smem > ctx->smem_optin)
-        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
-                               "mfrec_sgd_epoch: Q tile of %d rows x %d needs %zu B shared memory (> %zu); pack with more row_blocks",
-                               r->max_cb_items, m->kpad, smem, ctx->smem_optin);
-    // debug: MFREC_SGD_TIMING=1 prints per-section cycle counts of the first launch to stderr
+    // debug: MFREC_SGD_TIMING=1 prints per-section cycle counts of the first launches to stderr
     static int timing_env = -1;
-    if (timing_env < 0) timing_env = getenv("MFREC_SGD_TIMING") ? 1 : 0;
+    if (timing_env < 0) timing_env = getenv("MFREC_SGD_TIMING") ? 3 : 0;
     DevBuf<unsigned long long> d_timing;
     prm.timing = nullptr;
     if (timing_env) {
         MF_CUDA(ctx, d_timing.alloc((size_t)r->B * r->W * 8));
-        MF_CUDA(ctx, cudaMemsetAsync(d_timing.p, 0, (size_t)r->B * r->W * 64, ctx->stream));
         prm.timing = d_timing.p;
     }
     int64_t part = 0;
     for (int g = s_lo; g < s_hi; ++g) {
-        for (int s = 0; s < r->B; ++s) {
+        for (int s = 0; s < r->B; s += persistent ? r->B : 1) {
             prm.slab = g;
-            prm.s = s;
+            prm.s_begin = s;
+            prm.s_end = persistent ? r->B : s + 1;
+            prm.ticks = persistent ? ctx->ticks : nullptr;
             prm.se_part = ctx->se_scratch + part;
             part += r->B;
-            int rc;
-            switch (m->kpad) {
-            case 32: rc = launch_sgd<1>(ctx, kernel, prm, smem); break;
-            case 64: rc = launch_sgd<2>(ctx, kernel, prm, smem); break;
-            case 128: rc = launch_sgd<4>(ctx, kernel, prm, smem); break;
-            case 256: rc = launch_sgd<8>(ctx, kernel, prm, smem); break;
-            default: rc = mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", m->kpad);
-            }
-            MF_TRY(rc);
+            if (persistent) MF_CUDA(ctx, cudaMemsetAsync(ctx->ticks, 0, (size_t)r->B * 4, ctx->stream));
             if (timing_env) {
+                MF_CUDA(ctx, cudaMemsetAsync(d_timing.p, 0, (size_t)r->B * r->W * 64, ctx->stream));
+                MF_TRY(launch_sgd_kpad<true>(ctx, m->kpad, kernel, prm, smem, persistent));
                 std::vector<unsigned long long> h((size_t)r->B * r->W * 8);
                 MF_CUDA(ctx, cudaMemcpyAsync(h.data(), d_timing.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
                 MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                double avg[8] = {0}, mx[8] = {0};
+                double avg[8] = {0};
                 double worst_tot = 0; int worst = 0;
                 for (int c = 0; c < r->B * r->W; ++c) {
-                    double tot = 0;
-                    for (int k2 = 0; k2 < 7; ++k2) { avg[k2] += (double)h[(size_t)c * 8 + k2]; tot += (double)h[(size_t)c * 8 + k2]; }
-                    if (tot - (double)h[(size_t)c * 8 + 6] > worst_tot) { worst_tot = tot - (double)h[(size_t)c * 8 + 6]; worst = c; }
+                    double busy = 0;
+                    for (int k2 = 0; k2 < 8; ++k2) avg[k2] += (double)h[(size_t)c * 8 + k2];
+                    for (int k2 = 0; k2 < 4; ++k2) busy += (double)h[(size_t)c * 8 + k2];
+                    if (busy > worst_tot) { worst_tot = busy; worst = c; }
                 }
-                fprintf(stderr, "[sgd timing] slab %d sub-epoch %d: avg cycles/warp by section:", g, s);
+                fprintf(stderr, "[sgd timing] slab %d sub-epochs [%d,%d): avg cycles/warp by section "
+                                "(issue, cp.async wait, quad load, update, hand-over wait, set-up, tail):",
+                        g, prm.s_begin, prm.s_end);
                 for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %.0f", avg[k2] / (r->B * r->W));
                 fprintf(stderr, " | busiest warp (cta %d warp %d):", worst / r->W, worst % r->W);
                 for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %llu", h[(size_t)worst * 8 + k2]);
                 fprintf(stderr, "\n");
-                (void)mx;
-                if (s >= 2) timing_env = 0;   // three launches are enough
+                if (--timing_env == 0) prm.timing = nullptr;
+            } else {
+                MF_TRY(launch_sgd_kpad<false>(ctx, m->kpad, kernel, prm, smem, persistent));
             }
         }
     }

@@ -182,7 +182,7 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
                                      nnz_r, k, nu_r * world, ni_tot, nnz_total),
                       "parallelism": "dsgd ring of %d, item slab = %d rows x %d B per hop" % (world, b0 - a0, 4 * (R.B and M.device_ptrs()[1][2]) + 4),
                       "kernel": "train_linear_kernel",
-                      "schedule": "stratified B=%d W=%d slabs=%d launches/epoch=%d" % (R.B, R.W, R.G, R.launches_per_epoch),
+                      "schedule": "stratified B=%d W=%d slabs=%d sub-epochs/epoch=%d" % (R.B, R.W, R.G, R.launches_per_epoch),
                       "l2": "inputs exceed the 126 MB L2", "hyper": hp},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
