@@ -31,10 +31,16 @@ struct mfrec_ctx {
     size_t se_cap = 0;
     int32_t *ticks = nullptr;      // per column block hand-over counters of the running SGD launch
     size_t ticks_cap = 0;
+    int refs = 1;                  // the creator + every live mfrec_ratings / mfrec_model
     std::string err;
 };
+// Objects allocate from the context's stream-ordered pool and free into it, so they keep the
+// context alive until the last of them is destroyed.
+void mfrec_ctx_retain(mfrec_ctx *ctx);
+void mfrec_ctx_release(mfrec_ctx *ctx);
 
 struct mfrec_ratings {
+    mfrec_ctx *ctx = nullptr;
     int device = 0;
     int64_t nnz = 0;
     int32_t ni = 0, nu = 0;
@@ -58,6 +64,7 @@ struct mfrec_ratings {
 };
 
 struct mfrec_model {
+    mfrec_ctx *ctx = nullptr;
     int device = 0;
     int k = 0, kpad = 0;
     int32_t ni = 0, nu = 0;
@@ -96,11 +103,15 @@ int mfrec_set_error(mfrec_ctx *ctx, int code, const char *fmt, ...);
         MF_CUDA((ctx), cudaGetLastError());  \
     } while (0)
 
-// Device buffer that frees itself (host-side RAII for scratch allocations).
+// Device buffer that frees itself (host-side RAII for scratch allocations).  With a stream the
+// memory comes from the device's stream-ordered pool (cudaMallocAsync): no device-wide
+// synchronisation on free, and the pool keeps the pages for the next call.
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t st = nullptr;
+    bool pooled = false;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -109,11 +120,23 @@ struct DevBuf {
     {
         release();
         n = count;
+        pooled = false;
         return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+    }
+    cudaError_t alloc(size_t count, cudaStream_t stream)
+    {
+        release();
+        n = count;
+        st = stream;
+        pooled = true;
+        return cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T), stream);
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pooled) cudaFreeAsync(p, st);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -123,6 +146,17 @@ struct DevBuf {
         p = nullptr;
         return q;
     }
+};
+
+// MFREC_TRACE=1: wall-clock trace of the host-side stages of an entry point, to stderr.
+struct Tracer {
+    bool on;
+    cudaStream_t st;
+    const char *what;
+    double t0, last;
+    static double now();
+    Tracer(const char *name, cudaStream_t stream);
+    void lap(const char *stage);   // synchronises the stream when tracing, otherwise free
 };
 
 static inline int mfrec_kpad(int k)

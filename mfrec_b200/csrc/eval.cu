@@ -193,26 +193,26 @@ extern "C" int mfrec_model_predict(mfrec_ctx *ctx, const mfrec_model *m, int pre
     p.real = real;
     p.out = out;
     if (!is_device) {
-        MF_CUDA(ctx, d_pairs.alloc((size_t)n * 2));
+        MF_CUDA(ctx, d_pairs.alloc((size_t)n * 2, ctx->stream));
         MF_CUDA(ctx, cudaMemcpyAsync(d_pairs.p, pairs, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         p.pairs = d_pairs.p;
         if (real) {
-            MF_CUDA(ctx, d_real.alloc((size_t)n * rsz));
+            MF_CUDA(ctx, d_real.alloc((size_t)n * rsz, ctx->stream));
             MF_CUDA(ctx, cudaMemcpyAsync(d_real.p, real, (size_t)n * rsz, cudaMemcpyHostToDevice, st));
             p.real = d_real.p;
         }
         if (out) {
-            MF_CUDA(ctx, d_out.alloc((size_t)n));
+            MF_CUDA(ctx, d_out.alloc((size_t)n, ctx->stream));
             p.out = d_out.p;
         }
     }
-    MF_CUDA(ctx, d_bad.alloc(1));
+    MF_CUDA(ctx, d_bad.alloc(1, ctx->stream));
     MF_CUDA(ctx, cudaMemsetAsync(d_bad.p, 0, 4, st));
     const int warps_per_block = 8;
     int grid = (int)std::min<int64_t>(ceil_div64(n, warps_per_block), (int64_t)ctx->sm_count * 16);
     if (stats_out) {
-        MF_CUDA(ctx, d_part.alloc((size_t)grid * 3));
-        MF_CUDA(ctx, d_stats.alloc(4));
+        MF_CUDA(ctx, d_part.alloc((size_t)grid * 3, ctx->stream));
+        MF_CUDA(ctx, d_stats.alloc(4, ctx->stream));
     }
     p.Q = m->Q; p.ib = m->ib; p.P = m->P; p.ub = m->ub;
     p.user_perm = m->user_perm; p.item_perm = m->item_perm;
@@ -308,11 +308,11 @@ extern "C" int mfrec_bias_stats(mfrec_ctx *ctx, const int32_t *ratings_index, co
     DevBuf<int32_t> d_idx, cnt_i, cnt_u, bad;
     DevBuf<double> d_r, acc_i, acc_u, part;
     const int grid = ctx->sm_count * 8;
-    MF_CUDA(ctx, d_idx.alloc((size_t)nnz * 2));
-    MF_CUDA(ctx, d_r.alloc((size_t)nnz));
-    MF_CUDA(ctx, cnt_i.alloc(ni)); MF_CUDA(ctx, cnt_u.alloc(nu));
-    MF_CUDA(ctx, acc_i.alloc(ni)); MF_CUDA(ctx, acc_u.alloc(nu));
-    MF_CUDA(ctx, part.alloc(grid)); MF_CUDA(ctx, bad.alloc(1));
+    MF_CUDA(ctx, d_idx.alloc((size_t)nnz * 2, ctx->stream));
+    MF_CUDA(ctx, d_r.alloc((size_t)nnz, ctx->stream));
+    MF_CUDA(ctx, cnt_i.alloc(ni)); MF_CUDA(ctx, cnt_u.alloc(nu, ctx->stream));
+    MF_CUDA(ctx, acc_i.alloc(ni)); MF_CUDA(ctx, acc_u.alloc(nu, ctx->stream));
+    MF_CUDA(ctx, part.alloc(grid)); MF_CUDA(ctx, bad.alloc(1, ctx->stream));
     MF_CUDA(ctx, cudaMemcpyAsync(d_idx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemcpyAsync(d_r.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemsetAsync(cnt_i.p, 0, (size_t)ni * 4, st));

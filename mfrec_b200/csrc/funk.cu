@@ -259,13 +259,13 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
     std::vector<double> h_fr(k, 0.0);
 
     DevBuf<double> du, dv, dib, dub;
-    MF_CUDA(ctx, du.alloc((size_t)k * ni));
-    MF_CUDA(ctx, dv.alloc((size_t)k * nu));
+    MF_CUDA(ctx, du.alloc((size_t)k * ni, ctx->stream));
+    MF_CUDA(ctx, dv.alloc((size_t)k * nu, ctx->stream));
     MF_CUDA(ctx, cudaMemcpyAsync(du.p, u, (size_t)k * ni * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemcpyAsync(dv.p, v, (size_t)k * nu * 8, cudaMemcpyHostToDevice, st));
     if (variant) {
-        MF_CUDA(ctx, dib.alloc(ni));
-        MF_CUDA(ctx, dub.alloc(nu));
+        MF_CUDA(ctx, dib.alloc(ni, ctx->stream));
+        MF_CUDA(ctx, dub.alloc(nu, ctx->stream));
         MF_CUDA(ctx, cudaMemcpyAsync(dib.p, items_bias, (size_t)ni * 8, cudaMemcpyHostToDevice, st));
         MF_CUDA(ctx, cudaMemcpyAsync(dub.p, users_bias, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
     }
@@ -279,11 +279,11 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
         }
         DevBuf<int32_t> didx, dfe;
         DevBuf<double> dr, dcache, dfr;
-        MF_CUDA(ctx, didx.alloc((size_t)nnz * 2));
-        MF_CUDA(ctx, dr.alloc(nnz));
-        MF_CUDA(ctx, dcache.alloc(nnz));
-        MF_CUDA(ctx, dfe.alloc(k));
-        MF_CUDA(ctx, dfr.alloc(k));
+        MF_CUDA(ctx, didx.alloc((size_t)nnz * 2, ctx->stream));
+        MF_CUDA(ctx, dr.alloc(nnz, ctx->stream));
+        MF_CUDA(ctx, dcache.alloc(nnz, ctx->stream));
+        MF_CUDA(ctx, dfe.alloc(k, ctx->stream));
+        MF_CUDA(ctx, dfr.alloc(k, ctx->stream));
         MF_CUDA(ctx, cudaMemcpyAsync(didx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
         MF_CUDA(ctx, cudaMemcpyAsync(dr.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
         funk_sequential_kernel<<<1, 1, 0, st>>>(variant, min_epochs, min_improvement, k, f_init,
@@ -306,14 +306,14 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
             return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_train_funk: tile needs %zu B shared memory", smem);
         MF_CUDA(ctx, cudaFuncSetAttribute(funk_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DevBuf<double> cache, ufp, vfp, ibp, ubp, se_part, se_tot;
-        MF_CUDA(ctx, cache.alloc((size_t)R->packed_len + 1));
+        MF_CUDA(ctx, cache.alloc((size_t)R->packed_len + 1, ctx->stream));
         MF_CUDA(ctx, cudaMemsetAsync(cache.p, 0, ((size_t)R->packed_len + 1) * 8, st));
-        MF_CUDA(ctx, ufp.alloc(ni));
-        MF_CUDA(ctx, vfp.alloc(nu));
-        MF_CUDA(ctx, ibp.alloc(ni));
-        MF_CUDA(ctx, ubp.alloc(nu));
-        MF_CUDA(ctx, se_part.alloc((size_t)R->B * R->B));
-        MF_CUDA(ctx, se_tot.alloc(1));
+        MF_CUDA(ctx, ufp.alloc(ni, ctx->stream));
+        MF_CUDA(ctx, vfp.alloc(nu, ctx->stream));
+        MF_CUDA(ctx, ibp.alloc(ni, ctx->stream));
+        MF_CUDA(ctx, ubp.alloc(nu, ctx->stream));
+        MF_CUDA(ctx, se_part.alloc((size_t)R->B * R->B, ctx->stream));
+        MF_CUDA(ctx, se_tot.alloc(1, ctx->stream));
         const int gi = (ni + 255) / 256, gu = (nu + 255) / 256;
         gather_row_kernel<<<gi, 256, 0, st>>>(variant ? dib.p : nullptr, ni, R->item_perm, ibp.p);
         MF_LAUNCH_CHECK(ctx);

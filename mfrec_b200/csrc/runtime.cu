@@ -1,6 +1,8 @@
 // Context, error reporting, resident model and the boundary layout conversion
 // ([k][n] float64 host  <->  [n][kpad] float32 device, optionally row-permuted).
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "common.cuh"
 
@@ -16,6 +18,28 @@ int mfrec_set_error(mfrec_ctx *ctx, int code, const char *fmt, ...)
     if (ctx) ctx->err = buf;
     g_tls_error = buf;
     return code;
+}
+
+double Tracer::now()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+Tracer::Tracer(const char *name, cudaStream_t stream) : st(stream), what(name)
+{
+    static int env = -1;
+    if (env < 0) env = getenv("MFREC_TRACE") ? 1 : 0;
+    on = env != 0;
+    t0 = last = on ? now() : 0.0;
+}
+void Tracer::lap(const char *stage)
+{
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const double t = now();
+    fprintf(stderr, "[mfrec trace] %s: %-28s %8.2f ms  (t = %8.2f)\n", what, stage, t - last, t - t0);
+    last = t;
 }
 
 extern "C" int mfrec_abi_version(void) { return MFREC_B200_ABI_VERSION; }
@@ -55,6 +79,15 @@ extern "C" int mfrec_ctx_create(int device, mfrec_ctx **out)
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     ctx->coop_launch = prop.cooperativeLaunch;
+    {
+        // keep freed scratch in the pool between calls: repeated training calls then pay for
+        // cudaMalloc / cudaFree only once
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
@@ -64,9 +97,16 @@ extern "C" int mfrec_ctx_create(int device, mfrec_ctx **out)
     return MFREC_OK;
 }
 
+void mfrec_ctx_retain(mfrec_ctx *ctx) { ctx->refs += 1; }
+
 extern "C" void mfrec_ctx_destroy(mfrec_ctx *ctx)
 {
-    if (!ctx) return;
+    if (ctx) mfrec_ctx_release(ctx);
+}
+
+void mfrec_ctx_release(mfrec_ctx *ctx)
+{
+    if (--ctx->refs > 0) return;   // a ratings / model object still frees into this stream
     cudaSetDevice(ctx->device);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
@@ -173,7 +213,7 @@ int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, 
         return MFREC_OK;
     }
     DevBuf<double> stage;
-    MF_CUDA(ctx, stage.alloc((size_t)k * n));
+    MF_CUDA(ctx, stage.alloc((size_t)k * n, ctx->stream));
     MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host_kn, (size_t)k * n * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
     dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
@@ -188,7 +228,7 @@ int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, 
 {
     if (n == 0 || !host_kn) return MFREC_OK;
     DevBuf<double> stage;
-    MF_CUDA(ctx, stage.alloc((size_t)k * n));
+    MF_CUDA(ctx, stage.alloc((size_t)k * n, ctx->stream));
     dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
     rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(src_nk, k, kpad, n, perm_dev, stage.p);
     MF_LAUNCH_CHECK(ctx);
@@ -207,7 +247,7 @@ int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_
         return MFREC_OK;
     }
     DevBuf<double> stage;
-    MF_CUDA(ctx, stage.alloc((size_t)n));
+    MF_CUDA(ctx, stage.alloc((size_t)n, ctx->stream));
     MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host, (size_t)n * sizeof(double),
                                  cudaMemcpyHostToDevice, ctx->stream));
     vec_to_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(stage.p, n, perm_dev, dst);
@@ -221,7 +261,7 @@ int mfrec_download_vec(mfrec_ctx *ctx, const float *src, int32_t n, const int32_
 {
     if (n == 0 || !host) return MFREC_OK;
     DevBuf<double> stage;
-    MF_CUDA(ctx, stage.alloc((size_t)n));
+    MF_CUDA(ctx, stage.alloc((size_t)n, ctx->stream));
     vec_from_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(src, n, perm_dev, stage.p);
     MF_LAUNCH_CHECK(ctx);
     MF_CUDA(ctx, cudaMemcpyAsync(host, stage.p, (size_t)n * sizeof(double),
@@ -237,12 +277,11 @@ extern "C" void mfrec_model_destroy(mfrec_model *m)
 {
     if (!m) return;
     cudaSetDevice(m->device);
-    cudaFree(m->Q);
-    cudaFree(m->ib);
-    cudaFree(m->P);
-    cudaFree(m->ub);
-    cudaFree(m->user_perm);
-    cudaFree(m->item_perm);
+    cudaStream_t st = m->ctx->stream;
+    void *ptrs[] = {m->Q, m->ib, m->P, m->ub, m->user_perm, m->item_perm};
+    for (void *q : ptrs)
+        if (q) cudaFreeAsync(q, st);
+    mfrec_ctx_release(m->ctx);
     delete m;
 }
 
@@ -265,6 +304,8 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     mfrec_model *m = new (std::nothrow) mfrec_model();
     if (!m) return mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_model_create: host OOM");
+    m->ctx = ctx;
+    mfrec_ctx_retain(ctx);
     m->device = ctx->device;
     m->k = k;
     m->kpad = kpad;
@@ -283,13 +324,13 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
                                         "%s -> %s", #call, cudaGetErrorString(e__)));     \
     } while (0)
     // +64 floats of slack so vector loads of the last row never leave the allocation
-    MF_M(cudaMalloc((void **)&m->Q, ((size_t)ni * kpad + 64) * sizeof(float)));
-    MF_M(cudaMalloc((void **)&m->P, ((size_t)nu * kpad + 64) * sizeof(float)));
-    MF_M(cudaMalloc((void **)&m->ib, ((size_t)ni + 64) * sizeof(float)));
-    MF_M(cudaMalloc((void **)&m->ub, ((size_t)nu + 64) * sizeof(float)));
+    MF_M(cudaMallocAsync((void **)&m->Q, ((size_t)ni * kpad + 64) * sizeof(float), ctx->stream));
+    MF_M(cudaMallocAsync((void **)&m->P, ((size_t)nu * kpad + 64) * sizeof(float), ctx->stream));
+    MF_M(cudaMallocAsync((void **)&m->ib, ((size_t)ni + 64) * sizeof(float), ctx->stream));
+    MF_M(cudaMallocAsync((void **)&m->ub, ((size_t)nu + 64) * sizeof(float), ctx->stream));
     if (layout) {
-        MF_M(cudaMalloc((void **)&m->user_perm, ((size_t)nu + 1) * sizeof(int32_t)));
-        MF_M(cudaMalloc((void **)&m->item_perm, ((size_t)ni + 1) * sizeof(int32_t)));
+        MF_M(cudaMallocAsync((void **)&m->user_perm, ((size_t)nu + 1) * sizeof(int32_t), ctx->stream));
+        MF_M(cudaMallocAsync((void **)&m->item_perm, ((size_t)ni + 1) * sizeof(int32_t), ctx->stream));
         MF_M(cudaMemcpyAsync(m->user_perm, layout->user_perm, (size_t)nu * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, ctx->stream));
         MF_M(cudaMemcpyAsync(m->item_perm, layout->item_perm, (size_t)ni * sizeof(int32_t),

@@ -450,7 +450,7 @@ sgd_block_kernel(const SgdParams prm)
                 // column group (warp + p) mod W comes from warp + 1, which used it in phase p - 1
                 const volatile int32_t *flag = phase_done + (warp + 1 == W ? 0 : warp + 1);
                 if (lane == 0) {
-                    while (*flag < done_base + p) { }
+                    while (*flag < done_base + p) __nanosleep(32);
                     __threadfence_block();
                 }
                 __syncwarp();
@@ -722,7 +722,7 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     DevBuf<unsigned long long> d_timing;
     prm.timing = nullptr;
     if (timing_env) {
-        MF_CUDA(ctx, d_timing.alloc((size_t)r->B * r->W * 8));
+        MF_CUDA(ctx, d_timing.alloc((size_t)r->B * r->W * 8, ctx->stream));
         prm.timing = d_timing.p;
     }
     int64_t part = 0;
@@ -778,13 +778,13 @@ static int train_kmf_sequential(mfrec_ctx *ctx, int kernel, int nbr_epochs, int 
     cudaStream_t st = ctx->stream;
     DevBuf<double> du, dv, dr, dib, dub, drm;
     DevBuf<int32_t> didx;
-    MF_CUDA(ctx, du.alloc((size_t)k * ni));
-    MF_CUDA(ctx, dv.alloc((size_t)k * nu));
-    MF_CUDA(ctx, dr.alloc((size_t)nnz));
-    MF_CUDA(ctx, didx.alloc((size_t)nnz * 2));
-    MF_CUDA(ctx, dib.alloc(ni));
-    MF_CUDA(ctx, dub.alloc(nu));
-    MF_CUDA(ctx, drm.alloc(nbr_epochs > 0 ? nbr_epochs : 1));
+    MF_CUDA(ctx, du.alloc((size_t)k * ni, ctx->stream));
+    MF_CUDA(ctx, dv.alloc((size_t)k * nu, ctx->stream));
+    MF_CUDA(ctx, dr.alloc((size_t)nnz, ctx->stream));
+    MF_CUDA(ctx, didx.alloc((size_t)nnz * 2, ctx->stream));
+    MF_CUDA(ctx, dib.alloc(ni, ctx->stream));
+    MF_CUDA(ctx, dub.alloc(nu, ctx->stream));
+    MF_CUDA(ctx, drm.alloc(nbr_epochs > 0 ? nbr_epochs : 1, ctx->stream));
     MF_CUDA(ctx, cudaMemcpyAsync(du.p, u, (size_t)k * ni * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemcpyAsync(dv.p, v, (size_t)k * nu * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemcpyAsync(dr.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
@@ -847,10 +847,13 @@ extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k
     if (o.k_hint == 0) o.k_hint = k;
     mfrec_ratings *R = nullptr;
     mfrec_model *M = nullptr;
+    Tracer tr("train_kmf", ctx->stream);
     MF_TRY(mfrec_ratings_pack(ctx, ratings_index, ratings, 0, 0, nnz, ni, nu, nullptr, &o, &R));
+    tr.lap("pack");
     int rc = mfrec_model_create(ctx, R, k, ni, nu, u, v, items_bias, users_bias, &M);
+    tr.lap("model upload");
     DevBuf<double> d_se;
-    if (rc == MFREC_OK && d_se.alloc(nbr_epochs) != cudaSuccess)
+    if (rc == MFREC_OK && d_se.alloc(nbr_epochs, ctx->stream) != cudaSuccess)
         rc = mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_train_kmf: device OOM");
     for (int e = 0; rc == MFREC_OK && e < nbr_epochs; ++e)
         rc = mfrec_sgd_epoch(ctx, R, M, kernel, learning_rate, K_users, K_items, K_bias, update_users,
@@ -863,8 +866,11 @@ extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k
         else if (rmse_per_epoch)
             for (int e = 0; e < nbr_epochs; ++e) rmse_per_epoch[e] = sqrt(h_se[e] / (double)nnz);
     }
+    tr.lap("epochs");
     if (rc == MFREC_OK) rc = mfrec_model_read(ctx, M, u, v, items_bias, users_bias);
+    tr.lap("model download");
     mfrec_model_destroy(M);
     mfrec_ratings_destroy(R);
+    tr.lap("free");
     return rc;
 }

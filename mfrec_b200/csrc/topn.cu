@@ -188,19 +188,19 @@ extern "C" int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u,
     DevBuf<int32_t> d_users, d_rated, d_items, d_counts;
     DevBuf<double> d_scores;
     DevBuf<char> tmp;
-    MF_CUDA(ctx, keys_a.alloc((size_t)batch * nc));
-    MF_CUDA(ctx, keys_b.alloc((size_t)batch * nc));
-    MF_CUDA(ctx, d_off.alloc((size_t)batch + 1));
-    MF_CUDA(ctx, d_users.alloc(n_users));
-    MF_CUDA(ctx, d_items.alloc((size_t)batch * N));
-    MF_CUDA(ctx, d_scores.alloc((size_t)batch * N));
-    MF_CUDA(ctx, d_counts.alloc(batch));
+    MF_CUDA(ctx, keys_a.alloc((size_t)batch * nc, ctx->stream));
+    MF_CUDA(ctx, keys_b.alloc((size_t)batch * nc, ctx->stream));
+    MF_CUDA(ctx, d_off.alloc((size_t)batch + 1, ctx->stream));
+    MF_CUDA(ctx, d_users.alloc(n_users, ctx->stream));
+    MF_CUDA(ctx, d_items.alloc((size_t)batch * N, ctx->stream));
+    MF_CUDA(ctx, d_scores.alloc((size_t)batch * N, ctx->stream));
+    MF_CUDA(ctx, d_counts.alloc(batch, ctx->stream));
     MF_CUDA(ctx, cudaMemcpyAsync(d_users.p, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, st));
     const int64_t n_rated = rated_indptr ? rated_indptr[n_users] : 0;
     if (rated_indptr && n_rated > 0) {
         if (!rated_items) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn: rated_items is NULL");
-        MF_CUDA(ctx, d_indptr.alloc((size_t)n_users + 1));
-        MF_CUDA(ctx, d_rated.alloc((size_t)n_rated));
+        MF_CUDA(ctx, d_indptr.alloc((size_t)n_users + 1, ctx->stream));
+        MF_CUDA(ctx, d_rated.alloc((size_t)n_rated, ctx->stream));
         MF_CUDA(ctx, cudaMemcpyAsync(d_indptr.p, rated_indptr, ((size_t)n_users + 1) * 8, cudaMemcpyHostToDevice, st));
         MF_CUDA(ctx, cudaMemcpyAsync(d_rated.p, rated_items, (size_t)n_rated * 4, cudaMemcpyHostToDevice, st));
     }
@@ -210,7 +210,7 @@ extern "C" int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u,
     cub::DoubleBuffer<uint64_t> dk(keys_a.p, keys_b.p);
     MF_CUDA(ctx, cub::DeviceSegmentedRadixSort::SortKeysDescending(nullptr, tmp_bytes, dk, (int64_t)batch * nc, batch,
                                                                    d_off.p, d_off.p + 1, 0, 64, st));
-    MF_CUDA(ctx, tmp.alloc(tmp_bytes));
+    MF_CUDA(ctx, tmp.alloc(tmp_bytes, ctx->stream));
 
     TopnParams prm;
     prm.P = M->P; prm.Q = M->Q; prm.ib = M->ib; prm.ub = M->ub;
