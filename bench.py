@@ -178,7 +178,12 @@ def run_native(args):
                                     ClockSampler, algorithmic_bytes_per_update, measured_peaks)
 
     t_setup = time.time()
-    idx_d, r_d = gpu_synth(torch, dev, nu, ni, nnz, seed=0)
+    G = max(1, args.emulate_slabs)
+    if G > 1:
+        # debug: the per-rank work of a G-GPU weak-scaling ring on ONE GPU (G item slabs processed
+        # back to back, no exchange) -- not a bench line
+        ni = ni * G
+    idx_d, r_d = gpu_synth(torch, dev, nu, ni, nnz, seed=0, item_tiles=G)
     torch.cuda.synchronize()
     ctx = _native.Context(local)
     u0, v0 = synth.init_factors(nu, ni, k, seed=2)
@@ -186,7 +191,7 @@ def run_native(args):
     # ---------------- device-resident arm: K epochs, CUDA events on the library stream ------
     R = _native.Ratings(None, None, ni, nu, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
                         nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
-                        workers=args.workers)
+                        workers=args.workers, n_slabs=G)
     M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
     layout_desc = ("stratified B=%d W=%d sub-epochs/epoch=%d max_bucket=%d widest_column_block=%d items"
                    % (R.B, R.W, R.launches_per_epoch, R.max_bucket, R.max_cb_items))
@@ -243,7 +248,7 @@ def run_native(args):
 
     # ---------------- end-to-end arm: the public drop-in call with host buffers -----------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and G == 1:
         del M, R
         idx_h = torch.empty((nnz, 2), dtype=torch.int32, pin_memory=True)
         r_h = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
@@ -373,6 +378,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--emulate-slabs", type=int, default=1,
+                    help="debug: run one rank's share of a G-GPU ring on one GPU (no exchange)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         print("bench.py: warmup < 3 breaks the timing rules; using 3", file=sys.stderr)
