@@ -1,0 +1,114 @@
+"""``GDRecommender``: Funk-SVD trained one feature at a time
+(reference: mfrec/recommendation/gradient_descent.py:30-120, 506-545, 621-648, 769-802, 879-905).
+
+``train`` (= ``feature_training``) calls ``mfrec_b200.lib.gd_estimator``, the drop-in for the
+reference's Cython module."""
+import numpy as np
+
+from mfrec_b200.lib import gd_estimator
+from mfrec_b200.recommendation.mf import MFRecommender
+
+
+class GDRecommender(MFRecommender):
+    PARAMETERS_INDEX = {'min_epochs': 'min_epochs',
+                        'max_epochs': 'max_epochs',
+                        'min_improvement': 'min_improvement',
+                        'feature_init': 'feature_init',
+                        'learning_rate': 'learning_rate',
+                        'learning_rate_users': 'learning_rate_users',
+                        'learning_rate_items': 'learning_rate_items',
+                        'regularization_model': 'K',
+                        'regularization_users_bias': 'K2',
+                        'regularization_items_bias': 'K3',
+                        'nbr_features': 'dimensionality'}
+    NATIVE_PREDICTORS = {'predict_rating': 'predict_rating',
+                         'predict_rating_with_bias': 'predict_rating_with_bias'}
+
+    def __init__(self, nbr_users=4, nbr_items=6, parameters=False, filename=False):
+        MFRecommender.__init__(self, nbr_users, nbr_items, False)
+        self.min_epochs = 275
+        self.max_epochs = 275
+        self.min_improvement = 0.0001
+        self.feature_init = 0.1
+        self.learning_rate = 0.001
+        self.learning_rate_users = 0.001
+        self.learning_rate_items = 0.001
+        self.K = 0.05
+        self.K2 = 0.01
+        self.K3 = 0.01
+        self.dimensionality = 40
+        if parameters:
+            self.set_parameters(parameters)
+        self.rmse_history = np.zeros(self.max_epochs)
+
+    def __repr__(self):
+        return ('Gradient Descent based Recommendation Engine\nNumber of users: %d\n'
+                'Number of items: %d\nDimensionality: %d\n'
+                % (self.nbr_users, self.nbr_items, self.dimensionality))
+
+    def get_nbr_ratings(self):
+        return self.relationship_matrix.tocoo().data.nonzero()[0].shape[0]
+
+    # ---- training (gradient_descent.py:506-545) ------------------------------------------------------
+    def feature_training(self, initialize_model=True, handle_bias=False, verbose=False):
+        if initialize_model:
+            self.svd_v = np.zeros([self.dimensionality, self.nbr_users]) + self.feature_init
+            self.svd_u = np.zeros([self.dimensionality, self.nbr_items]) + self.feature_init
+        ratings_index, ratings = self.get_ratings(randomize_order=True)
+        if handle_bias:
+            self.compute_overall_avg()
+            self.compute_items_bias_bk()
+            self.compute_users_bias_bk()
+            gd_estimator.estimator_loop_with_bias(
+                self.min_epochs, self.max_epochs, self.min_improvement, self.dimensionality,
+                self.feature_init, self.learning_rate, self.learning_rate_users,
+                self.learning_rate_items, self.K, self.overall_bias, self.svd_u, self.svd_v,
+                ratings_index, ratings, self.items_bias, self.users_bias, self.nbr_users,
+                self.nbr_items, int(verbose))
+        else:
+            gd_estimator.estimator_loop_without_bias(
+                self.min_epochs, self.max_epochs, self.min_improvement, self.dimensionality,
+                self.feature_init, self.learning_rate, self.K, self.svd_u, self.svd_v,
+                ratings_index, ratings, self.nbr_users, self.nbr_items, int(verbose))
+
+    train = feature_training
+
+    # ---- predictors (gradient_descent.py:621-648) ----------------------------------------------------
+    def predict_rating(self, item_index, user_index):
+        return np.dot(self.svd_u[:, item_index], self.svd_v[:, user_index]) + 1.0
+
+    predict = predict_rating
+
+    def predict_rating_with_bias(self, item_index, user_index):
+        s = np.dot(self.svd_u[:, item_index], self.svd_v[:, user_index])
+        return s + self.overall_bias + (self.items_bias[item_index] + self.users_bias[user_index])
+
+    def predict_rating_by_label(self, user_label, item_label):
+        return MFRecommender.predict_rating_by_label(self, user_label, item_label, 'predict_rating')
+
+    # ---- top-N over all items (gradient_descent.py:769-802) -------------------------------------------
+    def find_user_top_match(self, user_index, nbr_recommendations=5):
+        self.relationship_matrix_csc = self.relationship_matrix.T.tocsc()
+        return self._topn(user_index, self.nbr_items, nbr_recommendations, 'predict_rating')
+
+    # ---- fold-in (gradient_descent.py:879-905) ----------------------------------------------------------
+    def _retrain(self, valid_ids, ratings_index, ratings, update_users, update_items, verbose):
+        # the reference passes `ratings[valid_ids,:]` (a 2-D index into a 1-D array) and the
+        # unfiltered index; the evident intent is the filtered pair
+        gd_estimator.estimator_loop_with_bias_dev(
+            self.min_epochs, self.max_epochs, self.min_improvement, self.dimensionality,
+            self.feature_init, self.learning_rate, self.learning_rate_users,
+            self.learning_rate_items, self.K, self.overall_bias, self.svd_u, self.svd_v,
+            np.ascontiguousarray(ratings_index[valid_ids, :]), np.ascontiguousarray(ratings[valid_ids]),
+            self.items_bias, self.users_bias, self.nbr_users, self.nbr_items, update_users,
+            update_items, int(verbose))
+
+    def retrain_user(self, user_index, ratings_index, ratings, verbose=False):
+        valid_ids = np.where(ratings_index[:, 0] == user_index)[0]
+        self.init_user_features(user_index)
+        self._retrain(valid_ids, ratings_index, ratings, 1, 0, verbose)
+
+    def retrain_item(self, item_index, ratings_index, ratings, verbose=False):
+        valid_ids = np.where(ratings_index[:, 1] == item_index)[0]
+        self.init_item_features(item_index)
+        self._retrain(valid_ids, ratings_index, ratings, 0, 1, verbose)

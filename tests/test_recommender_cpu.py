@@ -1,0 +1,82 @@
+"""Host-side logic of the Python 3 recommender classes (no GPU): rating store, COO extraction
+order and RNG consumption (bit-exact with the reference's per-rating loop, base.py:1115-1131),
+parameter plumbing and its error behaviour."""
+import numpy as np
+import pytest
+from scipy.sparse import find
+
+
+def _reference_get_ratings(matrix, randomize_order):
+    """base.py:1115-1131 restated literally (per-rating Python loop)."""
+    nbr_ratings = find(matrix)[2].shape[0]
+    ratings = np.zeros(nbr_ratings, dtype=np.float64)
+    ratings_index = np.zeros([nbr_ratings, 2], dtype=np.int32)
+    cx = matrix.tocoo()
+    for i, (user_index, feature_index, rating) in enumerate(zip(cx.row, cx.col, cx.data)):
+        ratings_index[i] = [int(user_index), int(feature_index)]
+        ratings[i] = rating
+    index = np.arange(nbr_ratings)
+    if randomize_order:
+        np.random.shuffle(index)
+    return ratings_index[index], ratings[index]
+
+
+def _filled(cls, nu=30, ni=20, n=200, seed=0):
+    rng = np.random.default_rng(seed)
+    rec = cls(nu, ni)
+    for _ in range(n):
+        rec.set_item_by_id(int(rng.integers(nu)), int(rng.integers(ni)), float(rng.integers(1, 6)))
+    return rec
+
+
+def test_get_ratings_is_bit_exact_with_reference_loop():
+    from mfrec_b200.recommendation import KMFRecommender
+    rec = _filled(KMFRecommender)
+    for randomize in (False, True):
+        np.random.seed(11)
+        want_idx, want_r = _reference_get_ratings(rec.relationship_matrix, randomize)
+        after_ref = np.random.get_state()[1].copy()
+        np.random.seed(11)
+        got_idx, got_r = rec.get_ratings(randomize_order=randomize)
+        after = np.random.get_state()[1].copy()
+        assert got_idx.dtype == np.int32 and got_r.dtype == np.float64
+        assert np.array_equal(got_idx, want_idx) and np.array_equal(got_r, want_r)
+        assert np.array_equal(after, after_ref)      # same RNG consumption
+    # users ascending, items ascending inside a user (scipy lil -> coo order)
+    idx, _ = rec.get_ratings()
+    key = idx[:, 0].astype(np.int64) * 1000 + idx[:, 1]
+    assert (np.diff(key) > 0).all()
+
+
+def test_bulk_ingestion_equals_per_rating_calls():
+    from mfrec_b200.recommendation import GDRecommender
+    rng = np.random.default_rng(3)
+    nu, ni, n = 25, 15, 300
+    idx = np.stack([rng.integers(0, nu, n), rng.integers(0, ni, n)], axis=1).astype(np.int32)
+    r = rng.integers(1, 6, n).astype(np.float64)
+    a, b = GDRecommender(nu, ni), GDRecommender(nu, ni)
+    for (u, i), val in zip(idx, r):
+        a.set_item_by_id(int(u), int(i), val)        # duplicates overwrite
+    b.set_ratings(idx, r)
+    ia, ra = a.get_ratings()
+    ib, rb = b.get_ratings()
+    assert np.array_equal(ia, ib) and np.array_equal(ra, rb)
+    a.compute_overall_avg()
+    assert a.overall_bias == ra.mean()
+
+
+def test_parameters_and_labels():
+    from mfrec_b200.recommendation import Error, GDRecommender, KMFRecommender
+    rec = GDRecommender(4, 6, {'nbr_features': 7, 'regularization_model': 0.02, 'min_epochs': 3})
+    assert (rec.dimensionality, rec.K, rec.min_epochs, rec.max_epochs) == (7, 0.02, 3, 275)
+    with pytest.raises(Error):
+        rec.set_parameters({'no_such_parameter': 1})
+    k = KMFRecommender(4, 6, {'regularization_users': 0.5, 'nbr_epochs': 9})
+    # reference quirk (kmf.py:39-41 vs :219): the key lands in K, training reads K_users
+    assert k.K == 0.5 and k.K_users == 0.1 and k.nbr_epochs == 9
+    assert k.nbr_users == 4 and k.nbr_items == 6
+    assert k.users_index['user3'] == 3 and k.items_label[5] == 'item5'
+    k.set_item_label(5, 'matrix')
+    assert k.items_index['matrix'] == 5 and 'item5' not in k.items_index
+    k.set_item_by_label('user1', 'matrix', 4)
+    assert k.relationship_matrix[1, 5] == 4.0
