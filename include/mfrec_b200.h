@@ -149,6 +149,21 @@ int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u, const doub
                double min_rating, double max_rating, int32_t N, int32_t *out_items,
                double *out_scores, int32_t *out_counts);
 
+/* The same contract as mfrec_topn for MANY users (users == NULL: users 0 .. n_users-1), built
+ * for the all-users x all-items sweep: bf16 tcgen05 GEMM tiles with a per-user threshold in the
+ * TMEM epilogue pick a few hundred candidate items per user, which are then re-scored exactly in
+ * fp32, masked, ranked and certified; users that cannot be certified are redone by mfrec_topn.
+ * Results equal mfrec_topn's up to fp32 summation order.  Small problems (N * 16 > n_candidates, N > 128,
+ * fewer than 128 users) are forwarded to mfrec_topn.
+ * stats (nullable) = { users redone exactly, mean candidates per user, sweep kernel ms,
+ * useful FLOPs (2 * users * items * k), users whose candidate list overflowed, padded K, z, 0 }. */
+int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,
+                     int32_t ni, int32_t nu, const int32_t *users, int32_t n_users,
+                     int32_t n_candidates, const int64_t *rated_indptr, const int32_t *rated_items,
+                     double mu, const double *items_bias, const double *users_bias,
+                     double min_rating, double max_rating, int32_t N, int32_t *out_items,
+                     double *out_scores, int32_t *out_counts, double stats[8]);
+
 /* compute_overall_avg (base.py:504-508), compute_items_bias_bk / compute_users_bias_bk
  * (mf.py:78-121): mu, b_i = sum(r - mu)/(K3 + n_i), b_u = sum(r - mu - b_i)/(K2 + n_u). */
 int mfrec_bias_stats(mfrec_ctx *ctx, const int32_t *ratings_index, const double *ratings,

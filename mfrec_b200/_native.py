@@ -32,7 +32,7 @@ PREDICTORS = {
 EXPORTS = (
     "mfrec_abi_version", "mfrec_ctx_create", "mfrec_ctx_destroy", "mfrec_last_error",
     "mfrec_ctx_stream", "mfrec_ctx_sync", "mfrec_ctx_launch_count", "mfrec_train_kmf",
-    "mfrec_train_funk", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn",
+    "mfrec_train_funk", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn", "mfrec_topn_sweep",
     "mfrec_bias_stats", "mfrec_ratings_pack", "mfrec_ratings_destroy", "mfrec_ratings_info",
     "mfrec_ratings_perm", "mfrec_ratings_order", "mfrec_ratings_offsets", "mfrec_ratings_packed",
     "mfrec_ratings_slab_items", "mfrec_model_create", "mfrec_model_read", "mfrec_model_destroy",
@@ -241,6 +241,32 @@ def topn(predictor, u, v, users, n_candidates, rated_indptr, rated_items, N, mu=
         C.c_double(min_rating), C.c_double(max_rating), C.c_int32(N), _ptr(items), _ptr(scores),
         _ptr(counts)), ctx.handle)
     return items, scores, counts
+
+
+def topn_sweep(predictor, u, v, users, n_candidates, rated_indptr, rated_items, N, mu=0.0,
+               items_bias=None, users_bias=None, min_rating=1.0, max_rating=5.0, ctx=None):
+    """Top-N for many users on the tensor cores (``users`` = None: all users).  Same results as
+    ``topn``; returns (items, scores, counts, stats[8])."""
+    ctx = ctx or default_context()
+    u, v = _as(u, np.float64), _as(v, np.float64)
+    n_users = v.shape[1] if users is None else None
+    if users is not None:
+        users = _as(users, np.int32).reshape(-1)
+        n_users = users.shape[0]
+    indptr = _as(rated_indptr, np.int64)
+    rated = _as(rated_items, np.int32)
+    ib, ub = _as(items_bias, np.float64), _as(users_bias, np.float64)
+    items = np.full((n_users, N), -1, dtype=np.int32)
+    scores = np.zeros((n_users, N), dtype=np.float64)
+    counts = np.zeros(n_users, dtype=np.int32)
+    stats = np.zeros(8, dtype=np.float64)
+    _check(lib().mfrec_topn_sweep(
+        ctx.handle, C.c_int(PREDICTORS[predictor]), C.c_int(u.shape[0]), _ptr(u), _ptr(v),
+        C.c_int32(u.shape[1]), C.c_int32(v.shape[1]), _ptr(users), C.c_int32(n_users),
+        C.c_int32(n_candidates), _ptr(indptr), _ptr(rated), C.c_double(mu), _ptr(ib), _ptr(ub),
+        C.c_double(min_rating), C.c_double(max_rating), C.c_int32(N), _ptr(items), _ptr(scores),
+        _ptr(counts), _ptr(stats)), ctx.handle)
+    return items, scores, counts, stats
 
 
 def bias_stats(ratings_index, ratings, ni, nu, K2=0.01, K3=0.01, ctx=None):
