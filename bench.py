@@ -298,6 +298,72 @@ def run_native(args):
 
 
 # --------------------------------------------------------------------------------------------
+# secondary bench: BASELINE configs[4], top-N scoring of U.V^T on the tensor cores
+#   python bench.py --workload topn [--steps K --warmup W]
+# --------------------------------------------------------------------------------------------
+def run_topn(args):
+    import torch
+    from mfrec_b200 import _native, synth
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    nu, ni, _nnz, k = synth.SHAPES["netflix"]
+    N = 100
+    ctx = _native.Context(local)
+    u0, v0 = synth.init_factors(nu, ni, k, seed=2)
+    u_h, v_h = torch.from_numpy(u0).pin_memory(), torch.from_numpy(v0).pin_memory()
+    items = torch.empty((nu, N), dtype=torch.int32).pin_memory()
+    scores = torch.empty((nu, N), dtype=torch.float64).pin_memory()
+    counts = torch.empty(nu, dtype=torch.int32).pin_memory()
+    out = (items.numpy(), scores.numpy(), counts.numpy())
+
+    def call():
+        return _native.topn_sweep("predict_rating", u_h.numpy(), v_h.numpy(), None, ni, None, None, N,
+                                  ctx=ctx, out=out)[3]
+
+    for _ in range(args.warmup):
+        call()
+    torch.cuda.synchronize()
+    sweep_ms, finish_ms = [], []
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = call()
+            sweep_ms.append(st[2])
+            finish_ms.append(st[7])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    flops = 2.0 * nu * ni * k
+    sm = float(np.mean(sweep_ms))
+    peaks = {}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            peaks = json.load(f)
+    peak = float(peaks.get("bf16_tflops", 1590.0))   # the sweep kernel is timed alone: burst figure
+    # spot check against the exact (CUDA-core) path
+    users = np.random.default_rng(0).permutation(nu)[:64].astype(np.int32)
+    wi, ws, wc = _native.topn("predict_rating", u0, v0, users, ni, None, None, N, ctx=ctx)
+    ok = bool(all(np.allclose(out[1][x][:wc[j]], ws[j][:wc[j]], rtol=1e-5) for j, x in enumerate(users)))
+    return {"metric": "topn_user_item_scores_per_s", "value": nu * float(ni) / ((sm + float(np.mean(finish_ms))) * 1e-3),
+            "unit": "scores/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sm + float(np.mean(finish_ms)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 filter + f32 exact re-score", "data": "synthetic",
+            "config": {"workload": "top-%d of U.V^T, netflix-shaped factors %d users x %d items, k=%d (BASELINE configs[4])" % (N, nu, ni, k),
+                       "what": "value = device time of sweep (tcgen05) + finish (exact re-score, rank, certify) kernels"},
+            "roofline": {"bound": "tensor", "achieved": flops / (sm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (sm * 1e-3) / 1e12 / peak, "traffic": None,
+                         "kernel": "topn_sweep_kernel", "flops_per_launch": flops / 7.0,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback",
+                         "sweep_ms": sm, "finish_ms": float(np.mean(finish_ms))},
+            "cpu_baseline": None,
+            "e2e": {"value": nu * float(ni) * args.steps / dt, "unit": "scores/s",
+                    "h2d_bytes_per_step": u0.nbytes + v0.nbytes, "d2h_bytes_per_step": sum(a.nbytes for a in out),
+                    "ms_per_step": dt * 1e3 / args.steps},
+            "gpu_launches": None, "users_redone_exactly": float(st[0]), "candidates_per_user": float(st[1]),
+            "matches_exact_path_on_64_users": ok, "clocks": clocks.summary()}
+
+
+# --------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU kernel (oracle/_ref, else our C port) on host cores
 # --------------------------------------------------------------------------------------------
 def time_reference(workload, nnz_sample, epochs=1):
@@ -369,7 +435,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="netflix", choices=["ml100k", "ml20m", "netflix", "yahoo"])
+    ap.add_argument("--workload", default="netflix", choices=["ml100k", "ml20m", "netflix", "yahoo", "topn"])
     ap.add_argument("--nnz", type=int, default=0, help="override the number of ratings (debug)")
     ap.add_argument("--row-blocks", type=int, default=0)
     ap.add_argument("--workers", type=int, default=0)
@@ -384,7 +450,10 @@ def main():
     if args.warmup < 3 and args.impl == "native":
         print("bench.py: warmup < 3 breaks the timing rules; using 3", file=sys.stderr)
         args.warmup = 3
-    out = run_reference(args) if args.impl == "reference" else run_native(args)
+    if args.workload == "topn":
+        out = run_topn(args)
+    else:
+        out = run_reference(args) if args.impl == "reference" else run_native(args)
     if out is not None:
         print(json.dumps(out))
 

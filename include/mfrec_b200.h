@@ -156,7 +156,8 @@ int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u, const doub
  * Results equal mfrec_topn's up to fp32 summation order.  Small problems (N * 16 > n_candidates, N > 128,
  * fewer than 128 users) are forwarded to mfrec_topn.
  * stats (nullable) = { users redone exactly, mean candidates per user, sweep kernel ms,
- * useful FLOPs (2 * users * items * k), users whose candidate list overflowed, padded K, z, 0 }. */
+ * useful FLOPs (2 * users * items * k), users whose candidate list overflowed, padded K, z,
+ * finish kernel ms }. */
 int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,
                      int32_t ni, int32_t nu, const int32_t *users, int32_t n_users,
                      int32_t n_candidates, const int64_t *rated_indptr, const int32_t *rated_items,

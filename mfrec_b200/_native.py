@@ -244,9 +244,10 @@ def topn(predictor, u, v, users, n_candidates, rated_indptr, rated_items, N, mu=
 
 
 def topn_sweep(predictor, u, v, users, n_candidates, rated_indptr, rated_items, N, mu=0.0,
-               items_bias=None, users_bias=None, min_rating=1.0, max_rating=5.0, ctx=None):
+               items_bias=None, users_bias=None, min_rating=1.0, max_rating=5.0, ctx=None, out=None):
     """Top-N for many users on the tensor cores (``users`` = None: all users).  Same results as
-    ``topn``; returns (items, scores, counts, stats[8])."""
+    ``topn``; returns (items, scores, counts, stats[8]).  ``out`` = preallocated (items int32
+    [n, N], scores float64 [n, N], counts int32 [n]) arrays, e.g. in pinned memory."""
     ctx = ctx or default_context()
     u, v = _as(u, np.float64), _as(v, np.float64)
     n_users = v.shape[1] if users is None else None
@@ -256,9 +257,15 @@ def topn_sweep(predictor, u, v, users, n_candidates, rated_indptr, rated_items, 
     indptr = _as(rated_indptr, np.int64)
     rated = _as(rated_items, np.int32)
     ib, ub = _as(items_bias, np.float64), _as(users_bias, np.float64)
-    items = np.full((n_users, N), -1, dtype=np.int32)
-    scores = np.zeros((n_users, N), dtype=np.float64)
-    counts = np.zeros(n_users, dtype=np.int32)
+    if out is None:
+        items = np.full((n_users, N), -1, dtype=np.int32)
+        scores = np.zeros((n_users, N), dtype=np.float64)
+        counts = np.zeros(n_users, dtype=np.int32)
+    else:
+        items, scores, counts = out
+        assert items.shape == (n_users, N) and items.dtype == np.int32 and items.flags.c_contiguous
+        assert scores.shape == (n_users, N) and scores.dtype == np.float64 and scores.flags.c_contiguous
+        assert counts.shape == (n_users,) and counts.dtype == np.int32
     stats = np.zeros(8, dtype=np.float64)
     _check(lib().mfrec_topn_sweep(
         ctx.handle, C.c_int(PREDICTORS[predictor]), C.c_int(u.shape[0]), _ptr(u), _ptr(v),

@@ -9,16 +9,16 @@
 // decide which few hundred items per user are worth scoring exactly:
 //
 //   1. moments   : mean / covariance of the item rows -> per user a threshold tau_u on
-//                  x_ui = p_u.q_i + b_i  such that ~3N items are expected above it, and a bound
+//                  x_ui = p_u.q_i + b_i  such that ~2.5 N items are expected above it, and a bound
 //                  eps_u on the bf16 rounding error of x_ui
 //   2. pack      : U, V -> bf16 operand tiles, K-major, 128-byte swizzled, laid out in HBM exactly
 //                  as the MMA reads them from shared memory (one bulk copy per tile, no tensor map)
 //   3. sweep     : tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), 512 users x 64 items per
 //                  step; warp-specialised: 1 bulk-copy producer lane, 1 MMA issuer lane, 8
 //                  epilogue warps that pull the accumulators with tcgen05.ld and append every
-//                  (item, x) with x > tau_u to the user's candidate list.  U.V^T is never stored.
+//                  item with x > tau_u to the user's candidate list.  U.V^T is never stored.
 //   4. finish    : one CTA per user re-scores its candidates in fp32 with the predictor, applies
-//                  the masks, sorts (cub::BlockRadixSort) and CERTIFIES the list: the N-th exact
+//                  the masks, ranks them by counting and CERTIFIES the list: the N-th exact
 //                  x must clear tau_u + eps_u, i.e. no item below the threshold can belong to the
 //                  top N.  Users that cannot be certified (too few candidates, overflow) are
 //                  redone by the exact all-items path of topn.cu.
@@ -26,8 +26,6 @@
 // FLOPs: 2 * users * items * k on the tensor pipe (2.175e15 at Netflix shape); everything else is
 // O(users * (k^2 + C * k)) on the CUDA cores.
 #include <cuda_bf16.h>
-
-#include <cub/block/block_radix_sort.cuh>
 
 #include "common.cuh"
 
@@ -250,8 +248,8 @@ struct SweepParams {
     const __nv_bfloat16 *A;     // [groups * NA][KB][128][64]   user tiles of this batch
     const __nv_bfloat16 *B;     // [n_btiles][KB][64][64]       item tiles
     const float *tau;           // [n_users]
-    int2 *cand;                 // [n_users][kCand]  (item, x bits)
-    int32_t *cand_cnt;          // [n_users]  (may exceed kCand: overflow)
+    int32_t *cand;              // [n_users][kCand]  item ids above the threshold, ascending
+    int32_t *cand_cnt;          // [n_users]  (kCand + 1 = overflow: the list is incomplete)
     int32_t n_users, n_groups, n_btiles, nc;
 };
 
@@ -356,7 +354,7 @@ topn_sweep_kernel(const SweepParams p)
             const int64_t grp = (int64_t)blockIdx.x + (int64_t)gi * gridDim.x;
             float tau[NACC];
             int cnt[NACC];
-            int2 *buf_ptr[NACC];
+            int32_t *buf_ptr[NACC];
             int64_t row[NACC];
 #pragma unroll
             for (int t = 0; t < NACC; ++t) {
@@ -385,26 +383,31 @@ topn_sweep_kernel(const SweepParams p)
                 const int valid = min(kBN, p.nc - item0);    // < 64 only in the last tile
 #pragma unroll
                 for (int t = 0; t < NACC; ++t) {
+                    // one compare + one predicated OR per score: a 64-bit hit mask per row and tile.
+                    // (Every lane is a different user, so branching per score would diverge on
+                    // almost every instruction; ~1 of 60 scores passes.)
+                    uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            // max of 8 scores first: most groups hold nothing above the threshold
-                            float m = __uint_as_float(v[t][h][g8 * 8]);
-#pragma unroll
-                            for (int q = 1; q < 8; ++q) m = fmaxf(m, __uint_as_float(v[t][h][g8 * 8 + q]));
-                            if (m > tau[t]) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const int col = h * 32 + g8 * 8 + q;
-                                    const float x = __uint_as_float(v[t][h][g8 * 8 + q]);
-                                    if (x > tau[t] && col < valid) {
-                                        if (cnt[t] < kCand) buf_ptr[t][cnt[t]] = make_int2(item0 + col, (int)v[t][h][g8 * 8 + q]);
-                                        ++cnt[t];
-                                    }
-                                }
-                            }
-                        }
+                    for (int c = 0; c < 32; ++c) {
+                        if (__uint_as_float(v[t][0][c]) > tau[t]) m0 |= 1u << c;
+                        if (__uint_as_float(v[t][1][c]) > tau[t]) m1 |= 1u << c;
+                    }
+                    if (valid < kBN) {   // ragged last tile: zero-padded items do not exist
+                        m0 &= valid >= 32 ? 0xffffffffu : ((1u << valid) - 1u);
+                        m1 &= valid >= 64 ? 0xffffffffu : (valid > 32 ? ((1u << (valid - 32)) - 1u) : 0u);
+                    }
+                    // append the hits in ascending item order; a full list stops collecting
+                    while (m0) {
+                        const int c = __ffs(m0) - 1;
+                        m0 &= m0 - 1;
+                        if (cnt[t] < kCand) buf_ptr[t][cnt[t]] = item0 + c;
+                        cnt[t] = min(cnt[t] + 1, kCand + 1);
+                    }
+                    while (m1) {
+                        const int c = __ffs(m1) - 1;
+                        m1 &= m1 - 1;
+                        if (cnt[t] < kCand) buf_ptr[t][cnt[t]] = item0 + 32 + c;
+                        cnt[t] = min(cnt[t] + 1, kCand + 1);
                     }
                 }
             }
@@ -430,7 +433,7 @@ struct FinishParams {
     int32_t n_users, nu, nc, kpad, k;
     int predictor, has_bias;
     float mu, min_rating, max_rating;
-    const int2 *cand;
+    const int32_t *cand;
     const int32_t *cand_cnt;
     const float *tau, *eps;
     const int64_t *rated_indptr;  // nullable; indexed by list position (u0 + row)
@@ -447,110 +450,105 @@ __device__ __forceinline__ uint32_t order_bits_tc(float x)
     const uint32_t b = __float_as_uint(x);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-__device__ __forceinline__ float unorder_bits_tc(uint32_t k)
-{
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
 
+// One CTA per user: exact fp32 score of every candidate (thread per candidate), masks, then the
+// rank of every candidate by counting (n is a few hundred: n^2 / 128 compares per thread beat a
+// block radix sort, need no second pass and are stable: equal scores keep ascending item order).
 __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
 {
-    constexpr int IPT = kCand / 128;
-    typedef cub::BlockRadixSort<uint64_t, 128, IPT> Sort;
-    __shared__ typename Sort::TempStorage tmp;
-    __shared__ float prow[256];
-    __shared__ float xs[kCand];          // exact x of every candidate (for the certificate)
+    __shared__ __align__(16) float prow[256];
+    __shared__ __align__(16) uint32_t keys[kCand];   // order-preserving score bits, 0 = dropped
+    __shared__ float xs[kCand];                      // exact x (the quantity the threshold is on)
+    __shared__ float scs[kCand];
     __shared__ int s_valid;
+    __shared__ float x_nth;
     const int row = blockIdx.x;
     const int64_t pos = p.u0 + row;
     const int64_t uid = p.users ? p.users[pos] : pos;
     const int n = p.cand_cnt[row];
-    if (threadIdx.x == 0) s_valid = 0;
-    for (int f = threadIdx.x; f < p.kpad; f += 128) prow[f] = p.P[uid * p.kpad + f];
-    __syncthreads();
     const int nn = min(n, kCand);
+    if (threadIdx.x == 0) { s_valid = 0; x_nth = -INFINITY; }
+    for (int f = threadIdx.x; f < p.kpad; f += 128) prow[f] = p.P[uid * p.kpad + f];
+    for (int c = nn + threadIdx.x; c < ((nn + 3) & ~3); c += 128) keys[c] = 0;   // pad to a multiple of 4
+    __syncthreads();
     const int64_t ra = p.rated_indptr ? p.rated_indptr[pos] : 0, rbnd = p.rated_indptr ? p.rated_indptr[pos + 1] : 0;
     const float bu = p.ub[uid];
-    uint64_t keys[IPT];
+    const int32_t *cand = p.cand + (size_t)row * kCand;
     int valid = 0;
-#pragma unroll
-    for (int t = 0; t < IPT; ++t) {
-        const int c = threadIdx.x + t * 128;    // striped: thread-contiguous order is not needed
-        uint64_t key = 0;
-        float x = -INFINITY;
-        if (c < nn) {
-            const int it = p.cand[(size_t)row * kCand + c].x;
-            const float *q = p.Q + (size_t)it * p.kpad;
-            float dot = 0.f;
-            for (int f = 0; f < p.k; f += 4) {   // kpad is a multiple of 32 and zero padded
-                const float4 qv = *reinterpret_cast<const float4 *>(q + f);
-                dot = fmaf(prow[f], qv.x, dot); dot = fmaf(prow[f + 1], qv.y, dot);
-                dot = fmaf(prow[f + 2], qv.z, dot); dot = fmaf(prow[f + 3], qv.w, dot);
-            }
-            const float bi = p.ib[it];
-            x = p.has_bias ? dot + bi : dot;
-            const float bsum = bi + bu;
-            float s;
-            switch (p.predictor) {
-            case MFREC_PRED_GD_RATING: s = dot + 1.0f; break;
-            case MFREC_PRED_GD_RATING_BIAS: s = dot + (p.mu + bsum); break;
-            case MFREC_PRED_KMF_LINEAR: s = dot + bsum; break;
-            case MFREC_PRED_KMF_LOGISTIC:
-                s = p.min_rating + (1.f / (1.f + expf(-(dot + bsum)))) * (p.max_rating - p.min_rating);
-                break;
-            case MFREC_PRED_KMF_LINEAR_NEG: s = p.min_rating + (dot + bsum) * (p.max_rating - p.min_rating); break;
-            default: s = dot; break;
-            }
-            bool ok = (s == s) && s != 0.f && it != (int)uid;
-            if (ok && rbnd > ra) {   // binary search in the user's (ascending) rated list
-                int64_t lo = ra, hi = rbnd;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (p.rated_items[mid] < it) lo = mid + 1; else hi = mid;
-                }
-                ok = !(lo < rbnd && p.rated_items[lo] == it);
-            }
-            if (ok) {
-                key = ((uint64_t)order_bits_tc(s) << 32) | (uint32_t)(~(uint32_t)it);
-                ++valid;
-            } else {
-                x = -INFINITY;
-            }
+    for (int c = threadIdx.x; c < nn; c += 128) {
+        const int it = cand[c];
+        const float4 *q = reinterpret_cast<const float4 *>(p.Q + (size_t)it * p.kpad);
+        float d0 = 0.f, d1 = 0.f;
+        for (int f = 0; f < p.kpad / 4; f += 2) {   // kpad is a multiple of 32, rows are zero padded
+            const float4 a = q[f], b = q[f + 1];
+            const float4 pa = reinterpret_cast<const float4 *>(prow)[f], pb = reinterpret_cast<const float4 *>(prow)[f + 1];
+            d0 = fmaf(pa.x, a.x, d0); d0 = fmaf(pa.y, a.y, d0); d0 = fmaf(pa.z, a.z, d0); d0 = fmaf(pa.w, a.w, d0);
+            d1 = fmaf(pb.x, b.x, d1); d1 = fmaf(pb.y, b.y, d1); d1 = fmaf(pb.z, b.z, d1); d1 = fmaf(pb.w, b.w, d1);
         }
-        keys[t] = key;
-        if (c < kCand) xs[c] = x;
+        const float dot = d0 + d1;
+        const float bi = p.ib[it];
+        const float bsum = bi + bu;
+        float sc;
+        switch (p.predictor) {
+        case MFREC_PRED_GD_RATING: sc = dot + 1.0f; break;
+        case MFREC_PRED_GD_RATING_BIAS: sc = dot + (p.mu + bsum); break;
+        case MFREC_PRED_KMF_LINEAR: sc = dot + bsum; break;
+        case MFREC_PRED_KMF_LOGISTIC:
+            sc = p.min_rating + (1.f / (1.f + expf(-(dot + bsum)))) * (p.max_rating - p.min_rating);
+            break;
+        case MFREC_PRED_KMF_LINEAR_NEG: sc = p.min_rating + (dot + bsum) * (p.max_rating - p.min_rating); break;
+        default: sc = dot; break;
+        }
+        bool ok = (sc == sc) && sc != 0.f && it != (int)uid;
+        if (ok && rbnd > ra) {   // binary search in the user's (ascending) rated list
+            int64_t lo = ra, hi = rbnd;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (p.rated_items[mid] < it) lo = mid + 1; else hi = mid;
+            }
+            ok = !(lo < rbnd && p.rated_items[lo] == it);
+        }
+        keys[c] = ok ? order_bits_tc(sc) : 0u;
+        xs[c] = p.has_bias ? dot + bi : dot;
+        scs[c] = sc;
+        valid += ok ? 1 : 0;
     }
-    atomicAdd(&s_valid, valid);
+    if (valid) atomicAdd(&s_valid, valid);
     __syncthreads();
-    Sort(tmp).SortDescendingBlockedToStriped(keys);   // rank r lands in thread r % 128, slot r / 128
     const int nvalid = s_valid;
-    // certificate: the N-th best exact x among the valid candidates must clear tau + eps
-    // (x is a monotone function of the score inside one user, so rank by score == rank by x)
-    __shared__ float x_nth;
-    __shared__ int s_cert;
-    if (threadIdx.x == 0) { x_nth = -INFINITY; s_cert = 0; }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < IPT; ++t) {
-        const int r = threadIdx.x + t * 128;
-        const uint64_t key = keys[t];
-        if (r < p.N) {
-            if (key) {
-                p.out_items[(size_t)row * p.N + r] = (int32_t)(~(uint32_t)(key & 0xffffffffu));
-                p.out_scores[(size_t)row * p.N + r] = (double)unorder_bits_tc((uint32_t)(key >> 32));
+    const int n4 = (nn + 3) >> 2;
+    for (int c = threadIdx.x; c < nn; c += 128) {
+        const uint32_t key = keys[c];
+        if (!key) continue;
+        int rank = 0;
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
+        const int c4 = c >> 2;
+        for (int j = 0; j < n4; ++j) {           // every thread reads the same word: broadcast
+            const uint4 kk = k4[j];
+            if (j < c4) {                        // earlier candidates (lower item id) win ties
+                rank += (kk.x >= key) + (kk.y >= key) + (kk.z >= key) + (kk.w >= key);
+            } else if (j > c4) {
+                rank += (kk.x > key) + (kk.y > key) + (kk.z > key) + (kk.w > key);
             } else {
-                p.out_items[(size_t)row * p.N + r] = -1;
-                p.out_scores[(size_t)row * p.N + r] = 0.0;
+                const uint32_t e[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rank += (q < (c & 3)) ? (e[q] >= key) : (e[q] > key);
             }
         }
-        if (r == p.N - 1 && key) {
-            // find this item's exact x again (the key holds the score, not x)
-            const int it = (int32_t)(~(uint32_t)(key & 0xffffffffu));
-            for (int c = 0; c < nn; ++c)
-                if (p.cand[(size_t)row * kCand + c].x == it) { x_nth = xs[c]; break; }
+        if (rank < p.N) {
+            p.out_items[(size_t)row * p.N + rank] = cand[c];
+            p.out_scores[(size_t)row * p.N + rank] = (double)scs[c];
+            if (rank == p.N - 1) x_nth = xs[c];
         }
+    }
+    for (int r = nvalid + threadIdx.x; r < p.N; r += 128) {   // fewer than N valid candidates: pad
+        p.out_items[(size_t)row * p.N + r] = -1;
+        p.out_scores[(size_t)row * p.N + r] = 0.0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // certificate: the N-th best exact x among the valid candidates clears tau + eps, so no
+        // item below the threshold can belong to the top N (x is monotone in the score per user)
         const bool certified = n <= kCand && nvalid >= p.N && x_nth > p.tau[row] + p.eps[row];
         p.out_counts[row] = min(nvalid, p.N);
         p.fallback[row] = certified ? 0 : 1;
@@ -647,7 +645,7 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
     DevBuf<double> d_sum, d_gram;
     DevBuf<float> d_qmax2, d_tau, d_eps;
     DevBuf<__nv_bfloat16> d_A, d_B;
-    DevBuf<int2> d_cand;
+    DevBuf<int32_t> d_cand;
     DevBuf<int32_t> d_cnt, d_users, d_rated, d_items, d_counts, d_fb;
     DevBuf<int64_t> d_indptr;
     DevBuf<double> d_scores;
@@ -684,20 +682,20 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
             M->Q, kpad, k, nullptr, 0, nc, nc, KB, has_bias ? k : -1, M->ib, d_B.p, chunks);
         MF_LAUNCH_CHECK(ctx);
     }
-    // expected 3N items above the threshold (normal approximation of a user's scores)
-    const float z = (float)inv_norm_cdf(1.0 - std::min(0.45, 3.0 * N / (double)nc));
+    // expected 2.5 N items above the threshold (normal approximation of a user's scores)
+    const float z = (float)inv_norm_cdf(1.0 - std::min(0.45, 2.5 * N / (double)nc));
     tr.lap("upload + moments + pack V");
 
-    cudaEvent_t ev[2];
-    MF_CUDA(ctx, cudaEventCreate(&ev[0]));
-    MF_CUDA(ctx, cudaEventCreate(&ev[1]));
-    double sweep_ms = 0.0, n_fallback = 0.0, n_cand = 0.0, n_overflow = 0.0;
+    cudaEvent_t ev[5];
+    for (int j = 0; j < 5; ++j) MF_CUDA(ctx, cudaEventCreate(&ev[j]));
+    double sweep_ms = 0.0, prep_ms = 0.0, finish_ms = 0.0, d2h_ms = 0.0, n_fallback = 0.0, n_cand = 0.0, n_overflow = 0.0;
     std::vector<int32_t> h_fb(batch), h_cnt(batch), fb_users;
     std::vector<int64_t> fb_pos;
     int rc = MFREC_OK;
     for (int64_t first = 0; first < n_users && rc == MFREC_OK; first += batch) {
         const int nub = (int)std::min<int64_t>(batch, n_users - first);
         const int n_groups = (nub + group - 1) / group;
+        cudaEventRecord(ev[2], st);
         const size_t smem_thr = ((size_t)ka * (ka | 1) + ka) * 4;
         if (smem_thr > 48 * 1024)
             cudaFuncSetAttribute(user_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_thr);
@@ -732,15 +730,23 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
         fp.out_items = d_items.p; fp.out_scores = d_scores.p; fp.out_counts = d_counts.p; fp.fallback = d_fb.p;
         topn_finish_kernel<<<nub, 128, 0, st>>>(fp);
         MF_LAUNCH_CHECK(ctx);
+        cudaEventRecord(ev[3], st);
         MF_CUDA(ctx, cudaMemcpyAsync(out_items + (size_t)first * N, d_items.p, (size_t)nub * N * 4, cudaMemcpyDeviceToHost, st));
         MF_CUDA(ctx, cudaMemcpyAsync(out_scores + (size_t)first * N, d_scores.p, (size_t)nub * N * 8, cudaMemcpyDeviceToHost, st));
         MF_CUDA(ctx, cudaMemcpyAsync(out_counts + first, d_counts.p, (size_t)nub * 4, cudaMemcpyDeviceToHost, st));
         MF_CUDA(ctx, cudaMemcpyAsync(h_fb.data(), d_fb.p, (size_t)nub * 4, cudaMemcpyDeviceToHost, st));
         MF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), d_cnt.p, (size_t)nub * 4, cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ev[4], st);
         MF_CUDA(ctx, cudaStreamSynchronize(st));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev[0], ev[1]);
         sweep_ms += ms;
+        cudaEventElapsedTime(&ms, ev[2], ev[0]);
+        prep_ms += ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[3]);
+        finish_ms += ms;
+        cudaEventElapsedTime(&ms, ev[3], ev[4]);
+        d2h_ms += ms;
         for (int j = 0; j < nub; ++j) {
             n_cand += std::min(h_cnt[j], kCand);
             if (h_cnt[j] > kCand) n_overflow += 1;
@@ -750,8 +756,10 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
             }
         }
     }
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
+    for (int j = 0; j < 5; ++j) cudaEventDestroy(ev[j]);
+    if (tr.on)
+        fprintf(stderr, "[mfrec trace] topn_sweep: device ms: thresholds + pack U %.2f, sweep %.2f, finish %.2f, D2H %.2f\n",
+                prep_ms, sweep_ms, finish_ms, d2h_ms);
     if (rc != MFREC_OK) return rc;
     tr.lap("sweep + finish");
     n_fallback = (double)fb_users.size();
@@ -787,6 +795,7 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
         stats[4] = n_overflow;
         stats[5] = (double)KB * 64;                                   // padded K the MMAs run over
         stats[6] = z;
+        stats[7] = finish_ms;
     }
     return MFREC_OK;
 }
