@@ -202,6 +202,7 @@ def run_native(args):
     cta = c4.max(axis=3).sum(axis=3)                              # [g, rb, cb]
     rbs = np.arange(R.B)
     crit = sum(int(cta[g, rbs, (rbs + s) % R.B].max()) for g in range(R.G) for s in range(R.B))
+    quad_types = R.quad_types()
     balance = {"critical_path_ratings": crit, "ideal": nnz / float(R.B * R.W),
                "efficiency": nnz / float(R.B * R.W) / max(crit, 1)}
     del cnt, c4, cta
@@ -289,6 +290,7 @@ def run_native(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "%s-shaped %dx%d nnz=%d k=%d (BASELINE configs[2])" % (args.workload, nu, ni, nnz, k),
                       "kernel": "train_linear_kernel", "schedule": layout_desc, "balance": balance,
+                      "quad_types": quad_types,
                       "l2": "inputs (1.2 GB ratings + 255 MB factors) exceed the 126 MB L2",
                       "hyper": HP},
            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,

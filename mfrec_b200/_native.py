@@ -34,7 +34,7 @@ EXPORTS = (
     "mfrec_ctx_stream", "mfrec_ctx_sync", "mfrec_ctx_launch_count", "mfrec_train_kmf",
     "mfrec_train_funk", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn", "mfrec_topn_sweep",
     "mfrec_bias_stats", "mfrec_ratings_pack", "mfrec_ratings_destroy", "mfrec_ratings_info",
-    "mfrec_ratings_perm", "mfrec_ratings_order", "mfrec_ratings_offsets", "mfrec_ratings_packed",
+    "mfrec_ratings_quad_types", "mfrec_ratings_perm", "mfrec_ratings_order", "mfrec_ratings_offsets", "mfrec_ratings_packed",
     "mfrec_ratings_slab_items", "mfrec_model_create", "mfrec_model_read", "mfrec_model_destroy",
     "mfrec_model_device_ptrs", "mfrec_sgd_epoch", "mfrec_model_predict",
 )
@@ -360,6 +360,12 @@ class Ratings(object):
         raw = np.zeros((self.packed_len, 3), dtype=np.int32)
         _check(lib().mfrec_ratings_packed(self.ctx.handle, self._h, _ptr(raw)), self.ctx.handle)
         return raw[:, 0].copy(), raw[:, 1].copy(), raw[:, 2].copy().view(np.float32)
+
+    def quad_types(self):
+        """{generic, chain, clean} quad counts of the layout (SGD kernel fast paths)."""
+        out = (C.c_int64 * 3)()
+        _check(lib().mfrec_ratings_quad_types(self._h, out))
+        return dict(generic=int(out[0]), chain=int(out[1]), clean=int(out[2]))
 
     def slab_items(self, slab):
         a, b = C.c_int32(), C.c_int32()

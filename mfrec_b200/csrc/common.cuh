@@ -18,6 +18,17 @@ struct __align__(4) PackedRating {
     float r;
 };
 static_assert(sizeof(PackedRating) == 12, "rating triple must be 12 bytes");
+// Packed ids use the low 28 bits; the packer leaves hints for the SGD kernel in the bits above,
+// so that the hot loop needs no run-time hazard detection:
+constexpr int32_t kIdMask = 0x0fffffff;
+constexpr int32_t kFlagStale = 1 << 28;     // .i : the user also occurs among the 32 ratings that precede
+                                            //      this one in its warp's stream (a prefetched row may be stale)
+constexpr int32_t kFlagSameItem = 1 << 29;  // .i : same item as the previous rating of the bucket
+constexpr int32_t kFlagPad = 1 << 30;       // .i : alignment padding, not a rating
+constexpr int kQuadShift = 28;              // .u of the first entry of an aligned quad, 2 bits:
+constexpr int kQuadGeneric = 0;             //      anything (padding, repeated users, ...)
+constexpr int kQuadChain = 1;               //      4 ratings of ONE item, 4 distinct fresh users
+constexpr int kQuadClean = 2;               //      4 ratings, 4 distinct fresh users, any items
 
 struct mfrec_ctx {
     int device = 0;
@@ -50,6 +61,7 @@ struct mfrec_ratings {
     int32_t max_cb_items = 0;      // widest column block (items) -> shared-memory tile size
     int64_t max_bucket = 0;
     float max_abs_rating = 0.f;    // sizes the fixed-point scale of the warp reduction
+    int64_t quad_types[3] = {0, 0, 0};  // quads by kQuadGeneric / kQuadChain / kQuadClean
     // device
     int32_t *user_perm = nullptr;  // [nu] old -> packed id
     int32_t *item_perm = nullptr;  // [ni]

@@ -102,22 +102,33 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
             double c = 0.0, vfu = 0.0, bb = 1.0;
             if (j < n) {
                 rt = prm.packed[a + j];
+                rt.u &= kIdMask;   // the packer's hint bits (common.cuh) stay in rt.i until the replay
                 c = prm.cache[a + j];
                 vfu = prm.vf[rt.u];
                 // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
-                bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[rt.i - cs]), prm.ubp[rt.u])
+                bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[(rt.i & kIdMask) - cs]), prm.ubp[rt.u])
                                  : 1.0;
             }
             const int cnt = min(32, n - base);
             for (int t = 0; t < cnt; ++t) {
                 const int u_t = __shfl_sync(0xffffffffu, rt.u, t);
-                const int i_t = __shfl_sync(0xffffffffu, rt.i, t);
+                const int if_t = __shfl_sync(0xffffffffu, rt.i, t);
+                const int i_t = if_t & kIdMask;
                 const double r_t = (double)__shfl_sync(0xffffffffu, rt.r, t);
                 const double c_t = __shfl_sync(0xffffffffu, c, t);
                 double v_t = __shfl_sync(0xffffffffu, vfu, t);
                 const double b_t = __shfl_sync(0xffffffffu, bb, t);
-                if (u_t == prev_u) v_t = vf_cur;                   // same user as the last rating
-                else if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
+                if (u_t == prev_u) {
+                    v_t = vf_cur;                                  // same user as the last rating
+                } else {
+                    if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
+                    if (if_t & kFlagStale) {
+                        // the user occurred among the 32 preceding ratings: the staged scalar may
+                        // predate that update; lane 0 has written it back, read it again
+                        __syncwarp();
+                        v_t = prm.vf[u_t];
+                    }
+                }
                 const double mf = ufs[i_t - cs];
                 const double pr = funk_estimate(mf, v_t, c_t, b_t, prm.trail, 1);
                 const double err = __dadd_rn(r_t, -pr);
@@ -152,7 +163,10 @@ __global__ void funk_cache_kernel(const PackedRating *__restrict__ packed, int64
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const PackedRating rt = packed[j];
+        PackedRating rt = packed[j];
+        if (rt.i & kFlagPad) continue;
+        rt.u &= kIdMask;
+        rt.i &= kIdMask;
         const double bb = variant ? __dadd_rn(__dadd_rn(overall, ibp[rt.i]), ubp[rt.u]) : 1.0;
         cache[j] = funk_estimate(uf[rt.i], vf[rt.u], cache[j], bb, 0.0, 0);
     }

@@ -117,6 +117,18 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
         pr.u = (int32_t)((key >> kl.bits_i) & mask_u);
         pr.i = (int32_t)(key & mask_i);
         pr.r = (float)ratings[src];
+        // hints for the SGD kernel (common.cuh).  The ratings that precede this one in its warp's
+        // stream are its predecessors in sorted order down to the first bucket of the worker
+        // (bucket index rounded down to a multiple of W); looking at 32 RATINGS back covers at
+        // least 32 stream POSITIONS back (padding only adds distance).
+        const uint64_t first_b = b - b % (uint64_t)kl.W;
+        const int shift = kl.bits_u + kl.bits_i;
+        for (int64_t j = s - 1; j >= 0 && j >= s - 32; --j) {
+            const uint64_t kj = __ldg(keys + j);
+            if ((kj >> shift) < first_b) break;
+            if ((int32_t)((kj >> kl.bits_i) & mask_u) == pr.u) { pr.i |= kFlagStale; break; }
+        }
+        if (s > raw_off[b] && (int32_t)(__ldg(keys + s - 1) & mask_i) == (pr.i & kIdMask)) pr.i |= kFlagSameItem;
         packed[dst] = pr;
         if (order) order[dst] = (int64_t)src;
     }
@@ -132,6 +144,35 @@ __global__ void max_abs_rating_kernel(const PackedRating *__restrict__ packed, i
         mx = max(mx, __float_as_int(fabsf(packed[j].r)));
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, mx);
+}
+
+// every slot starts as padding; gather_kernel overwrites the real ratings
+__global__ void fill_padding_kernel(PackedRating *__restrict__ packed, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    PackedRating pad;
+    pad.u = 0; pad.i = kFlagPad; pad.r = 0.f;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) packed[j] = pad;
+}
+
+// classify every aligned quad (buckets are quad aligned, so a quad never spans two buckets)
+__global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_quads,
+                                 unsigned long long *__restrict__ type_count)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += stride) {
+        const int4 *src = reinterpret_cast<const int4 *>(packed + q * 4);
+        const int4 a = src[0], b = src[1], c = src[2];
+        const int i0 = a.y, i1 = b.x, i2 = b.w, i3 = c.z;
+        const int any = i0 | i1 | i2 | i3;
+        int type = kQuadGeneric;
+        if (!(any & (kFlagPad | kFlagStale))) {
+            const int m0 = i0 & kIdMask;
+            type = ((i1 & kIdMask) == m0 && (i2 & kIdMask) == m0 && (i3 & kIdMask) == m0) ? kQuadChain : kQuadClean;
+        }
+        packed[q * 4].u = (a.x & kIdMask) | (type << kQuadShift);
+        if (!(i0 & kFlagPad)) atomicAdd(type_count + type, 1ull);   // statistics (empty quads excluded)
+    }
 }
 
 __global__ void fill_i64_kernel(int64_t *p, int64_t n, int64_t v)
@@ -309,6 +350,8 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
                                (long long)nnz, ni, nu);
     if (nnz >= (1ll << 32))
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: nnz >= 2^32 per device");
+    if (nu > kIdMask || ni > kIdMask)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: more than 2^28 users or items");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Tracer tr("pack", st);
@@ -492,7 +535,8 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     // ---- 6. gather ------------------------------------------------------------------------
     // +16 entries of slack: bulk copies are rounded up to 16 bytes
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->packed, ((size_t)packed_len + 16) * sizeof(PackedRating), st));
-    MF_CUDA(ctx, cudaMemsetAsync(R->packed, 0, ((size_t)packed_len + 16) * sizeof(PackedRating), st));
+    fill_padding_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len + 16);
+    MF_LAUNCH_CHECK(ctx);
     if (keep_order) {
         MF_CUDA(ctx, cudaMallocAsync((void **)&R->order, ((size_t)packed_len + 1) * 8, st));
         fill_i64_kernel<<<(unsigned)ceil_div64(packed_len + 1, 256), 256, 0, st>>>(R->order, packed_len, -1);
@@ -508,6 +552,17 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
                                                         (const double *)d_r, kl, raw_off.p,
                                                         R->bucket_off, R->packed, R->order);
         MF_LAUNCH_CHECK(ctx);
+    }
+    if (packed_len > 0) {
+        DevBuf<unsigned long long> d_tc;
+        MF_CUDA(ctx, d_tc.alloc(4, ctx->stream));
+        MF_CUDA(ctx, cudaMemsetAsync(d_tc.p, 0, 32, st));
+        quad_type_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len / 4, d_tc.p);
+        MF_LAUNCH_CHECK(ctx);
+        unsigned long long h_tc[4];
+        MF_CUDA(ctx, cudaMemcpyAsync(h_tc, d_tc.p, 32, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+        for (int t = 0; t < 3; ++t) R->quad_types[t] = (int64_t)h_tc[t];
     }
     // largest |rating| (sizes the fixed-point reduction scale of the SGD kernel)
     {
@@ -552,6 +607,13 @@ extern "C" int mfrec_ratings_info(const mfrec_ratings *r, int64_t info[8])
     return MFREC_OK;
 }
 
+extern "C" int mfrec_ratings_quad_types(const mfrec_ratings *r, int64_t counts[3])
+{
+    if (!r || !counts) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ratings_quad_types: NULL argument");
+    for (int t = 0; t < 3; ++t) counts[t] = r->quad_types[t];
+    return MFREC_OK;
+}
+
 extern "C" int mfrec_ratings_perm(mfrec_ctx *ctx, const mfrec_ratings *r, int32_t *user_perm,
                                   int32_t *item_perm)
 {
@@ -589,6 +651,12 @@ extern "C" int mfrec_ratings_packed(mfrec_ctx *ctx, const mfrec_ratings *r, void
     if (!ctx || !r || !out) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_packed: NULL argument");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     MF_CUDA(ctx, cudaMemcpy(out, r->packed, (size_t)r->packed_len * sizeof(PackedRating), cudaMemcpyDeviceToHost));
+    // strip the kernel hints: callers see plain ids, padding all-zero
+    PackedRating *h = static_cast<PackedRating *>(out);
+    for (int64_t j = 0; j < r->packed_len; ++j) {
+        h[j].u &= kIdMask;
+        h[j].i = (h[j].i & kFlagPad) ? 0 : (h[j].i & kIdMask);
+    }
     return MFREC_OK;
 }
 

@@ -214,9 +214,13 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
 //                     cursor runs across phase boundaries
 //   consume cursor  : the update itself
 // Stale-prefetch hazard: the row of rating x is fetched while up to kDepth + 3 earlier ratings are
-// still being applied.  Equal adjacent users are served from registers; otherwise a
-// lane-distributed history of the users of the last 32 stream positions detects a repeat inside
-// the window and the row is re-read from global memory.
+// still being applied.  The hot loop does not look for it: the packer (pack.cu) marks every rating
+// whose user also occurs among the 32 preceding ratings of the stream, and classifies every
+// aligned quad, so that the two common cases -- four ratings of one hot item (the item row stays
+// in registers: a pure dependent chain, which is what bounds a sub-epoch) and four ratings with
+// fresh users and no item repeated back to back -- run as straight-line code; everything else
+// takes the generic path, which picks each row's source (registers / prefetch ring / global
+// memory) with warp-uniform branches.
 // ------------------------------------------------------------------------------------------
 template <int E, int KERNEL, bool TIMING>
 __global__ void __launch_bounds__(512, 1)
@@ -267,7 +271,6 @@ sgd_block_kernel(const SgdParams prm)
 
     double se = 0.0;          // fp64 total of fp32 per-bucket partials, over the whole launch
     uint32_t chunk_seq = 0;   // chunks this warp has pulled so far (ring stage + mbarrier parity)
-    int hist = -1;            // user consumed at the stream position == lane (mod 32)
     // opt-in section timer (cycles per warp): 0 bookkeeping + prefetch issue, 1 cp.async wait,
     // 2 quad load, 3 updates, 4 phase hand-over wait, 5 sub-epoch set-up (ticket + tile), 6 tail
     unsigned long long tsec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -350,7 +353,7 @@ sgd_block_kernel(const SgdParams prm)
                     const PackedRating *src = ring + (g % kStages) * kChunk + (pos % kChunk);
                     const int4 *qsrc = reinterpret_cast<const int4 *>(src);
                     const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
-                    const int us[4] = {a.x, a.w, b.z, c2.y};
+                    const int us[4] = {a.x & kIdMask, a.w & kIdMask, b.z & kIdMask, c2.y & kIdMask};
                     const uint32_t slot0 = pos % kDepth;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -360,7 +363,7 @@ sgd_block_kernel(const SgdParams prm)
                         for (int c = 0; c < Frag<E>::NV; ++c)
                             cp_async<Frag<E>::V * 4>(dst + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
                     }
-                    if (lane < 4) cp_async<4>(pbias + slot0 + lane, prm.ub + src[lane].u);
+                    if (lane < 4) cp_async<4>(pbias + slot0 + lane, prm.ub + (src[lane].u & kIdMask));
                 }
                 cp_async_commit();
                 ++pfq;
@@ -380,37 +383,18 @@ sgd_block_kernel(const SgdParams prm)
         float cbu = 0.f, cbi = 0.f, se_f = 0.f;
         int prev_u = -1, prev_i = -1;
 
-        // one rating: pos = stream position, (u, it, r) the triple
-        auto update_one = [&](uint32_t pos, int u, int it, float r) {
-            const uint32_t slot = pos % kDepth;
-            Frag<E> pu;
-            float bu;
-            const bool stale = __any_sync(FULL, hist == u);
-            if (u == prev_u) {                 // adjacent ratings of one user: row is in registers
+        // ---- the arithmetic of one update, on rows held in registers -----------------------------
+        // deterministic warp reduction in 32-bit fixed point: one REDUX instead of a 5-level
+        // shuffle butterfly; integer addition is associative, so the result does not depend on
+        // lane order.  fx_scale is a power of two chosen from max |rating| (see sgd_epoch).
+        auto dot_fx = [&](const Frag<E> &pu, const Frag<E> &q) {
+            float part = pu.x[0] * q.x[0];
 #pragma unroll
-                for (int e = 0; e < E; ++e) pu.x[e] = cp.x[e];
-                bu = cbu;
-            } else if (stale) {
-                // the row was updated after its prefetch was issued: re-read it from global memory
-                frag_load<E>(pu, prm.P + (size_t)u * KPAD, lane);
-                bu = prm.ub[u];
-            } else {
-                frag_load<E>(pu, prow + slot * KPAD, lane);
-                bu = pbias[slot];
-            }
-            float *qrow = Qs + (size_t)(it - cs) * KPAD;
-            if (it != prev_i) {   // otherwise the item row is still in registers
-                frag_load<E>(cq, qrow, lane);
-                cbi = ibs[it - cs];
-            }
-            float part = pu.x[0] * cq.x[0];
-#pragma unroll
-            for (int e = 1; e < E; ++e) part = fmaf(pu.x[e], cq.x[e], part);
-            // deterministic warp reduction in 32-bit fixed point: one REDUX instead of a 5-level
-            // shuffle butterfly; integer addition is associative, so the result does not depend on
-            // lane order.  fx_scale is a power of two chosen from max |rating| (see sgd_epoch).
-            const float dot = (float)__reduce_add_sync(FULL, __float2int_rn(part * fx_scale)) * fx_inv;
-            const float pred = dot + (cbi + bu);
+            for (int e = 1; e < E; ++e) part = fmaf(pu.x[e], q.x[e], part);
+            return __float2int_rn(part * fx_scale);
+        };
+        auto apply = [&](int isum, float r, Frag<E> &pu, float &bu, Frag<E> &q, float &bi) {
+            const float pred = fmaf((float)isum, fx_inv, bi + bu);
             float err, grad;
             if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
                 err = r - pred;
@@ -422,24 +406,116 @@ sgd_block_kernel(const SgdParams prm)
             }
             se_f = fmaf(err, err, se_f);
             const float gl = lr * grad;
-            cbu = upd_bu ? fmaf(a_b, bu, gl) : bu;
-            cbi = upd_bi ? fmaf(a_b, cbi, gl) : cbi;
+            bu = upd_bu ? fmaf(a_b, bu, gl) : bu;
+            bi = upd_bi ? fmaf(a_b, bi, gl) : bi;
             const float gli = upd_i ? gl : 0.f, glu = upd_u ? gl : 0.f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const float pe = pu.x[e], qe = cq.x[e];
-                cp.x[e] = fmaf(glu, qe, a_u * pe);
-                cq.x[e] = fmaf(gli, pe, a_i * qe);
+                const float pe = pu.x[e], qe = q.x[e];
+                pu.x[e] = fmaf(glu, qe, a_u * pe);
+                q.x[e] = fmaf(gli, pe, a_i * qe);
             }
+        };
+        auto store_p = [&](int u, const Frag<E> &pu, float bu) {
+            frag_store<E>(pu, prm.P + (size_t)u * KPAD, lane);
+            if (lane == 0) prm.ub[u] = bu;
+        };
+        auto store_q = [&](int it, const Frag<E> &q, float bi) {
+            frag_store<E>(q, Qs + (size_t)(it - cs) * KPAD, lane);
+            if (lane == 0) ibs[it - cs] = bi;
+        };
+
+        // generic path, one rating: sources picked at run time (warp-uniform branches).
+        // stale = the packer saw this user among the 32 preceding ratings of the stream, so the
+        // prefetched copy of the row may predate an update: take it from registers (adjacent
+        // ratings of one user) or re-read it from global memory.
+        auto update_one = [&](uint32_t pos, int u, int it, float r, bool stale) {
+            const uint32_t slot = pos % kDepth;
+            Frag<E> pu;
+            float bu;
+            if (u == prev_u) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) pu.x[e] = cp.x[e];
+                bu = cbu;
+            } else if (stale) {
+                __syncwarp();   // lane 0's bias store of an earlier rating is visible to every lane
+                frag_load<E>(pu, prm.P + (size_t)u * KPAD, lane);
+                bu = prm.ub[u];
+            } else {
+                frag_load<E>(pu, prow + slot * KPAD, lane);
+                bu = pbias[slot];
+            }
+            if (it != prev_i) {   // otherwise the item row is still in registers
+                frag_load<E>(cq, Qs + (size_t)(it - cs) * KPAD, lane);
+                cbi = ibs[it - cs];
+            }
+            const int isum = __reduce_add_sync(FULL, dot_fx(pu, cq));
+            apply(isum, r, pu, bu, cq, cbi);
+            store_q(it, cq, cbi);
+            store_p(u, pu, bu);
+#pragma unroll
+            for (int e = 0; e < E; ++e) cp.x[e] = pu.x[e];
+            cbu = bu;
             prev_u = u;
             prev_i = it;
-            if (lane == (int)(pos & 31u)) hist = u;
-            frag_store<E>(cq, qrow, lane);
-            frag_store<E>(cp, prm.P + (size_t)u * KPAD, lane);
-            if (lane == 0) {
-                ibs[it - cs] = cbi;
-                prm.ub[u] = cbu;
+        };
+
+        // straight-line paths for the quads the packer classified (common.cuh): four fresh,
+        // pairwise distinct users, so all four P rows come from the prefetch ring up front
+        auto load_quad_p = [&](uint32_t pos, Frag<E> (&p4)[4], float (&b4)[4]) {
+            const uint32_t slot0 = pos % kDepth;   // pos is quad aligned, kDepth a multiple of 4
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                frag_load<E>(p4[t], prow + (slot0 + t) * KPAD, lane);
+                b4[t] = pbias[slot0 + t];
             }
+        };
+        // kQuadChain: one item; its row stays in registers and is stored once
+        auto chain_quad = [&](uint32_t pos, const int (&u4)[4], int it, const float (&r4)[4]) {
+            Frag<E> p4[4];
+            float b4[4];
+            load_quad_p(pos, p4, b4);
+            if (it != prev_i) {
+                frag_load<E>(cq, Qs + (size_t)(it - cs) * KPAD, lane);
+                cbi = ibs[it - cs];
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int isum = __reduce_add_sync(FULL, dot_fx(p4[t], cq));
+                apply(isum, r4[t], p4[t], b4[t], cq, cbi);
+                store_p(u4[t], p4[t], b4[t]);
+            }
+            store_q(it, cq, cbi);
+#pragma unroll
+            for (int e = 0; e < E; ++e) cp.x[e] = p4[3].x[e];
+            cbu = b4[3];
+            prev_u = u4[3];
+            prev_i = it;
+        };
+        // kQuadClean: any items; an item row equal to the previous rating's stays in registers
+        // (predicated loads, no branch), every updated row goes back to the shared-memory tile
+        // (a later rating of the quad may reuse an item: program order through the tile is exact)
+        auto clean_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4]) {
+            Frag<E> p4[4];
+            float b4[4];
+            load_quad_p(pos, p4, b4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (i4[t] != prev_i) {
+                    frag_load<E>(cq, Qs + (size_t)(i4[t] - cs) * KPAD, lane);
+                    cbi = ibs[i4[t] - cs];
+                }
+                prev_i = i4[t];
+                const int isum = __reduce_add_sync(FULL, dot_fx(p4[t], cq));
+                apply(isum, r4[t], p4[t], b4[t], cq, cbi);
+                store_q(i4[t], cq, cbi);
+                store_p(u4[t], p4[t], b4[t]);
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) cp.x[e] = p4[3].x[e];
+            cbu = b4[3];
+            prev_u = u4[3];
+            prev_i = i4[3];
         };
 
         const int32_t done_base = step * W;
@@ -474,12 +550,21 @@ sgd_block_kernel(const SgdParams prm)
                 const uint32_t g = chunk_seq + c_here;
                 const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (g % kStages) * kChunk + (rel % kChunk));
                 const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
-                const uint32_t nv = n - i;   // valid ratings in this quad (>= 1; >= 4 means all)
                 lap(2);
-                update_one(rel, a.x, a.y, __int_as_float(a.z));
-                if (nv > 1) update_one(rel + 1, a.w, b.x, __int_as_float(b.y));
-                if (nv > 2) update_one(rel + 2, b.z, b.w, __int_as_float(c2.x));
-                if (nv > 3) update_one(rel + 3, c2.y, c2.z, __int_as_float(c2.w));
+                const int u4[4] = {a.x & kIdMask, a.w & kIdMask, b.z & kIdMask, c2.y & kIdMask};
+                const int f4[4] = {a.y, b.x, b.w, c2.z};   // item ids with the packer's hint bits
+                const int i4[4] = {a.y & kIdMask, b.x & kIdMask, b.w & kIdMask, c2.z & kIdMask};
+                const float r4[4] = {__int_as_float(a.z), __int_as_float(b.y), __int_as_float(c2.x), __int_as_float(c2.w)};
+                const int qtype = (a.x >> kQuadShift) & 3;
+                if (qtype == kQuadChain) {
+                    chain_quad(rel, u4, i4[0], r4);
+                } else if (qtype == kQuadClean) {
+                    clean_quad(rel, u4, i4, r4);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (!(f4[t] & kFlagPad)) update_one(rel + t, u4[t], i4[t], r4[t], (f4[t] & kFlagStale) != 0);
+                }
                 lap(3);
             }
             se += (double)se_f;
