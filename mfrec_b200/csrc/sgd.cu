@@ -44,8 +44,14 @@
 namespace {
 
 constexpr int kChunk = 64;    // ratings per TMA chunk
-constexpr int kStages = 4;    // chunks in flight per warp (ring of kStages * kChunk ratings)
-constexpr int kDepth = 16;    // P rows in flight per warp (cp.async ring), in stream positions
+#ifndef MF_KSTAGES
+#define MF_KSTAGES 4
+#endif
+#ifndef MF_KDEPTH
+#define MF_KDEPTH 16
+#endif
+constexpr int kStages = MF_KSTAGES;   // chunks in flight per warp (ring of kStages * kChunk ratings)
+constexpr int kDepth = MF_KDEPTH;     // P rows in flight per warp (cp.async ring), in stream positions
 constexpr int kQuadsAhead = kDepth / 4;
 constexpr int kRing = kChunk * kStages;
 static_assert(kChunk % 4 == 0, "chunks must be 16-byte multiples");
@@ -338,9 +344,11 @@ sgd_block_kernel(const SgdParams prm)
 
         // Prefetch cursor: walks the stream one QUAD (4 positions = 48 bytes, 16-byte aligned) at a
         // time, padding entries included (they name packed user 0, a valid row, and are never
-        // consumed).  One cp.async group per quad, so group index == quad index and
-        // cp.async.wait_group<kQuadsAhead-1> at quad x guarantees its four rows have landed once
-        // the cursor stands at x + kQuadsAhead.  Quads past the end commit empty groups.
+        // consumed).  One cp.async group per quad, so group index == quad index.  The first
+        // kQuadsAhead - 1 quads are fetched here; after that the rows of quad x + kQuadsAhead - 1
+        // are requested WHILE quad x is being applied, one row after each warp reduction, so the
+        // address arithmetic and the copies fill the reduction's latency instead of preceding the
+        // dependent chain.  Quads past the end commit empty groups.
         uint32_t pfq = 0;
         auto prefetch_quads_to = [&](uint32_t target) {
 #pragma unroll 1
@@ -369,7 +377,7 @@ sgd_block_kernel(const SgdParams prm)
                 ++pfq;
             }
         };
-        prefetch_quads_to(kQuadsAhead);
+        prefetch_quads_to(kQuadsAhead - 1);
 
         if (nq > 0) mbar_wait(tile_bar, step & 1);
         // item biases of the block: L2 loads (another SM wrote them; L1 may hold a stale line)
@@ -471,7 +479,7 @@ sgd_block_kernel(const SgdParams prm)
             }
         };
         // kQuadChain: one item; its row stays in registers and is stored once
-        auto chain_quad = [&](uint32_t pos, const int (&u4)[4], int it, const float (&r4)[4]) {
+        auto chain_quad = [&](uint32_t pos, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
             load_quad_p(pos, p4, b4);
@@ -482,6 +490,7 @@ sgd_block_kernel(const SgdParams prm)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int isum = __reduce_add_sync(FULL, dot_fx(p4[t], cq));
+                hook(t);
                 apply(isum, r4[t], p4[t], b4[t], cq, cbi);
                 store_p(u4[t], p4[t], b4[t]);
             }
@@ -495,7 +504,7 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadClean: any items; an item row equal to the previous rating's stays in registers
         // (predicated loads, no branch), every updated row goes back to the shared-memory tile
         // (a later rating of the quad may reuse an item: program order through the tile is exact)
-        auto clean_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4]) {
+        auto clean_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
             load_quad_p(pos, p4, b4);
@@ -507,6 +516,7 @@ sgd_block_kernel(const SgdParams prm)
                 }
                 prev_i = i4[t];
                 const int isum = __reduce_add_sync(FULL, dot_fx(p4[t], cq));
+                hook(t);
                 apply(isum, r4[t], p4[t], b4[t], cq, cbi);
                 store_q(i4[t], cq, cbi);
                 store_p(u4[t], p4[t], b4[t]);
@@ -542,9 +552,33 @@ sgd_block_kernel(const SgdParams prm)
                     __syncwarp();
                     while (issued < nchunks && issued < c_here + kStages) issue_chunk(issued++);
                 }
-                prefetch_quads_to(rel / 4 + kQuadsAhead);
+                // the quad whose rows are requested during this iteration
+                const uint32_t fq = rel / 4 + (kQuadsAhead - 1);
+                const bool fvalid = fq < nquads;
+                int fu[4] = {0, 0, 0, 0};
+                const PackedRating *fsrc = ring;
+                if (fvalid) {
+                    const uint32_t fpos = fq * 4;
+                    const uint32_t fg = chunk_seq + fpos / kChunk;
+                    if ((fpos % kChunk) == 0)   // first touch of a chunk: wait for its bulk copy
+                        mbar_wait(my_bar + (fg % kStages), (fg / kStages) & 1u);
+                    fsrc = ring + (fg % kStages) * kChunk + (fpos % kChunk);
+                    const int4 *fq4 = reinterpret_cast<const int4 *>(fsrc);
+                    const int4 fa = fq4[0], fb = fq4[1], fc = fq4[2];
+                    fu[0] = fa.x & kIdMask; fu[1] = fa.w & kIdMask; fu[2] = fb.z & kIdMask; fu[3] = fc.y & kIdMask;
+                }
+                const uint32_t fslot0 = (fq * 4) % kDepth;
+                auto fetch_row = [&](int t) {
+                    if (fvalid) {
+                        float *dst = prow + (fslot0 + t) * KPAD + lane * Frag<E>::V;
+                        const float *gsrc = P_lane + (size_t)fu[t] * KPAD;
+#pragma unroll
+                        for (int c = 0; c < Frag<E>::NV; ++c)
+                            cp_async<Frag<E>::V * 4>(dst + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
+                    }
+                };
                 lap(0);
-                cp_async_wait<kQuadsAhead - 1>();   // the four rows of this quad have landed
+                cp_async_wait<kQuadsAhead - 2>();   // the four rows of this quad have landed
                 __syncwarp();                       // ... and the bias copies / lane 0's stores are visible
                 lap(1);
                 const uint32_t g = chunk_seq + c_here;
@@ -557,14 +591,18 @@ sgd_block_kernel(const SgdParams prm)
                 const float r4[4] = {__int_as_float(a.z), __int_as_float(b.y), __int_as_float(c2.x), __int_as_float(c2.w)};
                 const int qtype = (a.x >> kQuadShift) & 3;
                 if (qtype == kQuadChain) {
-                    chain_quad(rel, u4, i4[0], r4);
+                    chain_quad(rel, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
-                    clean_quad(rel, u4, i4, r4);
+                    clean_quad(rel, u4, i4, r4, fetch_row);
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
+                    for (int t = 0; t < 4; ++t) {
                         if (!(f4[t] & kFlagPad)) update_one(rel + t, u4[t], i4[t], r4[t], (f4[t] & kFlagStale) != 0);
+                        fetch_row(t);
+                    }
                 }
+                if (fvalid && lane < 4) cp_async<4>(pbias + fslot0 + lane, prm.ub + (fsrc[lane].u & kIdMask));
+                cp_async_commit();
                 lap(3);
             }
             se += (double)se_f;
