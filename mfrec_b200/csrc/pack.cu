@@ -250,12 +250,23 @@ void balanced_bins(const int32_t *ids, int64_t n, const std::vector<int32_t> &de
 // (groups are contiguous id ranges, ascending original id inside a group); start[g] = first
 // packed id of group g.
 void partition_ids(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted, int nblocks,
-                   int W, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
+                   int W, int n_slabs, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
                    std::vector<int32_t> &start)
 {
     const int64_t n = (int64_t)deg.size();
     std::vector<int32_t> block_of(n, 0);
     balanced_bins(sorted.data(), n, deg, nblocks, block_of);
+    if (n_slabs > 1) {
+        // The heaviest ids land in the lowest-numbered bins.  A heavy item is a long dependent
+        // chain for the SGD kernel, so deal the bins round-robin over the slabs (bin j -> slab
+        // j mod G): every slab then gets its share of hot items and the slabs of a DSGD ring take
+        // equal time, not just equal counts.
+        const int per = nblocks / n_slabs;
+        for (int64_t id = 0; id < n; ++id) {
+            const int j = block_of[id];
+            block_of[id] = (j % n_slabs) * per + j / n_slabs;
+        }
+    }
     // members of each block, still heaviest first
     std::vector<int64_t> bstart(nblocks + 1, 0);
     for (int64_t id = 0; id < n; ++id) bstart[block_of[id] + 1] += 1;
@@ -438,8 +449,8 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     MF_TRY(sorted_by_degree(ctx, deg_i.p, ni, seed ^ 0x5bd1e995u, sorted_i));
     tr.lap("degree sort");
     for (;;) {
-        partition_ids(h_deg_u, sorted_u, B, W, ug, up, R->h_row_start);
-        partition_ids(h_deg_i, sorted_i, G * B, W, ig, ip, R->h_col_start);
+        partition_ids(h_deg_u, sorted_u, B, W, 1, ug, up, R->h_row_start);
+        partition_ids(h_deg_i, sorted_i, G * B, W, G, ig, ip, R->h_col_start);
         int32_t widest = 0;
         for (int cb = 0; cb < G * B; ++cb)
             widest = std::max(widest, R->h_col_start[(cb + 1) * W] - R->h_col_start[cb * W]);

@@ -42,19 +42,33 @@ class Ring(object):
             return
         dist = self.dist
         dst, src = ring_peers(self.rank, self.world)
+        stage = getattr(self.backend, "stage", None)
+        send = self.backend.slab_tensors(done_slab)
+        recv = self.backend.slab_tensors(next_slab)
+        if stage:   # communicate through buffers the collective library can map directly
+            send, recv, finish = stage(send, recv)
         ops = []
-        for t in self.backend.slab_tensors(done_slab):
+        for t in send:
             ops.append(dist.P2POp(dist.isend, t, dst))
-        for t in self.backend.slab_tensors(next_slab):
+        for t in recv:
             ops.append(dist.P2POp(dist.irecv, t, src))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+        if stage:
+            finish()
 
-    def epoch(self):
+    def epoch(self, trace=None):
+        """trace: optional callable(label) invoked at the step boundaries (CUDA event timing)."""
         for step in range(self.world):
             c = slab_at(self.rank, step, self.world)
+            if trace:
+                trace("k%d" % step)
             self.backend.process_slab(c)
+            if trace:
+                trace("x%d" % step)
             self.exchange(c, slab_at(self.rank, step + 1, self.world))
+        if trace:
+            trace("end")
         return self.backend.sq_err()
 
     def gather_items(self):
@@ -90,6 +104,25 @@ class GpuBackend(object):
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
         self.se = torch.zeros(ratings.G, device=dev, dtype=torch.float64)
         self.bounds = [ratings.slab_items(c) for c in range(ratings.G)]
+
+    def stage(self, send, recv):
+        """The model lives in the library's stream-ordered pool (cudaMallocAsync), which NCCL cannot
+        map for direct peer copies; a 9 MB send through such memory took ~2 ms instead of ~50 us.
+        Stage both directions through torch-allocated buffers (two device copies of a few MB)."""
+        torch = self.torch
+        key = tuple(t.shape for t in send) + tuple(t.shape for t in recv)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage_send = [torch.empty_like(t) for t in send]
+            self._stage_recv = [torch.empty_like(t) for t in recv]
+            self._stage_key = key
+        for s_, t in zip(self._stage_send, send):
+            s_.copy_(t)
+        bufs_recv = self._stage_recv
+
+        def finish():
+            for t, r_ in zip(recv, bufs_recv):
+                t.copy_(r_)
+        return self._stage_send, bufs_recv, finish
 
     def process_slab(self, c):
         self.M.sgd_epoch(self.R, self.kernel, self.hp["lr"], self.hp["K_users"], self.hp["K_items"],
@@ -141,9 +174,18 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
     ring = Ring(be, rank, world, dist)
     nnz_total = nnz_r * world
 
+    import os
+    tracing = bool(os.environ.get("MFREC_DSGD_TRACE"))
+    marks = []
+
+    def mark(label):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(be.stream)
+        marks.append((label, ev))
+
     def one_epoch():
         with torch.cuda.stream(be.stream):
-            se = ring.epoch()
+            se = ring.epoch(mark if tracing else None)
             dist.all_reduce(se)
         return se
 
@@ -155,6 +197,7 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
     dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ses = []
+    del marks[:]
     with ClockSampler(local) as clocks:
         launches1 = ctx.launch_count
         ev0.record(be.stream)
@@ -164,6 +207,24 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
         ctx.sync()
         torch.cuda.synchronize()
         dist.barrier()
+    if tracing:
+        import sys
+        kern = exch = 0.0
+        per_step = {}
+        for (la, ea), (lb, eb) in zip(marks[:-1], marks[1:]):
+            if la == "end":
+                continue
+            dt_ = ea.elapsed_time(eb)
+            per_step[la] = per_step.get(la, 0.0) + dt_ / args.steps
+            if la.startswith("k"):
+                kern += dt_
+            else:
+                exch += dt_
+        print("[dsgd trace] rank %d per step: %s" % (rank, " ".join("%s=%.2f" % kv for kv in sorted(per_step.items()))),
+              file=sys.stderr, flush=True)
+        n_ep = args.steps
+        print("[dsgd trace] rank %d: per epoch: slab kernels %.2f ms, exchange (incl. waiting for the neighbour) %.2f ms"
+              % (rank, kern / n_ep, exch / n_ep), file=sys.stderr, flush=True)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)        # device time, max over ranks
     ms = float(ms.item())
