@@ -42,6 +42,15 @@ struct mfrec_ctx {
     size_t se_cap = 0;
     int32_t *ticks = nullptr;      // per column block hand-over counters of the running SGD launch
     size_t ticks_cap = 0;
+    // Overlap of the host -> device copies of a one-call drop-in with the packer (set by the caller,
+    // consumed and cleared by the callee): rating values / factor arrays that are being copied on
+    // copy_stream into device staging buffers while the context stream already works on the indices.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t values_ready = nullptr;     // mfrec_ratings_pack waits for it before it reads the values
+    struct {
+        const double *u = nullptr, *v = nullptr, *ib = nullptr, *ub = nullptr;  // device, [k][n] / [n]
+        cudaEvent_t ready = nullptr;
+    } staged;                               // mfrec_model_create converts from these instead of copying
     int refs = 1;                  // the creator + every live mfrec_ratings / mfrec_model
     std::string err;
 };
@@ -187,10 +196,10 @@ size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W);
 
 // runtime.cu
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
-                        const int32_t *perm_dev, float *dst_nk);
+                        const int32_t *perm_dev, float *dst_nk, const double *staged_dev = nullptr);
 int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,
                           const int32_t *perm_dev, double *host_kn);
 int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
-                     float *dst);
+                     float *dst, const double *staged_dev = nullptr);
 int mfrec_download_vec(mfrec_ctx *ctx, const float *src, int32_t n, const int32_t *perm_dev,
                        double *host);

@@ -120,14 +120,25 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
         // hints for the SGD kernel (common.cuh).  The ratings that precede this one in its warp's
         // stream are its predecessors in sorted order down to the first bucket of the worker
         // (bucket index rounded down to a multiple of W); looking at 32 RATINGS back covers at
-        // least 32 stream POSITIONS back (padding only adds distance).
+        // least 32 stream POSITIONS back (padding only adds distance).  Inside a bucket equal
+        // users are adjacent; in the earlier buckets of the window the user is found by bisection
+        // (every bucket is sorted by user).
         const uint64_t first_b = b - b % (uint64_t)kl.W;
-        const int shift = kl.bits_u + kl.bits_i;
-        for (int64_t j = s - 1; j >= 0 && j >= s - 32; --j) {
-            const uint64_t kj = __ldg(keys + j);
-            if ((kj >> shift) < first_b) break;
-            if ((int32_t)((kj >> kl.bits_i) & mask_u) == pr.u) { pr.i |= kFlagStale; break; }
+        const int64_t local = s - raw_off[b];
+        bool stale = local > 0 && (int32_t)((__ldg(keys + s - 1) >> kl.bits_i) & mask_u) == pr.u;
+        int64_t remaining = 32 - local;
+        for (uint64_t bb = b; !stale && remaining > 0 && bb > first_b;) {
+            --bb;
+            const int64_t end = raw_off[bb + 1], take = min(remaining, end - raw_off[bb]);
+            int64_t lo = end - take, hi = end;
+            while (lo < hi) {   // first rating of the window whose user is >= pr.u
+                const int64_t mid = (lo + hi) >> 1;
+                if ((int32_t)((__ldg(keys + mid) >> kl.bits_i) & mask_u) < pr.u) lo = mid + 1; else hi = mid;
+            }
+            stale = lo < end && (int32_t)((__ldg(keys + lo) >> kl.bits_i) & mask_u) == pr.u;
+            remaining -= take;
         }
+        if (stale) pr.i |= kFlagStale;
         if (s > raw_off[b] && (int32_t)(__ldg(keys + s - 1) & mask_i) == (pr.i & kIdMask)) pr.i |= kFlagSameItem;
         packed[dst] = pr;
         if (order) order[dst] = (int64_t)src;
@@ -160,6 +171,7 @@ __global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_qu
                                  unsigned long long *__restrict__ type_count)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int mine[3] = {0, 0, 0};
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += stride) {
         const int4 *src = reinterpret_cast<const int4 *>(packed + q * 4);
         const int4 a = src[0], b = src[1], c = src[2];
@@ -171,7 +183,12 @@ __global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_qu
             type = ((i1 & kIdMask) == m0 && (i2 & kIdMask) == m0 && (i3 & kIdMask) == m0) ? kQuadChain : kQuadClean;
         }
         packed[q * 4].u = (a.x & kIdMask) | (type << kQuadShift);
-        if (!(i0 & kFlagPad)) atomicAdd(type_count + type, 1ull);   // statistics (empty quads excluded)
+        if (!(i0 & kFlagPad)) mine[type] += 1;   // statistics (empty quads excluded)
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int tot = __reduce_add_sync(0xffffffffu, mine[t]);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(type_count + t, (unsigned long long)tot);
     }
 }
 
@@ -552,6 +569,11 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         MF_CUDA(ctx, cudaMallocAsync((void **)&R->order, ((size_t)packed_len + 1) * 8, st));
         fill_i64_kernel<<<(unsigned)ceil_div64(packed_len + 1, 256), 256, 0, st>>>(R->order, packed_len, -1);
         MF_LAUNCH_CHECK(ctx);
+    }
+    if (ctx->values_ready) {   // the caller is still copying the rating values on another stream
+        cudaEvent_t ev = ctx->values_ready;
+        ctx->values_ready = nullptr;
+        MF_CUDA(ctx, cudaStreamWaitEvent(st, ev, 0));
     }
     if (nnz > 0) {
         if (ratings_are_f32)

@@ -89,6 +89,7 @@ extern "C" int mfrec_ctx_create(int device, mfrec_ctx **out)
         }
     }
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete ctx;
         return mfrec_set_error(nullptr, MFREC_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
@@ -111,6 +112,10 @@ void mfrec_ctx_release(mfrec_ctx *ctx)
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->se_scratch) cudaFree(ctx->se_scratch);
     if (ctx->ticks) cudaFree(ctx->ticks);
@@ -205,7 +210,7 @@ __global__ void vec_from_dev_kernel(const float *__restrict__ src, int32_t n,
 }
 
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
-                        const int32_t *perm_dev, float *dst_nk)
+                        const int32_t *perm_dev, float *dst_nk, const double *staged_dev)
 {
     if (n == 0) return MFREC_OK;
     if (!host_kn) {
@@ -213,13 +218,17 @@ int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, 
         return MFREC_OK;
     }
     DevBuf<double> stage;
-    MF_CUDA(ctx, stage.alloc((size_t)k * n, ctx->stream));
-    MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host_kn, (size_t)k * n * sizeof(double),
-                                 cudaMemcpyHostToDevice, ctx->stream));
+    const double *src = staged_dev;
+    if (!src) {
+        MF_CUDA(ctx, stage.alloc((size_t)k * n, ctx->stream));
+        MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host_kn, (size_t)k * n * sizeof(double),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        src = stage.p;
+    }
     dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
-    factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(stage.p, k, kpad, n, perm_dev, dst_nk);
+    factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, perm_dev, dst_nk);
     MF_LAUNCH_CHECK(ctx);
-    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!staged_dev) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host buffer is borrowed
     return MFREC_OK;
 }
 
@@ -239,7 +248,7 @@ int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, 
 }
 
 int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
-                     float *dst)
+                     float *dst, const double *staged_dev)
 {
     if (n == 0) return MFREC_OK;
     if (!host) {
@@ -247,12 +256,16 @@ int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_
         return MFREC_OK;
     }
     DevBuf<double> stage;
-    MF_CUDA(ctx, stage.alloc((size_t)n, ctx->stream));
-    MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host, (size_t)n * sizeof(double),
-                                 cudaMemcpyHostToDevice, ctx->stream));
-    vec_to_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(stage.p, n, perm_dev, dst);
+    const double *src = staged_dev;
+    if (!src) {
+        MF_CUDA(ctx, stage.alloc((size_t)n, ctx->stream));
+        MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host, (size_t)n * sizeof(double),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        src = stage.p;
+    }
+    vec_to_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(src, n, perm_dev, dst);
     MF_LAUNCH_CHECK(ctx);
-    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!staged_dev) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MFREC_OK;
 }
 
@@ -337,10 +350,17 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
                              cudaMemcpyDeviceToDevice, ctx->stream));
     }
 #undef MF_M
-    if ((rc = mfrec_upload_factor(ctx, u, k, kpad, ni, m->item_perm, m->Q)) != MFREC_OK) return fail(rc);
-    if ((rc = mfrec_upload_factor(ctx, v, k, kpad, nu, m->user_perm, m->P)) != MFREC_OK) return fail(rc);
-    if ((rc = mfrec_upload_vec(ctx, items_bias, ni, m->item_perm, m->ib)) != MFREC_OK) return fail(rc);
-    if ((rc = mfrec_upload_vec(ctx, users_bias, nu, m->user_perm, m->ub)) != MFREC_OK) return fail(rc);
+    // a one-call drop-in may have staged the float64 arrays on the device already (common.cuh)
+    const auto staged = ctx->staged;
+    ctx->staged = {};
+    if (staged.ready) {
+        cudaError_t we = cudaStreamWaitEvent(ctx->stream, staged.ready, 0);
+        if (we != cudaSuccess) return fail(mfrec_set_error(ctx, MFREC_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(we)));
+    }
+    if ((rc = mfrec_upload_factor(ctx, u, k, kpad, ni, m->item_perm, m->Q, staged.u)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_factor(ctx, v, k, kpad, nu, m->user_perm, m->P, staged.v)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_vec(ctx, items_bias, ni, m->item_perm, m->ib, staged.ib)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_vec(ctx, users_bias, nu, m->user_perm, m->ub, staged.ub)) != MFREC_OK) return fail(rc);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess)
         return fail(mfrec_set_error(ctx, MFREC_ERR_CUDA, "model upload: %s", cudaGetErrorString(e)));

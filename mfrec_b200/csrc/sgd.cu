@@ -971,9 +971,56 @@ extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k
     mfrec_ratings *R = nullptr;
     mfrec_model *M = nullptr;
     Tracer tr("train_kmf", ctx->stream);
-    MF_TRY(mfrec_ratings_pack(ctx, ratings_index, ratings, 0, 0, nnz, ni, nu, nullptr, &o, &R));
+    // Host -> device: the index array goes first on the context stream, so the packer can start
+    // (degrees, partition, sort) while the rating values and the float64 factor arrays are still
+    // crossing PCIe on the copy stream; the packer's gather and the layout conversion wait for
+    // their events.
+    cudaStream_t sa = ctx->stream, sb = ctx->copy_stream;
+    DevBuf<int32_t> d_idx;
+    DevBuf<double> d_r, d_u, d_v, d_ib, d_ub;
+    cudaEvent_t ev_idx = nullptr, ev_val = nullptr, ev_fac = nullptr;
+    struct EvGuard {
+        cudaEvent_t *e[3];
+        mfrec_ctx *c;
+        ~EvGuard()
+        {
+            c->values_ready = nullptr;
+            c->staged = {};
+            cudaStreamSynchronize(c->copy_stream);   // nothing may still write the staging buffers
+            for (auto p : e) if (*p) cudaEventDestroy(*p);
+        }
+    } evg{{&ev_idx, &ev_val, &ev_fac}, ctx};
+    MF_CUDA(ctx, cudaEventCreateWithFlags(&ev_idx, cudaEventDisableTiming));
+    MF_CUDA(ctx, cudaEventCreateWithFlags(&ev_val, cudaEventDisableTiming));
+    MF_CUDA(ctx, cudaEventCreateWithFlags(&ev_fac, cudaEventDisableTiming));
+    MF_CUDA(ctx, d_idx.alloc((size_t)nnz * 2, sa));
+    MF_CUDA(ctx, d_r.alloc((size_t)nnz, sa));
+    MF_CUDA(ctx, d_u.alloc((size_t)k * ni, sa));
+    MF_CUDA(ctx, d_v.alloc((size_t)k * nu, sa));
+    MF_CUDA(ctx, d_ib.alloc(ni, sa));
+    MF_CUDA(ctx, d_ub.alloc(nu, sa));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_idx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, sa));
+    MF_CUDA(ctx, cudaEventRecord(ev_idx, sa));
+    MF_CUDA(ctx, cudaStreamWaitEvent(sb, ev_idx, 0));   // (also orders the pool allocations before sb's use)
+    MF_CUDA(ctx, cudaMemcpyAsync(d_r.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, sb));
+    MF_CUDA(ctx, cudaEventRecord(ev_val, sb));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_v.p, v, (size_t)k * nu * 8, cudaMemcpyHostToDevice, sb));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_u.p, u, (size_t)k * ni * 8, cudaMemcpyHostToDevice, sb));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_ib.p, items_bias, (size_t)ni * 8, cudaMemcpyHostToDevice, sb));
+    MF_CUDA(ctx, cudaMemcpyAsync(d_ub.p, users_bias, (size_t)nu * 8, cudaMemcpyHostToDevice, sb));
+    MF_CUDA(ctx, cudaEventRecord(ev_fac, sb));
+    ctx->values_ready = ev_val;
+    MF_TRY(mfrec_ratings_pack(ctx, d_idx.p, d_r.p, 0, 1, nnz, ni, nu, nullptr, &o, &R));
     tr.lap("pack");
+    ctx->staged.u = d_u.p; ctx->staged.v = d_v.p; ctx->staged.ib = d_ib.p; ctx->staged.ub = d_ub.p;
+    ctx->staged.ready = ev_fac;
     int rc = mfrec_model_create(ctx, R, k, ni, nu, u, v, items_bias, users_bias, &M);
+    if (rc == MFREC_OK) {   // the staging buffers go back to the pool on sa: sb must be done with them
+        cudaError_t we = cudaStreamWaitEvent(sa, ev_fac, 0);
+        if (we != cudaSuccess) rc = mfrec_set_error(ctx, MFREC_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(we));
+    } else {
+        cudaStreamSynchronize(sb);
+    }
     tr.lap("model upload");
     DevBuf<double> d_se;
     if (rc == MFREC_OK && d_se.alloc(nbr_epochs, ctx->stream) != cudaSuccess)
