@@ -18,17 +18,20 @@ struct __align__(4) PackedRating {
     float r;
 };
 static_assert(sizeof(PackedRating) == 12, "rating triple must be 12 bytes");
-// Packed ids use the low 28 bits; the packer leaves hints for the SGD kernel in the bits above,
+// Packed ids use the low 27 bits; the packer leaves hints for the SGD kernel in the bits above,
 // so that the hot loop needs no run-time hazard detection:
-constexpr int32_t kIdMask = 0x0fffffff;
-constexpr int32_t kFlagStale = 1 << 28;     // .i : the user also occurs among the 32 ratings that precede
-                                            //      this one in its warp's stream (a prefetched row may be stale)
+constexpr int32_t kIdMask = 0x07ffffff;
+constexpr int32_t kFlagAdjUser = 1 << 27;   // .i : same user as the previous rating of the bucket (its row is
+                                            //      in registers)
+constexpr int32_t kFlagStale = 1 << 28;     // .i : the user also occurs, NOT adjacently, among the 32 ratings
+                                            //      that precede this one in its warp's stream (a prefetched
+                                            //      row may be stale)
 constexpr int32_t kFlagSameItem = 1 << 29;  // .i : same item as the previous rating of the bucket
 constexpr int32_t kFlagPad = 1 << 30;       // .i : alignment padding, not a rating
 constexpr int kQuadShift = 28;              // .u of the first entry of an aligned quad, 2 bits:
 constexpr int kQuadGeneric = 0;             //      anything (padding, repeated users, ...)
 constexpr int kQuadChain = 1;               //      4 ratings of ONE item, 4 distinct fresh users
-constexpr int kQuadClean = 2;               //      4 ratings, 4 distinct fresh users, any items
+constexpr int kQuadClean = 2;               //      4 ratings, users fresh or equal to their predecessor, any items
 
 struct mfrec_ctx {
     int device = 0;

@@ -125,9 +125,10 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
         // (every bucket is sorted by user).
         const uint64_t first_b = b - b % (uint64_t)kl.W;
         const int64_t local = s - raw_off[b];
-        bool stale = local > 0 && (int32_t)((__ldg(keys + s - 1) >> kl.bits_i) & mask_u) == pr.u;
+        const bool adjacent = local > 0 && (int32_t)((__ldg(keys + s - 1) >> kl.bits_i) & mask_u) == pr.u;
+        bool stale = false;
         int64_t remaining = 32 - local;
-        for (uint64_t bb = b; !stale && remaining > 0 && bb > first_b;) {
+        for (uint64_t bb = b; !adjacent && !stale && remaining > 0 && bb > first_b;) {
             --bb;
             const int64_t end = raw_off[bb + 1], take = min(remaining, end - raw_off[bb]);
             int64_t lo = end - take, hi = end;
@@ -138,6 +139,7 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
             stale = lo < end && (int32_t)((__ldg(keys + lo) >> kl.bits_i) & mask_u) == pr.u;
             remaining -= take;
         }
+        if (adjacent) pr.i |= kFlagAdjUser;   // the predecessor's registers hold the latest row
         if (stale) pr.i |= kFlagStale;
         if (s > raw_off[b] && (int32_t)(__ldg(keys + s - 1) & mask_i) == (pr.i & kIdMask)) pr.i |= kFlagSameItem;
         packed[dst] = pr;
@@ -180,7 +182,8 @@ __global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_qu
         int type = kQuadGeneric;
         if (!(any & (kFlagPad | kFlagStale))) {
             const int m0 = i0 & kIdMask;
-            type = ((i1 & kIdMask) == m0 && (i2 & kIdMask) == m0 && (i3 & kIdMask) == m0) ? kQuadChain : kQuadClean;
+            const bool one_item = (i1 & kIdMask) == m0 && (i2 & kIdMask) == m0 && (i3 & kIdMask) == m0;
+            type = (one_item && !(any & kFlagAdjUser)) ? kQuadChain : kQuadClean;
         }
         packed[q * 4].u = (a.x & kIdMask) | (type << kQuadShift);
         if (!(i0 & kFlagPad)) mine[type] += 1;   // statistics (empty quads excluded)
@@ -379,7 +382,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     if (nnz >= (1ll << 32))
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: nnz >= 2^32 per device");
     if (nu > kIdMask || ni > kIdMask)
-        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: more than 2^28 users or items");
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: more than 2^27 users or items");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Tracer tr("pack", st);

@@ -504,12 +504,18 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadClean: any items; an item row equal to the previous rating's stays in registers
         // (predicated loads, no branch), every updated row goes back to the shared-memory tile
         // (a later rating of the quad may reuse an item: program order through the tile is exact)
-        auto clean_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
+        auto clean_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
+                              const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
             load_quad_p(pos, p4, b4);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
+                if (f4[t] & kFlagAdjUser) {   // same user as the previous rating: its registers, not the ring
+#pragma unroll
+                    for (int e = 0; e < E; ++e) p4[t].x[e] = t ? p4[t ? t - 1 : 0].x[e] : cp.x[e];
+                    b4[t] = t ? b4[t ? t - 1 : 0] : cbu;
+                }
                 if (i4[t] != prev_i) {
                     frag_load<E>(cq, Qs + (size_t)(i4[t] - cs) * KPAD, lane);
                     cbi = ibs[i4[t] - cs];
@@ -593,7 +599,7 @@ sgd_block_kernel(const SgdParams prm)
                 if (qtype == kQuadChain) {
                     chain_quad(rel, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
-                    clean_quad(rel, u4, i4, r4, fetch_row);
+                    clean_quad(rel, u4, i4, f4, r4, fetch_row);
                 } else {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
