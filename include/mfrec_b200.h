@@ -189,8 +189,8 @@ void mfrec_ratings_destroy(mfrec_ratings *r);
  * per epoch, max bucket nnz, packed bytes }. */
 int mfrec_ratings_info(const mfrec_ratings *r, int64_t info[8]);
 /* How the packer classified the aligned groups of 4 ratings for the SGD kernel:
- * counts = { generic, one-item chains, clean } (see mfrec_b200/csrc/common.cuh). */
-int mfrec_ratings_quad_types(const mfrec_ratings *r, int64_t counts[3]);
+ * counts = { generic, one-item chains, clean, independent } (see mfrec_b200/csrc/common.cuh). */
+int mfrec_ratings_quad_types(const mfrec_ratings *r, int64_t counts[4]);
 /* Relabelling: user_perm int32 [nu] / item_perm int32 [ni], old id -> packed id. */
 int mfrec_ratings_perm(mfrec_ctx *ctx, const mfrec_ratings *r, int32_t *user_perm,
                        int32_t *item_perm);

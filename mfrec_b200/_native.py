@@ -363,9 +363,9 @@ class Ratings(object):
 
     def quad_types(self):
         """{generic, chain, clean} quad counts of the layout (SGD kernel fast paths)."""
-        out = (C.c_int64 * 3)()
+        out = (C.c_int64 * 4)()
         _check(lib().mfrec_ratings_quad_types(self._h, out))
-        return dict(generic=int(out[0]), chain=int(out[1]), clean=int(out[2]))
+        return dict(generic=int(out[0]), chain=int(out[1]), clean=int(out[2]), independent=int(out[3]))
 
     def slab_items(self, slab):
         a, b = C.c_int32(), C.c_int32()

@@ -32,6 +32,7 @@ constexpr int kQuadShift = 28;              // .u of the first entry of an align
 constexpr int kQuadGeneric = 0;             //      anything (padding, repeated users, ...)
 constexpr int kQuadChain = 1;               //      4 ratings of ONE item, 4 distinct fresh users
 constexpr int kQuadClean = 2;               //      4 ratings, users fresh or equal to their predecessor, any items
+constexpr int kQuadIndep = 3;               //      4 ratings, 4 distinct fresh users, 4 distinct items
 
 struct mfrec_ctx {
     int device = 0;
@@ -73,7 +74,7 @@ struct mfrec_ratings {
     int32_t max_cb_items = 0;      // widest column block (items) -> shared-memory tile size
     int64_t max_bucket = 0;
     float max_abs_rating = 0.f;    // sizes the fixed-point scale of the warp reduction
-    int64_t quad_types[3] = {0, 0, 0};  // quads by kQuadGeneric / kQuadChain / kQuadClean
+    int64_t quad_types[4] = {0, 0, 0, 0};  // quads by kQuadGeneric / kQuadChain / kQuadClean / kQuadIndep
     // device
     int32_t *user_perm = nullptr;  // [nu] old -> packed id
     int32_t *item_perm = nullptr;  // [ni]

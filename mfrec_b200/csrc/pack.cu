@@ -173,7 +173,7 @@ __global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_qu
                                  unsigned long long *__restrict__ type_count)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int mine[3] = {0, 0, 0};
+    int mine[4] = {0, 0, 0, 0};
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += stride) {
         const int4 *src = reinterpret_cast<const int4 *>(packed + q * 4);
         const int4 a = src[0], b = src[1], c = src[2];
@@ -184,12 +184,15 @@ __global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_qu
             const int m0 = i0 & kIdMask;
             const bool one_item = (i1 & kIdMask) == m0 && (i2 & kIdMask) == m0 && (i3 & kIdMask) == m0;
             type = (one_item && !(any & kFlagAdjUser)) ? kQuadChain : kQuadClean;
+            const int m1 = i1 & kIdMask, m2 = i2 & kIdMask, m3 = i3 & kIdMask;
+            if (!(any & kFlagAdjUser) && m0 != m1 && m0 != m2 && m0 != m3 && m1 != m2 && m1 != m3 && m2 != m3)
+                type = kQuadIndep;
         }
         packed[q * 4].u = (a.x & kIdMask) | (type << kQuadShift);
         if (!(i0 & kFlagPad)) mine[type] += 1;   // statistics (empty quads excluded)
     }
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
+    for (int t = 0; t < 4; ++t) {
         const int tot = __reduce_add_sync(0xffffffffu, mine[t]);
         if ((threadIdx.x & 31) == 0 && tot) atomicAdd(type_count + t, (unsigned long long)tot);
     }
@@ -598,7 +601,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         unsigned long long h_tc[4];
         MF_CUDA(ctx, cudaMemcpyAsync(h_tc, d_tc.p, 32, cudaMemcpyDeviceToHost, st));
         MF_CUDA(ctx, cudaStreamSynchronize(st));
-        for (int t = 0; t < 3; ++t) R->quad_types[t] = (int64_t)h_tc[t];
+        for (int t = 0; t < 4; ++t) R->quad_types[t] = (int64_t)h_tc[t];
     }
     // largest |rating| (sizes the fixed-point reduction scale of the SGD kernel)
     {
@@ -643,10 +646,10 @@ extern "C" int mfrec_ratings_info(const mfrec_ratings *r, int64_t info[8])
     return MFREC_OK;
 }
 
-extern "C" int mfrec_ratings_quad_types(const mfrec_ratings *r, int64_t counts[3])
+extern "C" int mfrec_ratings_quad_types(const mfrec_ratings *r, int64_t counts[4])
 {
     if (!r || !counts) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ratings_quad_types: NULL argument");
-    for (int t = 0; t < 3; ++t) counts[t] = r->quad_types[t];
+    for (int t = 0; t < 4; ++t) counts[t] = r->quad_types[t];
     return MFREC_OK;
 }
 

@@ -501,6 +501,39 @@ sgd_block_kernel(const SgdParams prm)
             prev_u = u4[3];
             prev_i = it;
         };
+        // kQuadIndep: four ratings that share neither a user nor an item: their order does not
+        // matter, so all loads, the four reductions and the four updates are issued side by side
+        // (four independent dependency chains for the scheduler instead of one)
+        auto indep_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
+            Frag<E> p4[4], q4[4];
+            float b4[4], c4[4];
+            load_quad_p(pos, p4, b4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                frag_load<E>(q4[t], Qs + (size_t)(i4[t] - cs) * KPAD, lane);
+                c4[t] = ibs[i4[t] - cs];
+            }
+            int f[4], sm[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) f[t] = dot_fx(p4[t], q4[t]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) sm[t] = __reduce_add_sync(FULL, f[t]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) hook(t);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) apply(sm[t], r4[t], p4[t], b4[t], q4[t], c4[t]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                store_q(i4[t], q4[t], c4[t]);
+                store_p(u4[t], p4[t], b4[t]);
+            }
+#pragma unroll
+            for (int e = 0; e < E; ++e) { cp.x[e] = p4[3].x[e]; cq.x[e] = q4[3].x[e]; }
+            cbu = b4[3];
+            cbi = c4[3];
+            prev_u = u4[3];
+            prev_i = i4[3];
+        };
         // kQuadClean: any items; an item row equal to the previous rating's stays in registers
         // (predicated loads, no branch), every updated row goes back to the shared-memory tile
         // (a later rating of the quad may reuse an item: program order through the tile is exact)
@@ -596,7 +629,9 @@ sgd_block_kernel(const SgdParams prm)
                 const int i4[4] = {a.y & kIdMask, b.x & kIdMask, b.w & kIdMask, c2.z & kIdMask};
                 const float r4[4] = {__int_as_float(a.z), __int_as_float(b.y), __int_as_float(c2.x), __int_as_float(c2.w)};
                 const int qtype = (a.x >> kQuadShift) & 3;
-                if (qtype == kQuadChain) {
+                if (qtype == kQuadIndep) {
+                    indep_quad(rel, u4, i4, r4, fetch_row);
+                } else if (qtype == kQuadChain) {
                     chain_quad(rel, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
                     clean_quad(rel, u4, i4, f4, r4, fetch_row);

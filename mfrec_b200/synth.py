@@ -45,6 +45,10 @@ def marginals(nu, ni, seed=0, item_shift=None, top_item_share=0.0025):
     wi = 1.0 / (np.arange(1, ni + 1, dtype=np.float64) + item_shift)
     wi = wi[rng.permutation(ni)]
     wi /= wi.sum()
+    import os
+    if os.environ.get("MFREC_SYNTH_UNIFORM"):   # experiment: no popularity skew at all
+        wu = np.full(nu, 1.0 / nu)
+        wi = np.full(ni, 1.0 / ni)
     return wu, wi
 
 
