@@ -91,6 +91,17 @@ class GDRecommender(MFRecommender):
         self.relationship_matrix_csc = self.relationship_matrix.T.tocsc()
         return self._topn(user_index, self.nbr_items, nbr_recommendations, 'predict_rating')
 
+    # ---- item-item similarity (gradient_descent.py:827-875): feature 0 is skipped, Pearson default
+    def similar_items(self, item_index, nbr_recommendations=2, similarity_threshold=False,
+                      similarities_output=False, method='pearson'):
+        rows = self.svd_u[1:self.dimensionality, :].T
+        if method == 'norm_cosine':   # log(1 + cosine of the rows centred by the per-feature means)
+            rows = rows - self.svd_u[1:self.dimensionality, :].mean(axis=1)[None, :]
+            return self._similar_rows(rows, item_index, nbr_recommendations, similarity_threshold,
+                                      similarities_output, 'cosine', transform=lambda c: float(np.log(1.0 + c)))
+        return self._similar_rows(rows, item_index, nbr_recommendations, similarity_threshold,
+                                  similarities_output, method)
+
     # ---- fold-in (gradient_descent.py:879-905) ----------------------------------------------------------
     def _retrain(self, valid_ids, ratings_index, ratings, update_users, update_items, verbose):
         # the reference passes `ratings[valid_ids,:]` (a 2-D index into a 1-D array) and the

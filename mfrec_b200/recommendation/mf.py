@@ -99,6 +99,48 @@ class MFRecommender(BaseRecommender):
             items = [self.items_label[i] for i in items]
         return items, scores
 
+    # ---- item-item similarity in factor space (base.py:1420-1466) ----------------------------------
+    def _similar_rows(self, rows, query, nbr_recommendations, similarity_threshold, similarities_output,
+                      method, transform=None):
+        """Top neighbours of row ``query`` of ``rows`` ([n, d]) by cosine / Pearson similarity.
+        Both are dot products of normalised rows, i.e. one row of a Gram matrix: scored and ranked
+        on the device by the top-N kernel (the query itself is excluded there -- the reference
+        drops the first entry of the sorted list, which is the item itself)."""
+        if method not in ('cosine', 'pearson'):
+            raise NotImplementedError("similarity method %r: only 'cosine' and 'pearson' run on the device" % method)
+        x = np.array(rows, dtype=np.float64)
+        if method == 'pearson':
+            x = x - x.mean(axis=1, keepdims=True)
+        norm = np.sqrt((x * x).sum(axis=1, keepdims=True))
+        x = np.divide(x, norm, out=np.zeros_like(x), where=norm > 0)
+        xt = np.ascontiguousarray(x.T)                      # [d, n]: "item factors" and "user factors"
+        n = x.shape[0]
+        N = n - 1 if nbr_recommendations == 'All' else int(nbr_recommendations)
+        items, scores, counts = _native.topn('predict_dot', xt, xt, np.array([query], dtype=np.int32), n,
+                                             None, None, max(N, 1))
+        c = int(counts[0])
+        ids = [int(i) for i in items[0, :c]]
+        sims = [float(v) for v in scores[0, :c]]
+        if transform is not None:
+            sims = [transform(v) for v in sims]
+        if similarity_threshold:
+            keep = [j for j, v in enumerate(sims) if v > similarity_threshold]
+            ids, sims = [ids[j] for j in keep], [sims[j] for j in keep]
+        ids, sims = ids[:N], sims[:N]
+        return (ids, sims) if similarities_output else ids
+
+    def similar_items(self, item_index, nbr_recommendations=2, similarity_threshold=False,
+                      similarities_output=False, method='cosine'):
+        return self._similar_rows(self.svd_u.T, item_index, nbr_recommendations, similarity_threshold,
+                                  similarities_output, method)
+
+    def similar_items_by_label(self, item_label, nbr_recommendations=2, similarity_threshold=False,
+                               similarities_output=False, method='cosine'):
+        out = self.similar_items(self.items_index[item_label], nbr_recommendations, similarity_threshold,
+                                 True, method)
+        labels = [self.items_label[i] for i in out[0]]
+        return (labels, out[1]) if similarities_output else labels
+
     def _predict_alias(self, predictor):
         """'predict' is a class attribute aliasing one of the named predictors."""
         target = getattr(type(self), predictor)

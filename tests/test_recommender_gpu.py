@@ -141,3 +141,44 @@ def test_fold_in_a_new_user():
     assert new_id == nu and rec.svd_v.shape[1] == nu + 1 and rec.users_index['alice'] == nu
     assert np.array_equal(rec.svd_u, items_before)            # items stay frozen (update_items = 0)
     assert np.isfinite(rec.predict_linear(5, new_id))
+
+
+def test_similar_items_match_the_reference_loops():
+    """base.py:1420-1466 / gradient_descent.py:827-875: similarity of one item to every item, sorted,
+    the item itself dropped."""
+    from mfrec_b200.recommendation import GDRecommender, KMFRecommender
+    rng = np.random.default_rng(0)
+    nu, ni, k = 30, 90, 12
+    rec = KMFRecommender(nu, ni, {'nbr_features': k})
+    rec.svd_u = rng.normal(0, 0.3, (k, ni))
+    rec.svd_v = rng.normal(0, 0.3, (k, nu))
+
+    def reference(rows, q, n, method):
+        sims = []
+        for coord in rows:
+            a, b = coord, rows[q]
+            if method == 'pearson':
+                a, b = a - a.mean(), b - b.mean()
+            ip = np.inner(a, b)
+            sims.append(ip / (np.linalg.norm(a) * np.linalg.norm(b)) if ip != 0 else 0.0)
+        order = sorted(range(len(sims)), key=lambda i: sims[i], reverse=True)
+        return order[1:n + 1], [sims[i] for i in order[1:n + 1]]
+
+    for method in ('cosine', 'pearson'):
+        ids, sims = rec.similar_items(17, nbr_recommendations=6, similarities_output=True, method=method)
+        wi, ws = reference(rec.svd_u.T, 17, 6, method)
+        assert ids == wi
+        np.testing.assert_allclose(sims, ws, rtol=1e-5, atol=1e-6)
+    assert rec.similar_items(3, nbr_recommendations=4) == reference(rec.svd_u.T, 3, 4, 'cosine')[0]
+    labels = rec.similar_items_by_label('item5', nbr_recommendations=3)
+    assert labels == ['item%d' % i for i in reference(rec.svd_u.T, 5, 3, 'cosine')[0]]
+    high = rec.similar_items(17, nbr_recommendations='All', similarity_threshold=0.3, similarities_output=True)
+    assert all(v > 0.3 for v in high[1]) and 17 not in high[0]
+    gd = GDRecommender(nu, ni, {'nbr_features': k})
+    gd.svd_u, gd.svd_v = rec.svd_u.copy(), rec.svd_v.copy()
+    ids, sims = gd.similar_items(8, nbr_recommendations=5, similarities_output=True)      # Pearson on features 1..k-1
+    wi, ws = reference(gd.svd_u[1:k, :].T, 8, 5, 'pearson')
+    assert ids == wi
+    np.testing.assert_allclose(sims, ws, rtol=1e-5, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        rec.similar_items(1, method='euclidean')
