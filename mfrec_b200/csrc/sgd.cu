@@ -72,6 +72,7 @@ struct SgdParams {
     int update_users, update_items;
     float fx_scale, fx_inv;       // fixed-point scale of the warp reduction (power of two)
     unsigned long long *timing;   // debug (MFREC_SGD_TIMING=1): [B][W][8] cycle counters, or null
+    int exp;                      // debug (MFREC_SGD_EXP, timing build only): knock-out experiments, results are WRONG
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) + cp.async ------------
@@ -395,6 +396,10 @@ sgd_block_kernel(const SgdParams prm)
         // deterministic warp reduction in 32-bit fixed point: one REDUX instead of a 5-level
         // shuffle butterfly; integer addition is associative, so the result does not depend on
         // lane order.  fx_scale is a power of two chosen from max |rating| (see sgd_epoch).
+        auto warp_sum_fx = [&](int v) {
+            if constexpr (TIMING) { if (prm.exp & 4) return v; }
+            return __reduce_add_sync(FULL, v);
+        };
         auto dot_fx = [&](const Frag<E> &pu, const Frag<E> &q) {
             float part = pu.x[0] * q.x[0];
 #pragma unroll
@@ -402,6 +407,7 @@ sgd_block_kernel(const SgdParams prm)
             return __float2int_rn(part * fx_scale);
         };
         auto apply = [&](int isum, float r, Frag<E> &pu, float &bu, Frag<E> &q, float &bi) {
+            if constexpr (TIMING) { if (prm.exp & 16) { se_f += (float)isum; return; } }
             const float pred = fmaf((float)isum, fx_inv, bi + bu);
             float err, grad;
             if constexpr (KERNEL == MFREC_KERNEL_LINEAR) {
@@ -425,10 +431,12 @@ sgd_block_kernel(const SgdParams prm)
             }
         };
         auto store_p = [&](int u, const Frag<E> &pu, float bu) {
+            if constexpr (TIMING) { if (prm.exp & 1) return; }
             frag_store<E>(pu, prm.P + (size_t)u * KPAD, lane);
             if (lane == 0) prm.ub[u] = bu;
         };
         auto store_q = [&](int it, const Frag<E> &q, float bi) {
+            if constexpr (TIMING) { if (prm.exp & 2) return; }
             frag_store<E>(q, Qs + (size_t)(it - cs) * KPAD, lane);
             if (lane == 0) ibs[it - cs] = bi;
         };
@@ -457,7 +465,7 @@ sgd_block_kernel(const SgdParams prm)
                 frag_load<E>(cq, Qs + (size_t)(it - cs) * KPAD, lane);
                 cbi = ibs[it - cs];
             }
-            const int isum = __reduce_add_sync(FULL, dot_fx(pu, cq));
+            const int isum = warp_sum_fx(dot_fx(pu, cq));
             apply(isum, r, pu, bu, cq, cbi);
             store_q(it, cq, cbi);
             store_p(u, pu, bu);
@@ -489,7 +497,7 @@ sgd_block_kernel(const SgdParams prm)
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int isum = __reduce_add_sync(FULL, dot_fx(p4[t], cq));
+                const int isum = warp_sum_fx(dot_fx(p4[t], cq));
                 hook(t);
                 apply(isum, r4[t], p4[t], b4[t], cq, cbi);
                 store_p(u4[t], p4[t], b4[t]);
@@ -517,7 +525,7 @@ sgd_block_kernel(const SgdParams prm)
 #pragma unroll
             for (int t = 0; t < 4; ++t) f[t] = dot_fx(p4[t], q4[t]);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) sm[t] = __reduce_add_sync(FULL, f[t]);
+            for (int t = 0; t < 4; ++t) sm[t] = warp_sum_fx(f[t]);
 #pragma unroll
             for (int t = 0; t < 4; ++t) hook(t);
 #pragma unroll
@@ -554,7 +562,7 @@ sgd_block_kernel(const SgdParams prm)
                     cbi = ibs[i4[t] - cs];
                 }
                 prev_i = i4[t];
-                const int isum = __reduce_add_sync(FULL, dot_fx(p4[t], cq));
+                const int isum = warp_sum_fx(dot_fx(p4[t], cq));
                 hook(t);
                 apply(isum, r4[t], p4[t], b4[t], cq, cbi);
                 store_q(i4[t], cq, cbi);
@@ -608,6 +616,7 @@ sgd_block_kernel(const SgdParams prm)
                 }
                 const uint32_t fslot0 = (fq * 4) % kDepth;
                 auto fetch_row = [&](int t) {
+                    if constexpr (TIMING) { if (prm.exp & 8) return; }
                     if (fvalid) {
                         float *dst = prow + (fslot0 + t) * KPAD + lane * Frag<E>::V;
                         const float *gsrc = P_lane + (size_t)fu[t] * KPAD;
@@ -882,9 +891,10 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     }
     // debug: MFREC_SGD_TIMING=1 prints per-section cycle counts of the first launches to stderr
     static int timing_env = -1;
-    if (timing_env < 0) timing_env = getenv("MFREC_SGD_TIMING") ? 3 : 0;
+    if (timing_env < 0) timing_env = getenv("MFREC_SGD_TIMING") ? std::max(3, atoi(getenv("MFREC_SGD_TIMING"))) : 0;
     DevBuf<unsigned long long> d_timing;
     prm.timing = nullptr;
+    prm.exp = getenv("MFREC_SGD_EXP") ? atoi(getenv("MFREC_SGD_EXP")) : 0;
     if (timing_env) {
         MF_CUDA(ctx, d_timing.alloc((size_t)r->B * r->W * 8, ctx->stream));
         prm.timing = d_timing.p;
