@@ -171,6 +171,17 @@ int mfrec_bias_stats(mfrec_ctx *ctx, const int32_t *ratings_index, const double 
                      int64_t nnz, int32_t ni, int32_t nu, double K2, double K3, double *mu_out,
                      double *items_bias, double *users_bias);
 
+/* Replaces als_wrmf (mfrec/lib/als_implicit.pyx:208-352) as called by WRMFRecommender.train
+ * (mfrec/recommendation/wrmf.py:83-110): nbr_epochs of alternating least squares for
+ * implicit-feedback WRMF, float64, u [k][nbr_items] and v [k][nbr_users] updated in place.
+ * users_row / items_row are the reference's own arrays (mfrec/lib/datasets.py:13-32):
+ * [0, count_0, count_1, ...] with n_*_row entries, i.e. n_*_row - 1 active rows; *_col hold the
+ * neighbour ids in row order.  c_pos and reg are the reference's c_pos and k arguments. */
+int mfrec_train_als_wrmf(mfrec_ctx *ctx, int nbr_epochs, int k, double *u, double *v,
+                         const int32_t *users_row, int64_t n_users_row, const int32_t *users_col,
+                         const int32_t *items_row, int64_t n_items_row, const int32_t *items_col,
+                         int32_t nbr_users, int32_t nbr_items, int c_pos, double reg);
+
 /* ---- resident objects (what the one-call drop-ins are made of) ------------------- */
 
 /* Ratings layout: COO -> block-bucketed, user-sorted COO in HBM (the GPU counterpart of

@@ -32,7 +32,7 @@ PREDICTORS = {
 EXPORTS = (
     "mfrec_abi_version", "mfrec_ctx_create", "mfrec_ctx_destroy", "mfrec_last_error",
     "mfrec_ctx_stream", "mfrec_ctx_sync", "mfrec_ctx_launch_count", "mfrec_train_kmf",
-    "mfrec_train_funk", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn", "mfrec_topn_sweep",
+    "mfrec_train_funk", "mfrec_train_als_wrmf", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn", "mfrec_topn_sweep",
     "mfrec_bias_stats", "mfrec_ratings_pack", "mfrec_ratings_destroy", "mfrec_ratings_info",
     "mfrec_ratings_quad_types", "mfrec_ratings_perm", "mfrec_ratings_order", "mfrec_ratings_offsets", "mfrec_ratings_packed",
     "mfrec_ratings_slab_items", "mfrec_model_create", "mfrec_model_read", "mfrec_model_destroy",
@@ -183,6 +183,17 @@ def train_funk(variant, min_epochs, max_epochs, min_improvement, k, f_init, lr, 
         _ptr(items_bias), _ptr(users_bias), C.c_int(update_users), C.c_int(update_items),
         C.byref(o), _ptr(fe), _ptr(fr)), ctx.handle)
     return fe, fr
+
+
+def train_als_wrmf(nbr_epochs, k, u, v, users_row, users_col, items_row, items_col, nbr_users,
+                   nbr_items, c_pos=1, reg=0.015, ctx=None):
+    """In-place ALS-WRMF (als_implicit.pyx:208-352) on u [k, ni], v [k, nu]."""
+    ctx = ctx or default_context()
+    _check(lib().mfrec_train_als_wrmf(
+        ctx.handle, C.c_int(nbr_epochs), C.c_int(k), _ptr(u), _ptr(v), _ptr(users_row),
+        C.c_int64(users_row.shape[0]), _ptr(users_col), _ptr(items_row),
+        C.c_int64(items_row.shape[0]), _ptr(items_col), C.c_int32(nbr_users), C.c_int32(nbr_items),
+        C.c_int(int(c_pos)), C.c_double(float(reg))), ctx.handle)
 
 
 def _as(a, dtype):

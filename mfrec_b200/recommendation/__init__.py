@@ -6,3 +6,4 @@ from mfrec_b200.recommendation.base import BaseRecommender, Error  # noqa: F401
 from mfrec_b200.recommendation.mf import MFRecommender  # noqa: F401
 from mfrec_b200.recommendation.kmf import KMFRecommender  # noqa: F401
 from mfrec_b200.recommendation.gradient_descent import GDRecommender  # noqa: F401
+from mfrec_b200.recommendation.wrmf import WRMFRecommender  # noqa: F401

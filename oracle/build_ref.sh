@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE ONLY -- builds the *unmodified* reference kernels as a CPU oracle.
 #
-# Cythonises mfrec/lib/{kmf_train,gd_estimator}.pyx straight from the read-only
+# Cythonises mfrec/lib/{kmf_train,gd_estimator,als_implicit}.pyx straight from the read-only
 # reference checkout (no source is copied into this repository) and compiles the
 # generated C into oracle/_ref/ (git-ignored, NOT gpurun-ignored: the built
 # extension modules travel to the GPU box, where /root/reference does not exist).
@@ -21,7 +21,7 @@ mkdir -p "$OUT"
 PYINC="$($PY -c 'import sysconfig;print(sysconfig.get_paths()["include"])')"
 NPINC="$($PY -c 'import numpy;print(numpy.get_include())')"
 SUFFIX="$($PY -c 'import sysconfig;print(sysconfig.get_config_var("EXT_SUFFIX"))')"
-for m in kmf_train gd_estimator; do
+for m in kmf_train gd_estimator als_implicit; do
   if [ "$OUT/$m$SUFFIX" -nt "$REF/mfrec/lib/$m.pyx" ]; then continue; fi
   $PY -m cython -2 "$REF/mfrec/lib/$m.pyx" -o "$OUT/$m.c" >/dev/null 2>&1 || \
       $PY -m cython -2 "$REF/mfrec/lib/$m.pyx" -o "$OUT/$m.c"

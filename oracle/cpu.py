@@ -149,3 +149,13 @@ def bias_stats(ratings_index, ratings, ni, nu, K2=0.01, K3=0.01):
         C.c_int64(ratings.shape[0]), C.c_int64(ni), C.c_int64(nu), C.c_double(K2),
         C.c_double(K3), _p(ib, np.float64), _p(ub, np.float64))
     return float(mu), ib, ub
+
+
+def als_wrmf(nbr_epochs, dim, u, v, users_row, users_col, items_row, items_col, c_pos=1, k=0.015):
+    """als_implicit.pyx:208-352; in place on u [dim, ni], v [dim, nu]."""
+    ur, uc = np.ascontiguousarray(users_row, np.int32), np.ascontiguousarray(users_col, np.int32)
+    ir, ic = np.ascontiguousarray(items_row, np.int32), np.ascontiguousarray(items_col, np.int32)
+    lib().oracle_als_wrmf(C.c_int(nbr_epochs), C.c_int(dim), _p(u, np.float64), _p(v, np.float64),
+                          _p(ur, np.int32), C.c_int64(ur.shape[0]), _p(uc, np.int32), _p(ir, np.int32),
+                          C.c_int64(ir.shape[0]), _p(ic, np.int32), C.c_int64(v.shape[1]),
+                          C.c_int64(u.shape[1]), C.c_int(c_pos), C.c_double(k))

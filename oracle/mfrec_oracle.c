@@ -347,3 +347,81 @@ double oracle_bias_stats(const int32_t *ratings_index, const double *ratings, in
     free(cnt_i); free(cnt_u);
     return mu;
 }
+
+/*
+ * ALS for implicit-feedback WRMF: mfrec/lib/als_implicit.pyx:208-352 (als_wrmf), restated.
+ * u = item factors [dim][ni], v = user factors [dim][nu]; *_row = [0, count_0, count_1, ...]
+ * (lib/datasets.py:13-32), *_col = neighbour ids.  The reference inverts the dim x dim system
+ * matrix with numpy.linalg.inv (LAPACK) and multiplies; here the system is solved by Gauss-Jordan
+ * elimination with partial pivoting -- equal to float64 round-off for these SPD systems; the
+ * pin against oracle/_ref/als_implicit is at 1e-9 (tests/test_oracle.py).
+ */
+static void solve_dense(double *m, double *b, int n)
+{
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (fabs(m[r * n + c]) > fabs(m[piv * n + c])) piv = r;
+        if (piv != c) {
+            for (int j = 0; j < n; ++j) { double t = m[c * n + j]; m[c * n + j] = m[piv * n + j]; m[piv * n + j] = t; }
+            double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+        const double d = m[c * n + c];
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = m[r * n + c] / d;
+            if (f == 0.0) continue;
+            for (int j = c; j < n; ++j) m[r * n + j] -= f * m[c * n + j];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int c = 0; c < n; ++c) b[c] /= m[c * n + c];
+}
+
+static void als_pass(int dim, const double *x, int64_t nx, double *y, int64_t ny, const int32_t *row,
+                     int64_t n_active, const int32_t *col, int c_pos, double reg, double *HH, double *M,
+                     double *b)
+{
+    for (int f1 = 0; f1 < dim; ++f1)                     /* :257-262 */
+        for (int f2 = 0; f2 < dim; ++f2) {
+            double d = 0.0;
+            for (int64_t i = 0; i < nx; ++i) d += x[f1 * nx + i] * x[f2 * nx + i];
+            HH[f1 + dim * f2] = d;
+        }
+    int64_t start = 0;
+    for (int64_t j = 0; j < n_active; ++j) {
+        start += row[j];                                  /* :267 */
+        const int64_t span = row[j + 1];
+        for (int f1 = 0; f1 < dim; ++f1)
+            for (int f2 = 0; f2 < dim; ++f2) {
+                double d = 0.0;
+                for (int64_t i = 0; i < span; ++i) {
+                    const int64_t id = col[start + i];
+                    d += x[f1 * nx + id] * x[f2 * nx + id] * c_pos;
+                }
+                M[f1 * dim + f2] = HH[f1 + dim * f2] + d + (f1 == f2 ? reg : 0.0);
+            }
+        for (int f = 0; f < dim; ++f) {
+            double d = 0.0;
+            for (int64_t i = 0; i < span; ++i) d += x[f * nx + col[start + i]] * (1 + c_pos);
+            b[f] = d;
+        }
+        solve_dense(M, b, dim);
+        for (int f = 0; f < dim; ++f) y[f * ny + j] = b[f];
+    }
+}
+
+void oracle_als_wrmf(int nbr_epochs, int dim, double *u, double *v, const int32_t *users_row,
+                     int64_t n_users_row, const int32_t *users_col, const int32_t *items_row,
+                     int64_t n_items_row, const int32_t *items_col, int64_t nu, int64_t ni, int c_pos,
+                     double reg)
+{
+    double *HH = (double *)malloc((size_t)dim * dim * sizeof(double));
+    double *M = (double *)malloc((size_t)dim * dim * sizeof(double));
+    double *b = (double *)malloc((size_t)dim * sizeof(double));
+    for (int e = 0; e < nbr_epochs; ++e) {
+        als_pass(dim, u, ni, v, nu, users_row, n_users_row - 1, users_col, c_pos, reg, HH, M, b);
+        als_pass(dim, v, nu, u, ni, items_row, n_items_row - 1, items_col, c_pos, reg, HH, M, b);
+    }
+    free(HH); free(M); free(b);
+}

@@ -1,6 +1,6 @@
 """The reference's own native kernels (TEST INFRASTRUCTURE ONLY).
 
-``oracle/build_ref.sh`` cythonises ``mfrec/lib/{kmf_train,gd_estimator}.pyx`` unmodified
+``oracle/build_ref.sh`` cythonises ``mfrec/lib/{kmf_train,gd_estimator,als_implicit}.pyx`` unmodified
 from the read-only reference checkout into ``oracle/_ref/``; this module just imports the
 resulting extension modules.  On the GPU box only the prebuilt files exist.
 """
@@ -37,6 +37,16 @@ def kmf_train():
     if "kmf" not in _cache:
         _cache["kmf"] = _load("kmf_train")
     return _cache["kmf"]
+
+
+def als_implicit():
+    """mfrec.lib.als_implicit: als_wrmf (None if it was not built)."""
+    if "als" not in _cache:
+        try:
+            _cache["als"] = _load("als_implicit")
+        except ImportError:
+            _cache["als"] = None
+    return _cache["als"]
 
 
 def gd_estimator():

@@ -137,3 +137,33 @@ def test_synth_is_deterministic_and_unique():
     keys = a["idx"][:, 0].astype(np.int64) * 150 + a["idx"][:, 1]
     assert np.unique(keys).shape[0] == 4000
     assert a["r"].min() >= 1 and a["r"].max() <= 5
+
+
+def test_als_wrmf_port_matches_reference_kernel():
+    """oracle_als_wrmf (Gauss-Jordan solve) against the reference's own als_wrmf
+    (als_implicit.pyx:208-352, numpy.linalg.inv) built into oracle/_ref: 1e-9."""
+    from scipy.sparse import lil_matrix
+
+    from mfrec_b200.lib.datasets import create_bool_sparse_col, create_bool_sparse_row
+    from oracle import cpu, ref
+    mod = ref.als_implicit()
+    if mod is None:
+        pytest.skip("oracle/_ref/als_implicit not built")
+    rng = np.random.default_rng(4)
+    nu, ni, k = 23, 17, 6
+    m = lil_matrix((nu, ni))
+    for _ in range(120):
+        m[int(rng.integers(nu - 2)), int(rng.integers(ni - 1))] = 1.0     # trailing rows / cols stay empty
+    ur, uc = create_bool_sparse_row(m)
+    ir, ic = create_bool_sparse_col(m)
+    # the arrays are what the reference's own helpers produce (lib/datasets.py:13-32)
+    rows, cols = m.nonzero()
+    assert np.array_equal(ur, np.r_[0, np.bincount(rows)]) and np.array_equal(uc, cols.astype(np.int32))
+    u0 = rng.normal(0, 0.1, (k, ni))
+    v0 = rng.normal(0, 0.1, (k, nu))
+    u1, v1 = u0.copy(), v0.copy()
+    mod.als_wrmf(3, k, u0, v0, np.zeros((k, k)), np.zeros((k, k)), ur, uc, ir, ic, nu, ni, 1, 0.015, 0)
+    cpu.als_wrmf(3, k, u1, v1, ur, uc, ir, ic, 1, 0.015)
+    np.testing.assert_allclose(u1, u0, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(v1, v0, rtol=1e-9, atol=1e-12)
+    assert not np.array_equal(v0[:, :5], np.zeros((k, 5)))
