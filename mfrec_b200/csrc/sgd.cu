@@ -229,8 +229,8 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
 // takes the generic path, which picks each row's source (registers / prefetch ring / global
 // memory) with warp-uniform branches.
 // ------------------------------------------------------------------------------------------
-template <int E, int KERNEL, bool TIMING>
-__global__ void __launch_bounds__(512, 1)
+template <int E, int KERNEL, bool TIMING, int MAXT>   // MAXT: 256 (W <= 8: 255 registers per thread) or 512
+__global__ void __launch_bounds__(MAXT, 1)
 sgd_block_kernel(const SgdParams prm)
 {
     constexpr int KPAD = E * 32;
@@ -784,12 +784,14 @@ namespace {
 template <int E, bool TIMING>
 int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative)
 {
-    auto fn = kernel == MFREC_KERNEL_LINEAR ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING>
-                                            : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING>;
-    static size_t configured[2] = {0, 0};  // per instantiation (E, TIMING) and kernel
-    if (configured[kernel] < smem) {
+    const bool wide = prm.W > 8;
+    auto fn = kernel == MFREC_KERNEL_LINEAR
+                  ? (wide ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING, 512> : sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING, 256>)
+                  : (wide ? sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING, 512> : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING, 256>);
+    static size_t configured[2][2] = {{0, 0}, {0, 0}};  // per instantiation (E, TIMING), kernel and width
+    if (configured[kernel][wide] < smem) {
         MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[kernel] = smem;
+        configured[kernel][wide] = smem;
     }
     if (cooperative) {
         // all B CTAs must be resident at once: they wait on one another's column blocks
