@@ -250,11 +250,7 @@ extern "C" int mfrec_train_als_wrmf(mfrec_ctx *ctx, int nbr_epochs, int k, doubl
     MF_CUDA(ctx, cudaMemcpyAsync(d_stage.p, v, (size_t)k * nbr_users * 8, cudaMemcpyHostToDevice, st));
     to_rows_f64_kernel<<<dim3((unsigned)ceil_div64(nbr_users, 32), (k + 31) / 32), 256, 0, st>>>(d_stage.p, k, nbr_users, d_V.p);
     MF_LAUNCH_CHECK(ctx);
-    static size_t configured = 0;
-    if (configured < smem) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(als_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    MF_CUDA(ctx, cudaFuncSetAttribute(als_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e = 0; e < nbr_epochs; ++e) {
         MF_TRY(gram(ctx, d_U.p, nbr_items, k, d_part.p, nblocks, d_HH.p));
         if (nau > 0) {

@@ -641,7 +641,10 @@ sgd_block_kernel(const SgdParams prm)
                 if (qtype == kQuadIndep) {
                     indep_quad(rel, u4, i4, r4, fetch_row);
                 } else if (qtype == kQuadChain) {
-                    chain_quad(rel, u4, i4[0], r4, fetch_row);
+                    bool skip = false;
+                    if constexpr (TIMING) skip = (prm.exp & 32) != 0;   // experiment: chains cost nothing
+                    if (skip) { fetch_row(0); fetch_row(1); fetch_row(2); fetch_row(3); }
+                    else chain_quad(rel, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
                     clean_quad(rel, u4, i4, f4, r4, fetch_row);
                 } else {
@@ -788,11 +791,8 @@ int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool coo
     auto fn = kernel == MFREC_KERNEL_LINEAR
                   ? (wide ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING, 512> : sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING, 256>)
                   : (wide ? sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING, 512> : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING, 256>);
-    static size_t configured[2][2] = {{0, 0}, {0, 0}};  // per instantiation (E, TIMING), kernel and width
-    if (configured[kernel][wide] < smem) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[kernel][wide] = smem;
-    }
+    // per device and cheap: set on every launch (a process may hold contexts on several devices)
+    MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cooperative) {
         // all B CTAs must be resident at once: they wait on one another's column blocks
         void *args[] = {(void *)&prm};

@@ -559,11 +559,7 @@ template <int KB, int NA, int ST>
 int launch_sweep(mfrec_ctx *ctx, const SweepParams &prm, int grid)
 {
     const size_t smem = (size_t)NA * KB * 16384 + (size_t)ST * KB * kBN * 128 + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        MF_CUDA(ctx, cudaFuncSetAttribute(topn_sweep_kernel<KB, NA, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    MF_CUDA(ctx, cudaFuncSetAttribute(topn_sweep_kernel<KB, NA, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     topn_sweep_kernel<KB, NA, ST><<<grid, kSweepThreads, smem, ctx->stream>>>(prm);
     MF_LAUNCH_CHECK(ctx);
     return MFREC_OK;
