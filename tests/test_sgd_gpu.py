@@ -257,3 +257,32 @@ def test_item_slabs_on_one_device(native, small_problem):
                   np.ascontiguousarray(p["r"][rep]), ib0, ub0)
     for a, b in ((u0, u1), (v0, v1), (ib0, ib1), (ub0, ub1)):
         np.testing.assert_allclose(b, a, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("k,nu,ni,nnz,B,W", [(128, 500, 8, 3000, 1, 8),      # one item per column group: chain quads
+                                              (64, 900, 16, 6000, 2, 4),      # two items per group
+                                              (20, 3000, 400, 9000, 1, 2),    # sparse users: independent / clean quads
+                                              (256, 700, 40, 5000, 1, 4)])
+def test_quad_fast_paths_match_oracle_replay(native, k, nu, ni, nnz, B, W):
+    """Layouts that make the packer emit mostly one kind of quad (chain / independent / clean), so
+    every straight-line path of the kernel is compared with the oracle replay, for every row width."""
+    from oracle import cpu
+    d = synth.make_ratings(nu, ni, nnz, seed=k)
+    R = native.Ratings(d["idx"], d["r"], ni, nu, row_blocks=B, workers=W, keep_order=1, k_hint=k)
+    qt = R.quad_types()
+    assert sum(qt.values()) > 0
+    rep = R.replay_order()
+    u0, v0, ib0, ub0 = _fresh(nu, ni, k)
+    M = native.Model(k, ni, nu, u0, v0, ib0, ub0, layout=R)
+    for kernel, kid in (("linear", native.KERNEL_LINEAR), ("logistic", native.KERNEL_LOGISTIC)):
+        M.sgd_epoch(R, kid, LR, KU, KI, KB)
+        cpu.kmf_train(kernel, 1, k, LR, KU, KI, KB, u0, v0, np.ascontiguousarray(d["idx"][rep]),
+                      np.ascontiguousarray(d["r"][rep]), ib0, ub0)
+    M.ctx.sync()
+    u1, v1, ib1, ub1 = M.read()
+    for a, b in ((u0, u1), (v0, v1), (ib0, ib1), (ub0, ub1)):
+        np.testing.assert_allclose(b, a, rtol=3e-4, atol=3e-5)
+    if ni == 8:
+        assert qt["chain"] > qt["clean"] + qt["independent"], qt
+    if ni == 400:
+        assert qt["independent"] + qt["clean"] > qt["chain"], qt
