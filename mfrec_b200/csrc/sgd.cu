@@ -229,7 +229,8 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
 // takes the generic path, which picks each row's source (registers / prefetch ring / global
 // memory) with warp-uniform branches.
 // ------------------------------------------------------------------------------------------
-template <int E, int KERNEL, bool TIMING, int MAXT>   // MAXT: 256 (W <= 8: 255 registers per thread) or 512
+template <int E, int KERNEL, bool TIMING, int MAXT, bool GATED>   // MAXT: 256 (W <= 8: 255 registers per thread) or 512;
+                                                                    // GATED: honour update_users / update_items (else both on)
 __global__ void __launch_bounds__(MAXT, 1)
 sgd_block_kernel(const SgdParams prm)
 {
@@ -266,7 +267,7 @@ sgd_block_kernel(const SgdParams prm)
     }
 
     const float lr = prm.lr;
-    const bool upd_u = prm.update_users != 0, upd_i = prm.update_items != 0;
+    const bool upd_u = !GATED || prm.update_users != 0, upd_i = !GATED || prm.update_items != 0;
     // q' = q + lr (g p - Ki q) = (1 - lr Ki) q + (lr g) p, likewise for p (frozen side: a = 1, gl = 0)
     const float a_i = upd_i ? 1.f - prm.lr * prm.Ki : 1.f;
     const float a_u = upd_u ? 1.f - prm.lr * prm.Ku : 1.f;
@@ -788,9 +789,15 @@ template <int E, bool TIMING>
 int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative)
 {
     const bool wide = prm.W > 8;
-    auto fn = kernel == MFREC_KERNEL_LINEAR
-                  ? (wide ? sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING, 512> : sgd_block_kernel<E, MFREC_KERNEL_LINEAR, TIMING, 256>)
-                  : (wide ? sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING, 512> : sgd_block_kernel<E, MFREC_KERNEL_LOGISTIC, TIMING, 256>);
+    // both sides updated (the training call) gets the variant without the gates; fold-in calls
+    // (update_users / update_items = 0) the gated one
+    const bool gated = !(prm.update_users && prm.update_items);
+    void (*fn)(const SgdParams) = nullptr;
+#define MF_PICK(K)                                                                                     \
+    fn = wide ? (gated ? sgd_block_kernel<E, K, TIMING, 512, true> : sgd_block_kernel<E, K, TIMING, 512, false>) \
+              : (gated ? sgd_block_kernel<E, K, TIMING, 256, true> : sgd_block_kernel<E, K, TIMING, 256, false>)
+    if (kernel == MFREC_KERNEL_LINEAR) { MF_PICK(MFREC_KERNEL_LINEAR); } else { MF_PICK(MFREC_KERNEL_LOGISTIC); }
+#undef MF_PICK
     // per device and cheap: set on every launch (a process may hold contexts on several devices)
     MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cooperative) {
