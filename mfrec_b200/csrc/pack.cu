@@ -33,6 +33,7 @@
 #include <queue>
 
 #include "common.cuh"
+#include "partition.h"
 
 namespace {
 
@@ -211,110 +212,6 @@ int bits_for(int64_t n)
     return b;
 }
 
-// Balanced partition of ids (given heaviest first) into `bins` bins by (degree + 1).
-// The head (8 ids per bin) is placed by exact longest-processing-time-first with a heap; the long
-// tail of light ids is dealt in rounds -- the bins still below the target load, lightest first,
-// each take the next heaviest id -- which is O(n) instead of O(n log bins) and within ~0.1 % of
-// LPT on power-law degrees.  Deterministic.
-void balanced_bins(const int32_t *ids, int64_t n, const std::vector<int32_t> &deg, int bins,
-                   std::vector<int32_t> &bin_of)
-{
-    typedef std::pair<int64_t, int> Load;  // (load, bin): min-heap, ties -> lowest bin
-    std::vector<int64_t> load(bins, 0);
-    int64_t total = 0;
-    for (int64_t j = 0; j < n; ++j) total += (int64_t)deg[ids[j]] + 1;
-    const int64_t head = std::min<int64_t>(n, (int64_t)8 * bins);
-    {
-        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-        for (int b = 0; b < bins; ++b) heap.push(Load(0, b));
-        for (int64_t j = 0; j < head; ++j) {
-            Load top = heap.top();
-            heap.pop();
-            bin_of[ids[j]] = top.second;
-            top.first += (int64_t)deg[ids[j]] + 1;
-            load[top.second] = top.first;
-            heap.push(top);
-        }
-    }
-    if (head == n) return;
-    const int64_t target = (total + bins - 1) / bins;
-    std::vector<int> order(bins);   // bins by (load, index), kept sorted with an adaptive sort
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-        return load[a] != load[b] ? load[a] < load[b] : a < b;
-    });
-    int64_t pos = head;
-    while (pos < n) {
-        int m = 0;   // bins below the target take part (all of them if none is)
-        while (m < bins && load[order[m]] < target) ++m;
-        if (m == 0) m = bins;
-        m = (int)std::min<int64_t>(m, n - pos);
-        for (int j = 0; j < m; ++j) {
-            const int32_t id = ids[pos + j];
-            bin_of[id] = order[j];
-            load[order[j]] += (int64_t)deg[id] + 1;
-        }
-        pos += m;
-        for (int j = 1; j < bins; ++j) {   // insertion sort: the order changes little per round
-            const int bj = order[j];
-            int i = j - 1;
-            while (i >= 0 && (load[order[i]] > load[bj] || (load[order[i]] == load[bj] && order[i] > bj))) {
-                order[i + 1] = order[i];
-                --i;
-            }
-            order[i + 1] = bj;
-        }
-    }
-}
-
-// Hierarchical partition: ids -> nblocks blocks -> W groups each, balanced by (degree + 1).
-// `sorted` lists all ids heaviest first (ties in a seeded pseudo-random order; computed on the
-// device).  Outputs, for every id, its group (block * W + group-in-block) and its packed id
-// (groups are contiguous id ranges, ascending original id inside a group); start[g] = first
-// packed id of group g.
-void partition_ids(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted, int nblocks,
-                   int W, int n_slabs, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
-                   std::vector<int32_t> &start)
-{
-    const int64_t n = (int64_t)deg.size();
-    std::vector<int32_t> block_of(n, 0);
-    balanced_bins(sorted.data(), n, deg, nblocks, block_of);
-    if (n_slabs > 1) {
-        // The heaviest ids land in the lowest-numbered bins.  A heavy item is a long dependent
-        // chain for the SGD kernel, so deal the bins round-robin over the slabs (bin j -> slab
-        // j mod G): every slab then gets its share of hot items and the slabs of a DSGD ring take
-        // equal time, not just equal counts.
-        const int per = nblocks / n_slabs;
-        for (int64_t id = 0; id < n; ++id) {
-            const int j = block_of[id];
-            block_of[id] = (j % n_slabs) * per + j / n_slabs;
-        }
-    }
-    // members of each block, still heaviest first
-    std::vector<int64_t> bstart(nblocks + 1, 0);
-    for (int64_t id = 0; id < n; ++id) bstart[block_of[id] + 1] += 1;
-    for (int b = 0; b < nblocks; ++b) bstart[b + 1] += bstart[b];
-    std::vector<int32_t> members(n);
-    {
-        std::vector<int64_t> cur(bstart.begin(), bstart.end() - 1);
-        for (int64_t j = 0; j < n; ++j) members[cur[block_of[sorted[j]]]++] = sorted[j];
-    }
-    group_of.assign(n, 0);
-    std::vector<int32_t> sub(n, 0);
-    for (int b = 0; b < nblocks; ++b) {
-        balanced_bins(members.data() + bstart[b], bstart[b + 1] - bstart[b], deg, W, sub);
-        for (int64_t j = bstart[b]; j < bstart[b + 1]; ++j) group_of[members[j]] = b * W + sub[members[j]];
-    }
-    const int ng = nblocks * W;
-    std::vector<int32_t> count(ng + 1, 0);
-    for (int64_t id = 0; id < n; ++id) count[group_of[id] + 1] += 1;
-    start.assign(ng + 1, 0);
-    for (int g = 0; g < ng; ++g) start[g + 1] = start[g] + count[g + 1];
-    std::vector<int32_t> cursor(start.begin(), start.end() - 1);
-    perm.assign(n, 0);
-    for (int64_t id = 0; id < n; ++id) perm[id] = cursor[group_of[id]]++;
-}
-
 // sort key of an id: heaviest first, ties in a seeded pseudo-random order
 __global__ void degree_key_kernel(const int32_t *__restrict__ deg, int32_t n, uint64_t seed,
                                   uint64_t *__restrict__ keys, int32_t *__restrict__ ids)
@@ -472,8 +369,8 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     MF_TRY(sorted_by_degree(ctx, deg_i.p, ni, seed ^ 0x5bd1e995u, sorted_i));
     tr.lap("degree sort");
     for (;;) {
-        partition_ids(h_deg_u, sorted_u, B, W, 1, ug, up, R->h_row_start);
-        partition_ids(h_deg_i, sorted_i, G * B, W, G, ig, ip, R->h_col_start);
+        mfrec_part::partition_ids(h_deg_u, sorted_u, B, W, 1, ug, up, R->h_row_start);
+        mfrec_part::partition_ids(h_deg_i, sorted_i, G * B, W, G, ig, ip, R->h_col_start);
         int32_t widest = 0;
         for (int cb = 0; cb < G * B; ++cb)
             widest = std::max(widest, R->h_col_start[(cb + 1) * W] - R->h_col_start[cb * W]);

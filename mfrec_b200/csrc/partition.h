@@ -1,0 +1,123 @@
+// Host-side balanced partition of users / items into blocks and groups (used by pack.cu).
+// Header-only and free of CUDA so that it can be unit-tested and timed on a CPU
+// (tools/partition_bench.cpp, tests/test_partition_cpu.py).
+#pragma once
+
+#include <stdint.h>
+
+#include <algorithm>
+#include <functional>
+#include <numeric>
+#include <queue>
+#include <utility>
+#include <vector>
+
+namespace mfrec_part {
+
+// Balanced partition of n elements, given HEAVIEST FIRST by their degrees, into `bins` bins by
+// (degree + 1).  Everything works on positions in that order ("ranks"): sequential memory only.
+// The head (8 elements per bin) is placed by exact longest-processing-time-first with a heap; the
+// long tail of light elements is dealt in rounds -- the bins still below the target load,
+// lightest first, each take the next heaviest element -- which is O(n) instead of O(n log bins)
+// and within ~0.1 % of LPT on power-law degrees.  Deterministic.
+inline void balanced_bins(const int32_t *deg_sorted, int64_t n, int bins, int32_t *bin_of_rank)
+{
+    typedef std::pair<int64_t, int> Load;  // (load, bin): min-heap, ties -> lowest bin
+    std::vector<int64_t> load(bins, 0);
+    int64_t total = 0;
+    for (int64_t j = 0; j < n; ++j) total += (int64_t)deg_sorted[j] + 1;
+    const int64_t head = std::min<int64_t>(n, (int64_t)8 * bins);
+    {
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+        for (int b = 0; b < bins; ++b) heap.push(Load(0, b));
+        for (int64_t j = 0; j < head; ++j) {
+            Load top = heap.top();
+            heap.pop();
+            bin_of_rank[j] = top.second;
+            top.first += (int64_t)deg_sorted[j] + 1;
+            load[top.second] = top.first;
+            heap.push(top);
+        }
+    }
+    if (head == n) return;
+    const int64_t target = (total + bins - 1) / bins;
+    std::vector<int> order(bins);   // bins by (load, index), kept sorted with an adaptive sort
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        return load[a] != load[b] ? load[a] < load[b] : a < b;
+    });
+    int64_t pos = head;
+    while (pos < n) {
+        int m = 0;   // bins below the target take part (all of them if none is)
+        while (m < bins && load[order[m]] < target) ++m;
+        if (m == 0) m = bins;
+        m = (int)std::min<int64_t>(m, n - pos);
+        for (int j = 0; j < m; ++j) {
+            bin_of_rank[pos + j] = order[j];
+            load[order[j]] += (int64_t)deg_sorted[pos + j] + 1;
+        }
+        pos += m;
+        for (int j = 1; j < bins; ++j) {   // insertion sort: the order changes little per round
+            const int bj = order[j];
+            int i = j - 1;
+            while (i >= 0 && (load[order[i]] > load[bj] || (load[order[i]] == load[bj] && order[i] > bj))) {
+                order[i + 1] = order[i];
+                --i;
+            }
+            order[i + 1] = bj;
+        }
+    }
+}
+
+// Hierarchical partition: ids -> nblocks blocks -> W groups each, balanced by (degree + 1).
+// `sorted` lists all ids heaviest first (ties in a seeded pseudo-random order; computed on the
+// device).  Outputs, for every id, its group (block * W + group-in-block) and its packed id
+// (groups are contiguous id ranges, ascending original id inside a group); start[g] = first
+// packed id of group g.
+inline void partition_ids(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted, int nblocks,
+                          int W, int n_slabs, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
+                          std::vector<int32_t> &start)
+{
+    const int64_t n = (int64_t)deg.size();
+    std::vector<int32_t> deg_sorted(n), block_r(n);
+    for (int64_t j = 0; j < n; ++j) deg_sorted[j] = deg[sorted[j]];   // the one gather by id
+    balanced_bins(deg_sorted.data(), n, nblocks, block_r.data());
+    if (n_slabs > 1) {
+        // The heaviest ids land in the lowest-numbered bins.  A heavy item is a long dependent
+        // chain for the SGD kernel, so deal the bins round-robin over the slabs (bin j -> slab
+        // j mod G): every slab then gets its share of hot items and the slabs of a DSGD ring take
+        // equal time, not just equal counts.
+        const int per = nblocks / n_slabs;
+        for (int64_t j = 0; j < n; ++j) block_r[j] = (block_r[j] % n_slabs) * per + block_r[j] / n_slabs;
+    }
+    // ranks of each block, still heaviest first (counting sort by block)
+    std::vector<int64_t> bstart(nblocks + 1, 0);
+    for (int64_t j = 0; j < n; ++j) bstart[block_r[j] + 1] += 1;
+    for (int b = 0; b < nblocks; ++b) bstart[b + 1] += bstart[b];
+    std::vector<int32_t> members(n), mdeg(n), sub(n);
+    {
+        std::vector<int64_t> cur(bstart.begin(), bstart.end() - 1);
+        for (int64_t j = 0; j < n; ++j) {
+            const int64_t at = cur[block_r[j]]++;
+            members[at] = (int32_t)j;
+            mdeg[at] = deg_sorted[j];
+        }
+    }
+    group_of.assign(n, 0);
+    for (int b = 0; b < nblocks; ++b) {
+        const int64_t a = bstart[b], m = bstart[b + 1] - a;
+        balanced_bins(mdeg.data() + a, m, W, sub.data() + a);
+        for (int64_t t = a; t < a + m; ++t) group_of[sorted[members[t]]] = b * W + sub[t];   // the one scatter by id
+    }
+    const int ng = nblocks * W;
+    std::vector<int32_t> count(ng + 1, 0);
+    for (int64_t id = 0; id < n; ++id) count[group_of[id] + 1] += 1;
+    start.assign(ng + 1, 0);
+    for (int g = 0; g < ng; ++g) start[g + 1] = start[g] + count[g + 1];
+    std::vector<int32_t> cursor(start.begin(), start.end() - 1);
+    perm.assign(n, 0);
+    for (int64_t id = 0; id < n; ++id) perm[id] = cursor[group_of[id]]++;
+}
+
+
+}  // namespace mfrec_part
