@@ -245,7 +245,11 @@ def run_native(args):
                 "kernel": "sgd_block_kernel", "algorithmic_bytes_per_update": bpu,
                 "algorithmic_bytes_per_launch": bpu * upl,
                 "updates_per_launch": upl,
-                "avg_launch_us": ms * 1e3 / max(n_sgd, 1)}
+                "avg_launch_us": ms * 1e3 / max(n_sgd, 1),
+                "note": "algorithmic bytes count the Q_i read+write of every update, but a column block's Q rows "
+                        "stay in shared memory for a whole sub-epoch and most P-row sectors hit in the 126 MB L2 "
+                        "(see traffic: measured DRAM bytes per launch), so frac can exceed 1; the kernel is "
+                        "instruction-issue bound, not DRAM bound (profiles/README.md)"}
 
     # ---------------- end-to-end arm: the public drop-in call with host buffers -----------------
     e2e = None
