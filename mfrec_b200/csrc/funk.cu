@@ -17,6 +17,7 @@
 // `while rmse <= rmse_last - min_improvement` control of the reference (rmse carried across
 // features, max_epochs ignored) runs on the host, one device reduction per pass.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -54,98 +55,124 @@ struct FunkParams {
     const double *ibp;   // [ni] item biases, packed order (variant > 0)
     const double *ubp;   // [nu]
     const double *cache; // [packed_len]
-    double *se_part;     // [B]
-    int B, W, s;
+    double *se_part;     // [B] per-CTA sums of this launch
+    int32_t *ticks;      // [B] sub-epochs finished on each column block in this launch, or null
+    int B, W, s_begin, s_end;
     int tile_rows;
     int variant;
     double lr, K, overall, trail;
     int update_users, update_items;
 };
 
+__device__ __forceinline__ int funk_ld_acquire(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void funk_st_release(int32_t *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One launch = sub-epochs [s_begin, s_end) of one training pass.  With `ticks` the launch is
+// persistent and cooperative (all B sub-epochs): column blocks pass from CTA to CTA through
+// release / acquire counters exactly as in sgd.cu, instead of one kernel boundary per sub-epoch.
 __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = prm.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rb = blockIdx.x;
-    const int cbl = (rb + prm.s) % prm.B;
-    const int cs = prm.col_start[cbl * W];
-    const int nq = prm.col_start[(cbl + 1) * W] - cs;
     double *ufs = reinterpret_cast<double *>(smem_raw);
     double *ibs = ufs + prm.tile_rows;
     double *se_s = ibs + prm.tile_rows;
     int64_t *boff = reinterpret_cast<int64_t *>(se_s + W);
     int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
-
-    const int64_t bucket_base = ((int64_t)rb * prm.B + cbl) * W * W;
-    for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
-        boff[i] = prm.bucket_off[bucket_base + i];
-        if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
-    }
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
-        ufs[i] = prm.uf[cs + i];
-        ibs[i] = prm.variant ? prm.ibp[cs + i] : 0.0;
-    }
-    __syncthreads();
-
     const double lr = prm.lr, K = prm.K;
     double se = 0.0;
-    for (int p = 0; p < W; ++p) {
-        const int64_t a = boff[warp * W + p];
-        const int n = bcnt[warp * W + p];
-        int prev_u = -1;
-        double vf_cur = 0.0;
-        for (int base = 0; base < n; base += 32) {
-            const int j = base + lane;
-            PackedRating rt;
-            rt.u = 0; rt.i = cs; rt.r = 0.f;
-            double c = 0.0, vfu = 0.0, bb = 1.0;
-            if (j < n) {
-                rt = prm.packed[a + j];
-                rt.u &= kIdMask;   // the packer's hint bits (common.cuh) stay in rt.i until the replay
-                c = prm.cache[a + j];
-                vfu = prm.vf[rt.u];
-                // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
-                bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[(rt.i & kIdMask) - cs]), prm.ubp[rt.u])
-                                 : 1.0;
-            }
-            const int cnt = min(32, n - base);
-            for (int t = 0; t < cnt; ++t) {
-                const int u_t = __shfl_sync(0xffffffffu, rt.u, t);
-                const int if_t = __shfl_sync(0xffffffffu, rt.i, t);
-                const int i_t = if_t & kIdMask;
-                const double r_t = (double)__shfl_sync(0xffffffffu, rt.r, t);
-                const double c_t = __shfl_sync(0xffffffffu, c, t);
-                double v_t = __shfl_sync(0xffffffffu, vfu, t);
-                const double b_t = __shfl_sync(0xffffffffu, bb, t);
-                if (u_t == prev_u) {
-                    v_t = vf_cur;                                  // same user as the last rating
-                } else {
-                    if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
-                    if (if_t & kFlagStale) {
-                        // the user occurred among the 32 preceding ratings: the staged scalar may
-                        // predate that update; lane 0 has written it back, read it again
-                        __syncwarp();
-                        v_t = prm.vf[u_t];
-                    }
-                }
-                const double mf = ufs[i_t - cs];
-                const double pr = funk_estimate(mf, v_t, c_t, b_t, prm.trail, 1);
-                const double err = __dadd_rn(r_t, -pr);
-                se = __dadd_rn(se, __dmul_rn(err, err));
-                const double cf = v_t;
-                if (prm.update_items)
-                    ufs[i_t - cs] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
-                vf_cur = prm.update_users
-                             ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
-                             : cf;
-                prev_u = u_t;
-            }
+    for (int s = prm.s_begin; s < prm.s_end; ++s) {
+        const int cbl = (rb + s) % prm.B;
+        const int cs = prm.col_start[cbl * W];
+        const int nq = prm.col_start[(cbl + 1) * W] - cs;
+        const int64_t bucket_base = ((int64_t)rb * prm.B + cbl) * W * W;
+        for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
+            boff[i] = prm.bucket_off[bucket_base + i];
+            if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
         }
-        if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
-        __syncthreads();   // phase boundary (also orders lane 0's stores before the next loads)
+        if (prm.ticks && threadIdx.x == 0)
+            while (funk_ld_acquire(prm.ticks + cbl) < s) __nanosleep(64);
+        __syncthreads();   // the column block is ours; descriptors visible
+        // item scalars: L2 loads (another SM wrote them; L1 may hold a stale line)
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+            ufs[i] = __ldcg(prm.uf + cs + i);
+            ibs[i] = prm.variant ? prm.ibp[cs + i] : 0.0;
+        }
+        __syncthreads();
+        for (int p = 0; p < W; ++p) {
+            const int64_t a = boff[warp * W + p];
+            const int n = bcnt[warp * W + p];
+            int prev_u = -1;
+            double vf_cur = 0.0;
+            for (int base = 0; base < n; base += 32) {
+                const int j = base + lane;
+                PackedRating rt;
+                rt.u = 0; rt.i = cs; rt.r = 0.f;
+                double c = 0.0, vfu = 0.0, bb = 1.0;
+                if (j < n) {
+                    rt = prm.packed[a + j];
+                    rt.u &= kIdMask;   // the packer's hint bits (common.cuh) stay in rt.i until the replay
+                    c = prm.cache[a + j];
+                    vfu = prm.vf[rt.u];
+                    // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
+                    bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[(rt.i & kIdMask) - cs]), prm.ubp[rt.u])
+                                     : 1.0;
+                }
+                const int cnt = min(32, n - base);
+                for (int t = 0; t < cnt; ++t) {
+                    const int u_t = __shfl_sync(0xffffffffu, rt.u, t);
+                    const int if_t = __shfl_sync(0xffffffffu, rt.i, t);
+                    const int i_t = if_t & kIdMask;
+                    const double r_t = (double)__shfl_sync(0xffffffffu, rt.r, t);
+                    const double c_t = __shfl_sync(0xffffffffu, c, t);
+                    double v_t = __shfl_sync(0xffffffffu, vfu, t);
+                    const double b_t = __shfl_sync(0xffffffffu, bb, t);
+                    if (u_t == prev_u) {
+                        v_t = vf_cur;                                  // same user as the last rating
+                    } else {
+                        if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
+                        if (if_t & (kFlagStale | kFlagAdjUser)) {
+                            // the user occurred among the 32 preceding ratings: the staged scalar may
+                            // predate that update; lane 0 has written it back, read it again
+                            __syncwarp();
+                            v_t = prm.vf[u_t];
+                        }
+                    }
+                    const double mf = ufs[i_t - cs];
+                    const double pr = funk_estimate(mf, v_t, c_t, b_t, prm.trail, 1);
+                    const double err = __dadd_rn(r_t, -pr);
+                    se = __dadd_rn(se, __dmul_rn(err, err));
+                    const double cf = v_t;
+                    if (prm.update_items)
+                        ufs[i_t - cs] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
+                    vf_cur = prm.update_users
+                                 ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
+                                 : cf;
+                    prev_u = u_t;
+                }
+            }
+            if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
+            __syncthreads();   // phase boundary (also orders lane 0's stores before the next loads)
+        }
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.uf[cs + i] = ufs[i];
+        if (prm.ticks) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) funk_st_release(prm.ticks + cbl, s + 1);
+        } else {
+            __syncthreads();
+        }
     }
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.uf[cs + i] = ufs[i];
     if (lane == 0) se_s[warp] = se;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -327,6 +354,10 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
         MF_CUDA(ctx, ibp.alloc(ni, ctx->stream));
         MF_CUDA(ctx, ubp.alloc(nu, ctx->stream));
         MF_CUDA(ctx, se_part.alloc((size_t)R->B * R->B, ctx->stream));
+        // one persistent cooperative launch per pass when all B CTAs fit at once (see sgd.cu)
+        const bool persistent = ctx->coop_launch && !getenv("MFREC_SGD_LAUNCH_PER_SUBEPOCH") && R->B <= ctx->sm_count;
+        DevBuf<int32_t> ticks;
+        MF_CUDA(ctx, ticks.alloc(R->B, ctx->stream));
         MF_CUDA(ctx, se_tot.alloc(1, ctx->stream));
         const int gi = (ni + 255) / 256, gu = (nu + 255) / 256;
         gather_row_kernel<<<gi, 256, 0, st>>>(variant ? dib.p : nullptr, ni, R->item_perm, ibp.p);
@@ -350,13 +381,22 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
             int epoch = 0;
             while (epoch < min_epochs || rmse <= rmse_last - min_improvement) {
                 rmse_last = rmse;
-                for (int s = 0; s < R->B; ++s) {
-                    prm.s = s;
-                    prm.se_part = se_part.p + (size_t)s * R->B;
-                    funk_train_kernel<<<R->B, R->W * 32, smem, st>>>(prm);
-                    MF_LAUNCH_CHECK(ctx);
+                if (persistent) {
+                    MF_CUDA(ctx, cudaMemsetAsync(ticks.p, 0, (size_t)R->B * 4, st));
+                    prm.s_begin = 0; prm.s_end = R->B; prm.ticks = ticks.p; prm.se_part = se_part.p;
+                    void *args[] = {(void *)&prm};
+                    MF_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)funk_train_kernel, dim3(R->B), dim3(R->W * 32),
+                                                             args, smem, st));
+                    ctx->launches += 1;
+                } else {
+                    for (int s = 0; s < R->B; ++s) {
+                        prm.s_begin = s; prm.s_end = s + 1; prm.ticks = nullptr;
+                        prm.se_part = se_part.p + (size_t)s * R->B;
+                        funk_train_kernel<<<R->B, R->W * 32, smem, st>>>(prm);
+                        MF_LAUNCH_CHECK(ctx);
+                    }
                 }
-                sum_parts_kernel<<<1, 32, 0, st>>>(se_part.p, R->B * R->B, se_tot.p);
+                sum_parts_kernel<<<1, 32, 0, st>>>(se_part.p, persistent ? R->B : R->B * R->B, se_tot.p);
                 MF_LAUNCH_CHECK(ctx);
                 double se = 0.0;
                 MF_CUDA(ctx, cudaMemcpyAsync(&se, se_tot.p, 8, cudaMemcpyDeviceToHost, st));
