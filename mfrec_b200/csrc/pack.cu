@@ -291,9 +291,12 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     if (W > 16) W = 16;  // the SGD kernel is built for at most 16 warps per CTA
     int B = (opts && opts->row_blocks > 0) ? opts->row_blocks : 0;
     if (B == 0) {
-        // keep ~16+ ratings per bucket, never more row blocks than SMs
+        // ~40 ratings per bucket, never more row blocks than SMs.  Measured on the Netflix shape
+        // (DESIGN.md section 5): a sub-epoch costs a fixed hand-over (ticket, tile load, write-back)
+        // plus the spread of its blocks' work, so with G slabs -- G times fewer ratings per
+        // sub-epoch -- fewer, larger sub-epochs win even though they leave SMs idle.
         double per_slab = (double)nnz / G;
-        B = (int)(sqrt(per_slab / 16.0) / W);
+        B = (int)(sqrt(per_slab / 40.0) / W);
         B = std::max(1, std::min(B, ctx->sm_count));
     }
     B = (int)std::max<int64_t>(1, std::min<int64_t>(B, std::min<int64_t>(nu, ni / G) / W));
@@ -379,7 +382,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         // grow B until the widest block fits
         const size_t need = mfrec_sgd_smem_bytes(widest, kpad_hint, W);
         if (need <= ctx->smem_optin || widest <= 1 || (opts && opts->row_blocks > 0)) break;
-        B *= 2;
+        B += std::max(1, B / 8);
     }
     tr.lap("host LPT partition");
     R->B = B;
