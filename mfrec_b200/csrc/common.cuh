@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,7 @@ struct mfrec_ctx {
         cudaEvent_t ready = nullptr;
     } staged;                               // mfrec_model_create converts from these instead of copying
     int refs = 1;                  // the creator + every live mfrec_ratings / mfrec_model
+    std::shared_ptr<void> pack_host;   // host scratch of mfrec_ratings_pack, reused across calls
     std::string err;
 };
 // Objects allocate from the context's stream-ordered pool and free into it, so they keep the

@@ -91,13 +91,18 @@ __global__ void bucket_hist_kernel(const uint64_t *__restrict__ keys, int64_t nn
 }
 
 __global__ void pad_counts_kernel(const int32_t *__restrict__ cnt, int64_t nb,
-                                  int64_t *__restrict__ raw, int64_t *__restrict__ padded)
+                                  int64_t *__restrict__ raw, int64_t *__restrict__ padded,
+                                  int32_t *__restrict__ widest)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t c = 0;
     if (b < nb) {
-        raw[b] = cnt[b];
-        padded[b] = (cnt[b] + 3) & ~3;
+        c = cnt[b];
+        raw[b] = c;
+        padded[b] = (c + 3) & ~3;
     }
+    for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(widest, c);
 }
 
 template <typename RT>
@@ -227,6 +232,34 @@ __global__ void degree_key_kernel(const int32_t *__restrict__ deg, int32_t n, ui
     ids[i] = i;
 }
 
+struct PackHost {
+    std::vector<int32_t> deg_u, deg_i, ug, up, ig, ip, sorted_u, sorted_i;
+    mfrec_part::Workspace ws_u, ws_i;
+    // pinned staging for the partition tables: the device PULLS them with a kernel instead of a
+    // host -> device copy, which would queue on the copy engine behind the caller's rating values
+    // (hundreds of MB in flight on the copy stream) and stall the sort for up to their duration
+    int32_t *pinned = nullptr;
+    size_t pinned_cap = 0;
+    ~PackHost() { if (pinned) cudaFreeHost(pinned); }
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= pinned_cap) return cudaSuccess;
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        pinned_cap = 0;
+        cudaError_t e = cudaHostAlloc((void **)&pinned, n * 4, cudaHostAllocDefault);
+        if (e == cudaSuccess) pinned_cap = n;
+        return e;
+    }
+};
+
+// copies n 32-bit words from pinned (mapped) host memory: SM loads over PCIe, no copy engine
+__global__ void pull_host_kernel(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[j] = src[j];
+}
+
 // ids sorted heaviest first -> host vector.  deg_dev may be overridden by deg_host (multi-GPU:
 // global item degrees), in which case it is uploaded first.
 int sorted_by_degree(mfrec_ctx *ctx, const int32_t *deg_dev, int32_t n, uint64_t seed,
@@ -335,7 +368,13 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         degree_kernel<<<grid, 256, 0, st>>>(d_idx, nnz, ni, nu, deg_u.p, deg_i.p, bad.p);
         MF_LAUNCH_CHECK(ctx);
     }
-    std::vector<int32_t> h_deg_u(nu), h_deg_i(ni);
+    // host scratch lives in the context: fresh multi-MB vectors would be page-faulted in on every
+    // call, which costs more than the partition that fills them
+    if (!ctx->pack_host) ctx->pack_host = std::make_shared<PackHost>();
+    PackHost &H = *static_cast<PackHost *>(ctx->pack_host.get());
+    std::vector<int32_t> &h_deg_u = H.deg_u, &h_deg_i = H.deg_i;
+    h_deg_u.resize(nu);
+    h_deg_i.resize(ni);
     int32_t h_bad = 0;
     MF_CUDA(ctx, cudaMemcpyAsync(h_deg_u.data(), deg_u.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, st));
     MF_CUDA(ctx, cudaMemcpyAsync(h_deg_i.data(), deg_i.p, (size_t)ni * 4, cudaMemcpyDeviceToHost, st));
@@ -365,15 +404,19 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     R->nu = nu;
     R->G = G;
     R->W = W;
-    std::vector<int32_t> ug, up, ig, ip, sorted_u, sorted_i;
+    std::vector<int32_t> &ug = H.ug, &up = H.up, &ig = H.ig, &ip = H.ip, &sorted_u = H.sorted_u, &sorted_i = H.sorted_i;
     if (item_degree)   // the device copy drives the sort: replace it by the global degrees
         MF_CUDA(ctx, cudaMemcpyAsync(deg_i.p, h_deg_i.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
     MF_TRY(sorted_by_degree(ctx, deg_u.p, nu, seed, sorted_u));
     MF_TRY(sorted_by_degree(ctx, deg_i.p, ni, seed ^ 0x5bd1e995u, sorted_i));
     tr.lap("degree sort");
     for (;;) {
-        mfrec_part::partition_ids(h_deg_u, sorted_u, B, W, 1, ug, up, R->h_row_start);
-        mfrec_part::partition_ids(h_deg_i, sorted_i, G * B, W, G, ig, ip, R->h_col_start);
+        // items on a second host thread while this one does the users (4 threads for their blocks)
+        std::thread items([&] {
+            mfrec_part::partition_ids(h_deg_i, sorted_i, G * B, W, G, ig, ip, R->h_col_start, H.ws_i, 1);
+        });
+        mfrec_part::partition_ids(h_deg_u, sorted_u, B, W, 1, ug, up, R->h_row_start, H.ws_u, 4);
+        items.join();
         int32_t widest = 0;
         for (int cb = 0; cb < G * B; ++cb)
             widest = std::max(widest, R->h_col_start[(cb + 1) * W] - R->h_col_start[cb * W]);
@@ -403,12 +446,23 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->user_perm, ((size_t)nu + 1) * 4, st));
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->item_perm, ((size_t)ni + 1) * 4, st));
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->col_start, R->h_col_start.size() * 4, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_ug.p, ug.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_ig.p, ig.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(R->user_perm, up.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(R->item_perm, ip.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(R->col_start, R->h_col_start.data(), R->h_col_start.size() * 4,
-                                 cudaMemcpyHostToDevice, st));
+    {
+        const size_t ncs = R->h_col_start.size();
+        // the previous call's pull kernels have finished: every pack ends with a stream sync
+        MF_CUDA(ctx, H.reserve(2 * (size_t)nu + 2 * (size_t)ni + ncs));
+        struct Seg { const int32_t *src; int32_t *dst; size_t n; } segs[5] = {
+            {ug.data(), d_ug.p, (size_t)nu}, {up.data(), R->user_perm, (size_t)nu},
+            {ig.data(), d_ig.p, (size_t)ni}, {ip.data(), R->item_perm, (size_t)ni},
+            {R->h_col_start.data(), R->col_start, ncs}};
+        size_t at = 0;
+        for (const Seg &sg : segs) {
+            memcpy(H.pinned + at, sg.src, sg.n * 4);
+            pull_host_kernel<<<std::max<int>(1, std::min<int>(grid, (int)((sg.n + 255) / 256))), 256, 0, st>>>(
+                H.pinned + at, sg.dst, (int64_t)sg.n);
+            MF_LAUNCH_CHECK(ctx);
+            at += sg.n;
+        }
+    }
 
     // ---- 3./4. keys + stable radix sort ------------------------------------------------
     DevBuf<uint64_t> keys_a, keys_b;
@@ -435,6 +489,12 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
 
     tr.lap("keys + radix sort");
     // ---- 5. bucket histogram -> offsets ---------------------------------------------------
+    // device-side statistics, read back once at the end: [0..3] quads by type (64-bit), then
+    // the bit pattern of the largest |rating| and the widest bucket (32-bit each)
+    DevBuf<unsigned long long> d_stats;
+    MF_CUDA(ctx, d_stats.alloc(5, ctx->stream));
+    MF_CUDA(ctx, cudaMemsetAsync(d_stats.p, 0, 40, st));
+    int32_t *d_stats32 = reinterpret_cast<int32_t *>(d_stats.p + 4);
     const int64_t nb = R->n_buckets;
     DevBuf<int64_t> raw_cnt, pad_cnt, raw_off;
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->bucket_cnt, (size_t)nb * 4, st));
@@ -449,7 +509,8 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         bucket_hist_kernel<<<grid, 256, 0, st>>>(dkeys.Current(), nnz, kl.bits_u + kl.bits_i, R->bucket_cnt);
         MF_LAUNCH_CHECK(ctx);
     }
-    pad_counts_kernel<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(R->bucket_cnt, nb, raw_cnt.p, pad_cnt.p);
+    pad_counts_kernel<<<(unsigned)ceil_div64(nb, 256), 256, 0, st>>>(R->bucket_cnt, nb, raw_cnt.p, pad_cnt.p,
+                                                                      d_stats32 + 1);
     MF_LAUNCH_CHECK(ctx);
     {
         size_t tmp_bytes = 0;
@@ -493,38 +554,21 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         MF_LAUNCH_CHECK(ctx);
     }
     if (packed_len > 0) {
-        DevBuf<unsigned long long> d_tc;
-        MF_CUDA(ctx, d_tc.alloc(4, ctx->stream));
-        MF_CUDA(ctx, cudaMemsetAsync(d_tc.p, 0, 32, st));
-        quad_type_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len / 4, d_tc.p);
+        quad_type_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len / 4, d_stats.p);
         MF_LAUNCH_CHECK(ctx);
-        unsigned long long h_tc[4];
-        MF_CUDA(ctx, cudaMemcpyAsync(h_tc, d_tc.p, 32, cudaMemcpyDeviceToHost, st));
-        MF_CUDA(ctx, cudaStreamSynchronize(st));
-        for (int t = 0; t < 4; ++t) R->quad_types[t] = (int64_t)h_tc[t];
+        // largest |rating| (sizes the fixed-point reduction scale of the SGD kernel)
+        max_abs_rating_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len, d_stats32);
+        MF_LAUNCH_CHECK(ctx);
     }
-    // largest |rating| (sizes the fixed-point reduction scale of the SGD kernel)
     {
-        DevBuf<int32_t> d_mx;
-        MF_CUDA(ctx, d_mx.alloc(1, ctx->stream));
-        MF_CUDA(ctx, cudaMemsetAsync(d_mx.p, 0, 4, st));
-        if (packed_len > 0) {
-            max_abs_rating_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len, d_mx.p);
-            MF_LAUNCH_CHECK(ctx);
-        }
-        int32_t bits = 0;
-        MF_CUDA(ctx, cudaMemcpyAsync(&bits, d_mx.p, 4, cudaMemcpyDeviceToHost, st));
+        unsigned long long h_stats[5];
+        MF_CUDA(ctx, cudaMemcpyAsync(h_stats, d_stats.p, 40, cudaMemcpyDeviceToHost, st));
         MF_CUDA(ctx, cudaStreamSynchronize(st));
-        memcpy(&R->max_abs_rating, &bits, 4);
-    }
-    // widest bucket (diagnostic; bounds the longest serial chain of one phase)
-    {
-        std::vector<int32_t> h_cnt((size_t)nb);
-        MF_CUDA(ctx, cudaMemcpyAsync(h_cnt.data(), R->bucket_cnt, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        MF_CUDA(ctx, cudaStreamSynchronize(st));
-        int32_t mx = 0;
-        for (int32_t c : h_cnt) mx = std::max(mx, c);
-        R->max_bucket = mx;
+        for (int t = 0; t < 4; ++t) R->quad_types[t] = (int64_t)h_stats[t];
+        int32_t tail[2];
+        memcpy(tail, &h_stats[4], 8);
+        memcpy(&R->max_abs_rating, &tail[0], 4);
+        R->max_bucket = tail[1];   // widest bucket (diagnostic; bounds the longest serial chain of one phase)
     }
     tr.lap("gather + stats");
     guard.r = nullptr;

@@ -9,6 +9,7 @@
 #include <functional>
 #include <numeric>
 #include <queue>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -69,19 +70,30 @@ inline void balanced_bins(const int32_t *deg_sorted, int64_t n, int bins, int32_
     }
 }
 
+// Scratch of partition_ids.  Kept by the caller across calls: the vectors are several MB at
+// Netflix size and a fresh allocation of that size is page-faulted in on every call, which costs
+// more than the partition itself.
+struct Workspace {
+    std::vector<int32_t> deg_sorted, block_r, members, mdeg, sub, count, cursor;
+    std::vector<int64_t> bstart, cur;
+};
+
 // Hierarchical partition: ids -> nblocks blocks -> W groups each, balanced by (degree + 1).
 // `sorted` lists all ids heaviest first (ties in a seeded pseudo-random order; computed on the
 // device).  Outputs, for every id, its group (block * W + group-in-block) and its packed id
 // (groups are contiguous id ranges, ascending original id inside a group); start[g] = first
-// packed id of group g.
+// packed id of group g.  `threads` > 1 splits the per-block second level over that many host
+// threads (the result does not depend on it).
 inline void partition_ids(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted, int nblocks,
                           int W, int n_slabs, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
-                          std::vector<int32_t> &start)
+                          std::vector<int32_t> &start, Workspace &ws, int threads = 1)
 {
     const int64_t n = (int64_t)deg.size();
-    std::vector<int32_t> deg_sorted(n), block_r(n);
+    ws.deg_sorted.resize(n);
+    ws.block_r.resize(n);
+    int32_t *deg_sorted = ws.deg_sorted.data(), *block_r = ws.block_r.data();
     for (int64_t j = 0; j < n; ++j) deg_sorted[j] = deg[sorted[j]];   // the one gather by id
-    balanced_bins(deg_sorted.data(), n, nblocks, block_r.data());
+    balanced_bins(deg_sorted, n, nblocks, block_r);
     if (n_slabs > 1) {
         // The heaviest ids land in the lowest-numbered bins.  A heavy item is a long dependent
         // chain for the SGD kernel, so deal the bins round-robin over the slabs (bin j -> slab
@@ -91,33 +103,61 @@ inline void partition_ids(const std::vector<int32_t> &deg, const std::vector<int
         for (int64_t j = 0; j < n; ++j) block_r[j] = (block_r[j] % n_slabs) * per + block_r[j] / n_slabs;
     }
     // ranks of each block, still heaviest first (counting sort by block)
-    std::vector<int64_t> bstart(nblocks + 1, 0);
+    ws.bstart.assign(nblocks + 1, 0);
+    int64_t *bstart = ws.bstart.data();
     for (int64_t j = 0; j < n; ++j) bstart[block_r[j] + 1] += 1;
     for (int b = 0; b < nblocks; ++b) bstart[b + 1] += bstart[b];
-    std::vector<int32_t> members(n), mdeg(n), sub(n);
+    ws.members.resize(n);
+    ws.mdeg.resize(n);
+    ws.sub.resize(n);
+    int32_t *members = ws.members.data(), *mdeg = ws.mdeg.data(), *sub = ws.sub.data();
     {
-        std::vector<int64_t> cur(bstart.begin(), bstart.end() - 1);
+        ws.cur.assign(ws.bstart.begin(), ws.bstart.end() - 1);
+        int64_t *cur = ws.cur.data();
         for (int64_t j = 0; j < n; ++j) {
             const int64_t at = cur[block_r[j]]++;
             members[at] = (int32_t)j;
             mdeg[at] = deg_sorted[j];
         }
     }
-    group_of.assign(n, 0);
-    for (int b = 0; b < nblocks; ++b) {
-        const int64_t a = bstart[b], m = bstart[b + 1] - a;
-        balanced_bins(mdeg.data() + a, m, W, sub.data() + a);
-        for (int64_t t = a; t < a + m; ++t) group_of[sorted[members[t]]] = b * W + sub[t];   // the one scatter by id
+    group_of.resize(n);
+    int32_t *gof = group_of.data();
+    const int32_t *srt = sorted.data();
+    auto second_level = [&](int b0, int b1) {
+        for (int b = b0; b < b1; ++b) {
+            const int64_t a = bstart[b], m = bstart[b + 1] - a;
+            balanced_bins(mdeg + a, m, W, sub + a);
+            for (int64_t t = a; t < a + m; ++t) gof[srt[members[t]]] = b * W + sub[t];   // the one scatter by id
+        }
+    };
+    threads = std::max(1, std::min(threads, nblocks));
+    if (threads == 1 || n < 65536) {
+        second_level(0, nblocks);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t)
+            pool.emplace_back(second_level, (int)((int64_t)nblocks * t / threads),
+                              (int)((int64_t)nblocks * (t + 1) / threads));
+        second_level(0, nblocks / threads);
+        for (auto &th : pool) th.join();
     }
     const int ng = nblocks * W;
-    std::vector<int32_t> count(ng + 1, 0);
-    for (int64_t id = 0; id < n; ++id) count[group_of[id] + 1] += 1;
+    ws.count.assign(ng + 1, 0);
+    for (int64_t id = 0; id < n; ++id) ws.count[gof[id] + 1] += 1;
     start.assign(ng + 1, 0);
-    for (int g = 0; g < ng; ++g) start[g + 1] = start[g] + count[g + 1];
-    std::vector<int32_t> cursor(start.begin(), start.end() - 1);
-    perm.assign(n, 0);
-    for (int64_t id = 0; id < n; ++id) perm[id] = cursor[group_of[id]]++;
+    for (int g = 0; g < ng; ++g) start[g + 1] = start[g] + ws.count[g + 1];
+    ws.cursor.assign(start.begin(), start.end() - 1);
+    int32_t *cursor = ws.cursor.data();
+    perm.resize(n);
+    for (int64_t id = 0; id < n; ++id) perm[id] = cursor[gof[id]]++;
 }
 
+inline void partition_ids(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted, int nblocks,
+                          int W, int n_slabs, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
+                          std::vector<int32_t> &start)
+{
+    Workspace ws;
+    partition_ids(deg, sorted, nblocks, W, n_slabs, group_of, perm, start, ws, 1);
+}
 
 }  // namespace mfrec_part

@@ -3,11 +3,12 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <random>
 
 #include "partition.h"
 
-int main()
+int main(int argc, char **argv)
 {
     const int nu = 480000, ni = 17700, B = 148, W = 8;
     std::mt19937_64 rng(1);
@@ -22,12 +23,14 @@ int main()
         return ids;
     };
     const auto su = sorted(du), si = sorted(di);
-    std::vector<int32_t> g, p, st;
-    for (int rep = 0; rep < 3; ++rep) {
+    std::vector<int32_t> g, p, st, g2, p2, st2;
+    mfrec_part::Workspace wu, wi;
+    const int threads = argc > 1 ? atoi(argv[1]) : 4;
+    for (int rep = 0; rep < 5; ++rep) {
         auto t0 = std::chrono::steady_clock::now();
-        mfrec_part::partition_ids(du, su, B, W, 1, g, p, st);
+        mfrec_part::partition_ids(du, su, B, W, 1, g, p, st, wu, threads);
         auto t1 = std::chrono::steady_clock::now();
-        mfrec_part::partition_ids(di, si, B, W, 1, g, p, st);
+        mfrec_part::partition_ids(di, si, B, W, 1, g2, p2, st2, wi, 1);
         auto t2 = std::chrono::steady_clock::now();
         std::printf("users %.2f ms, items %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
                     std::chrono::duration<double, std::milli>(t2 - t1).count());
