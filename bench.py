@@ -55,12 +55,20 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.
+
+    nvidia-smi needs a few hundred ms to produce its first row, so the sampler is started BEFORE the
+    warm-up steps (`with ClockSampler(i) as c:` around warm-up + timed region) and the timed region
+    is marked with c.begin() / c.end(); summary() uses the rows that fall inside the marks.  When
+    the timed region is shorter than the sampling period (multi-GPU runs: a few epochs of ~50 ms)
+    it falls back to the rows of the second before c.end() -- warm-up steps of the same kernel on
+    the same data, i.e. the same load -- and says so in "window"."""
 
     def __init__(self, device_index):
         self.device_index = device_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
@@ -69,7 +77,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,18 +87,33 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def __exit__(self, *a):
+        if self.t1 is None:
+            self.t1 = time.monotonic()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.1)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
+        t0 = self.t0 if self.t0 is not None else -1.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for (t, r) in self.rows if t1 - 1.0 <= t <= t1 + 0.05]
+            window = "last second before the end of the timed region (warm-up steps of the same load; the timed region is shorter than the sampling period)"
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -100,7 +123,7 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # --------------------------------------------------------------------------------------------
@@ -209,15 +232,16 @@ def run_native(args):
     se = torch.zeros(args.steps + args.warmup, device=dev, dtype=torch.float64)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     launches0 = ctx.launch_count
-    for e in range(args.warmup):
-        M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
-                    sq_err_ptr=se.data_ptr() + 8 * e)
-    ctx.sync()
-    launches_warm = ctx.launch_count - launches0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        for e in range(args.warmup):
+            M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
+                        sq_err_ptr=se.data_ptr() + 8 * e)
+        ctx.sync()
+        launches_warm = ctx.launch_count - launches0
         torch.cuda.synchronize()
         launches1 = ctx.launch_count
+        clocks.begin()
         ev0.record(stream)
         for e in range(args.steps):
             M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
@@ -225,6 +249,7 @@ def run_native(args):
         ev1.record(stream)
         ctx.sync()
         torch.cuda.synchronize()
+        clocks.end()
         launches_timed = ctx.launch_count - launches1
     ms = ev0.elapsed_time(ev1)
     ms_per_step = ms / args.steps
@@ -326,11 +351,12 @@ def run_topn(args):
         return _native.topn_sweep("predict_rating", u_h.numpy(), v_h.numpy(), None, ni, None, None, N,
                                   ctx=ctx, out=out)[3]
 
-    for _ in range(args.warmup):
-        call()
-    torch.cuda.synchronize()
     sweep_ms, finish_ms = [], []
     with ClockSampler(local) as clocks:
+        for _ in range(args.warmup):
+            call()
+        torch.cuda.synchronize()
+        clocks.begin()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             st = call()
@@ -338,6 +364,7 @@ def run_topn(args):
             finish_ms.append(st[7])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        clocks.end()
     flops = 2.0 * nu * ni * k
     sm = float(np.mean(sweep_ms))
     peaks = {}

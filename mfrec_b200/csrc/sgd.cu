@@ -178,6 +178,15 @@ __device__ __forceinline__ void row_cp_async(float *dst_row, const float *src_ro
         cp_async<V * 4>(dst_row + (c * 32 + lane) * V, src_row + (c * 32 + lane) * V);
 }
 
+// base + idx * stride as ONE 64-bit multiply-add (the compiler otherwise splits the masked id into
+// shifts and masks: 5-6 instructions per row address instead of 1)
+__device__ __forceinline__ float *row_ptr(float *base, uint32_t idx, uint32_t stride_bytes)
+{
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"(stride_bytes), "l"(base));
+    return reinterpret_cast<float *>(a);
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
@@ -329,10 +338,21 @@ sgd_block_kernel(const SgdParams prm)
         const uint32_t nchunks = (slen + kChunk - 1) / kChunk;
         const uint32_t nquads = slen / 4;
         const PackedRating *stream = prm.packed + S0;
-        const int32_t *cnt_w = bcnt + warp * W;
         const int64_t *off_w = boff + warp * W;
-        uint32_t issued = 0;
 
+        // Everything below counts in QUADS (4 stream positions = 48 bytes) from the start of this
+        // warp's stream: quad x sits in ring slot (base_q + x) mod kRingQ, its P rows in P-ring slots
+        // 4 (x mod kQuadsAhead) .., chunk c = quads [16 c, 16 c + 16).
+        constexpr uint32_t kRingQ = kRing / 4, kChunkQ = kChunk / 4;
+        static_assert((kRingQ & (kRingQ - 1)) == 0 && (kChunkQ & (kChunkQ - 1)) == 0 &&
+                      (kQuadsAhead & (kQuadsAhead - 1)) == 0, "ring sizes must be powers of two");
+        const uint32_t base_q = (chunk_seq % kStages) * kChunkQ;
+        const char *const ring_b = reinterpret_cast<const char *>(ring);
+        auto quad_rec = [&](uint32_t x) { return ring_b + ((base_q + x) & (kRingQ - 1)) * 48u; };
+        auto chunk_wait = [&](uint32_t c) {
+            const uint32_t g = chunk_seq + c;
+            mbar_wait(my_bar + (g % kStages), (g / kStages) & 1u);
+        };
         auto issue_chunk = [&](uint32_t c) {
             if (lane == 0) {
                 const uint32_t cnt = min((uint32_t)kChunk, slen - c * kChunk);
@@ -342,44 +362,36 @@ sgd_block_kernel(const SgdParams prm)
                 bulk_g2s(ring + (g % kStages) * kChunk, stream + (size_t)c * kChunk, cnt * 12u, bar);
             }
         };
-        while (issued < nchunks && issued < (uint32_t)kStages) issue_chunk(issued++);
+        for (uint32_t c = 0; c < nchunks && c < (uint32_t)kStages; ++c) issue_chunk(c);
 
-        // Prefetch cursor: walks the stream one QUAD (4 positions = 48 bytes, 16-byte aligned) at a
-        // time, padding entries included (they name packed user 0, a valid row, and are never
-        // consumed).  One cp.async group per quad, so group index == quad index.  The first
+        // Prefetch: one cp.async group per quad, so group index == quad index.  The first
         // kQuadsAhead - 1 quads are fetched here; after that the rows of quad x + kQuadsAhead - 1
         // are requested WHILE quad x is being applied, one row after each warp reduction, so the
-        // address arithmetic and the copies fill the reduction's latency instead of preceding the
-        // dependent chain.  Quads past the end commit empty groups.
-        uint32_t pfq = 0;
-        auto prefetch_quads_to = [&](uint32_t target) {
-#pragma unroll 1
-            while (pfq < target) {
-                if (pfq < nquads) {
-                    const uint32_t pos = pfq * 4;
-                    const uint32_t g = chunk_seq + pos / kChunk;
-                    if ((pos % kChunk) == 0)   // first touch of a chunk: wait for its bulk copy
-                        mbar_wait(my_bar + (g % kStages), (g / kStages) & 1u);
-                    const PackedRating *src = ring + (g % kStages) * kChunk + (pos % kChunk);
-                    const int4 *qsrc = reinterpret_cast<const int4 *>(src);
-                    const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
-                    const int us[4] = {a.x & kIdMask, a.w & kIdMask, b.z & kIdMask, c2.y & kIdMask};
-                    const uint32_t slot0 = pos % kDepth;
+        // copies fill the reduction's latency instead of preceding the dependent chain.  Padding
+        // entries name packed user 0, a valid row, and are never consumed.  Quads past the end
+        // commit empty groups.
+        float *const prow_lane = prow + lane * Frag<E>::V;
+        for (uint32_t fx = 0; fx + 1 < (uint32_t)kQuadsAhead; ++fx) {
+            if (fx < nquads) {
+                if ((fx & (kChunkQ - 1)) == 0) chunk_wait(fx / kChunkQ);
+                const char *rec = quad_rec(fx);
+                const uint32_t fslot0 = (fx & (kQuadsAhead - 1)) * 4;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        float *dst = prow + (slot0 + t) * KPAD + lane * Frag<E>::V;
-                        const float *gsrc = P_lane + (size_t)us[t] * KPAD;
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t ut = *reinterpret_cast<const uint32_t *>(rec + 12 * t) & kIdMask;
+                    const float *gsrc = row_ptr(P_lane, ut, KPAD * 4);
 #pragma unroll
-                        for (int c = 0; c < Frag<E>::NV; ++c)
-                            cp_async<Frag<E>::V * 4>(dst + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
-                    }
-                    if (lane < 4) cp_async<4>(pbias + slot0 + lane, prm.ub + (src[lane].u & kIdMask));
+                    for (int c = 0; c < Frag<E>::NV; ++c)
+                        cp_async<Frag<E>::V * 4>(prow_lane + (fslot0 + t) * KPAD + c * 32 * Frag<E>::V,
+                                                 gsrc + c * 32 * Frag<E>::V);
                 }
-                cp_async_commit();
-                ++pfq;
+                if (lane < 4) {
+                    const uint32_t ul = *reinterpret_cast<const uint32_t *>(rec + 12 * lane) & kIdMask;
+                    cp_async<4>(pbias + fslot0 + lane, row_ptr(prm.ub, ul, 4));
+                }
             }
-        };
-        prefetch_quads_to(kQuadsAhead - 1);
+            cp_async_commit();
+        }
 
         if (nq > 0) mbar_wait(tile_bar, step & 1);
         // item biases of the block: L2 loads (another SM wrote them; L1 may hold a stale line)
@@ -433,8 +445,8 @@ sgd_block_kernel(const SgdParams prm)
         };
         auto store_p = [&](int u, const Frag<E> &pu, float bu) {
             if constexpr (TIMING) { if (prm.exp & 1) return; }
-            frag_store<E>(pu, prm.P + (size_t)u * KPAD, lane);
-            if (lane == 0) prm.ub[u] = bu;
+            frag_store<E>(pu, row_ptr(prm.P, (uint32_t)u, KPAD * 4), lane);
+            if (lane == 0) *row_ptr(prm.ub, (uint32_t)u, 4) = bu;
         };
         auto store_q = [&](int it, const Frag<E> &q, float bi) {
             if constexpr (TIMING) { if (prm.exp & 2) return; }
@@ -446,8 +458,7 @@ sgd_block_kernel(const SgdParams prm)
         // stale = the packer saw this user among the 32 preceding ratings of the stream, so the
         // prefetched copy of the row may predate an update: take it from registers (adjacent
         // ratings of one user) or re-read it from global memory.
-        auto update_one = [&](uint32_t pos, int u, int it, float r, bool stale) {
-            const uint32_t slot = pos % kDepth;
+        auto update_one = [&](uint32_t slot, int u, int it, float r, bool stale) {
             Frag<E> pu;
             float bu;
             if (u == prev_u) {
@@ -456,8 +467,8 @@ sgd_block_kernel(const SgdParams prm)
                 bu = cbu;
             } else if (stale) {
                 __syncwarp();   // lane 0's bias store of an earlier rating is visible to every lane
-                frag_load<E>(pu, prm.P + (size_t)u * KPAD, lane);
-                bu = prm.ub[u];
+                frag_load<E>(pu, row_ptr(prm.P, (uint32_t)u, KPAD * 4), lane);
+                bu = *row_ptr(prm.ub, (uint32_t)u, 4);
             } else {
                 frag_load<E>(pu, prow + slot * KPAD, lane);
                 bu = pbias[slot];
@@ -479,8 +490,7 @@ sgd_block_kernel(const SgdParams prm)
 
         // straight-line paths for the quads the packer classified (common.cuh): four fresh,
         // pairwise distinct users, so all four P rows come from the prefetch ring up front
-        auto load_quad_p = [&](uint32_t pos, Frag<E> (&p4)[4], float (&b4)[4]) {
-            const uint32_t slot0 = pos % kDepth;   // pos is quad aligned, kDepth a multiple of 4
+        auto load_quad_p = [&](uint32_t slot0, Frag<E> (&p4)[4], float (&b4)[4]) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 frag_load<E>(p4[t], prow + (slot0 + t) * KPAD, lane);
@@ -488,10 +498,10 @@ sgd_block_kernel(const SgdParams prm)
             }
         };
         // kQuadChain: one item; its row stays in registers and is stored once
-        auto chain_quad = [&](uint32_t pos, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
+        auto chain_quad = [&](uint32_t slot0, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
-            load_quad_p(pos, p4, b4);
+            load_quad_p(slot0, p4, b4);
             if (it != prev_i) {
                 frag_load<E>(cq, Qs + (size_t)(it - cs) * KPAD, lane);
                 cbi = ibs[it - cs];
@@ -513,10 +523,10 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadIndep: four ratings that share neither a user nor an item: their order does not
         // matter, so all loads, the four reductions and the four updates are issued side by side
         // (four independent dependency chains for the scheduler instead of one)
-        auto indep_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
+        auto indep_quad = [&](uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4], q4[4];
             float b4[4], c4[4];
-            load_quad_p(pos, p4, b4);
+            load_quad_p(slot0, p4, b4);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 frag_load<E>(q4[t], Qs + (size_t)(i4[t] - cs) * KPAD, lane);
@@ -546,11 +556,11 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadClean: any items; an item row equal to the previous rating's stays in registers
         // (predicated loads, no branch), every updated row goes back to the shared-memory tile
         // (a later rating of the quad may reuse an item: program order through the tile is exact)
-        auto clean_quad = [&](uint32_t pos, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
+        auto clean_quad = [&](uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
                               const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
-            load_quad_p(pos, p4, b4);
+            load_quad_p(slot0, p4, b4);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 if (f4[t] & kFlagAdjUser) {   // same user as the previous rating: its registers, not the ring
@@ -577,9 +587,9 @@ sgd_block_kernel(const SgdParams prm)
         };
 
         const int32_t done_base = step * W;
+        uint32_t x = 0;   // quad cursor over the whole stream, runs across the phases
         for (int p = 0; p < W; ++p) {
-            const uint32_t n = (uint32_t)cnt_w[p];
-            const uint32_t rel0 = (uint32_t)(off_w[p] - S0);
+            const uint32_t xe = (uint32_t)(off_w[p + 1] - S0) >> 2;   // buckets are padded to quads
             if (p > 0) {
                 // column group (warp + p) mod W comes from warp + 1, which used it in phase p - 1
                 const volatile int32_t *flag = phase_done + (warp + 1 == W ? 0 : warp + 1);
@@ -592,70 +602,72 @@ sgd_block_kernel(const SgdParams prm)
             }
             se_f = 0.f;
 #pragma unroll 1
-            for (uint32_t i = 0; i < n; i += 4) {
-                const uint32_t rel = rel0 + i;   // quad aligned
-                const uint32_t c_here = rel / kChunk;
-                if (c_here + kStages > issued && issued < nchunks) {
-                    // every chunk before c_here has been consumed: its stage is free again
-                    __syncwarp();
-                    while (issued < nchunks && issued < c_here + kStages) issue_chunk(issued++);
+            for (; x < xe; ++x) {
+                if ((x & (kChunkQ - 1)) == 0 && x != 0) {
+                    // entering chunk x / 16: the one before it is consumed, its ring stage is free
+                    const uint32_t nc = x / kChunkQ - 1 + kStages;
+                    if (nc < nchunks) {
+                        __syncwarp();
+                        issue_chunk(nc);
+                    }
                 }
                 // the quad whose rows are requested during this iteration
-                const uint32_t fq = rel / 4 + (kQuadsAhead - 1);
-                const bool fvalid = fq < nquads;
-                int fu[4] = {0, 0, 0, 0};
-                const PackedRating *fsrc = ring;
+                const uint32_t fx = x + (kQuadsAhead - 1);
+                const bool fvalid = fx < nquads;
+                uint32_t fu[4] = {0, 0, 0, 0};
+                const char *frec = ring_b;
                 if (fvalid) {
-                    const uint32_t fpos = fq * 4;
-                    const uint32_t fg = chunk_seq + fpos / kChunk;
-                    if ((fpos % kChunk) == 0)   // first touch of a chunk: wait for its bulk copy
-                        mbar_wait(my_bar + (fg % kStages), (fg / kStages) & 1u);
-                    fsrc = ring + (fg % kStages) * kChunk + (fpos % kChunk);
-                    const int4 *fq4 = reinterpret_cast<const int4 *>(fsrc);
-                    const int4 fa = fq4[0], fb = fq4[1], fc = fq4[2];
-                    fu[0] = fa.x & kIdMask; fu[1] = fa.w & kIdMask; fu[2] = fb.z & kIdMask; fu[3] = fc.y & kIdMask;
+                    if ((fx & (kChunkQ - 1)) == 0) chunk_wait(fx / kChunkQ);   // first touch of a chunk
+                    frec = quad_rec(fx);
+                    fu[0] = *reinterpret_cast<const uint32_t *>(frec) & kIdMask;
+                    fu[1] = *reinterpret_cast<const uint32_t *>(frec + 12) & kIdMask;
+                    fu[2] = *reinterpret_cast<const uint32_t *>(frec + 24) & kIdMask;
+                    fu[3] = *reinterpret_cast<const uint32_t *>(frec + 36) & kIdMask;
                 }
-                const uint32_t fslot0 = (fq * 4) % kDepth;
+                const uint32_t fslot0 = (fx & (kQuadsAhead - 1)) * 4;
+                float *const fdst = prow_lane + fslot0 * KPAD;
                 auto fetch_row = [&](int t) {
                     if constexpr (TIMING) { if (prm.exp & 8) return; }
                     if (fvalid) {
-                        float *dst = prow + (fslot0 + t) * KPAD + lane * Frag<E>::V;
-                        const float *gsrc = P_lane + (size_t)fu[t] * KPAD;
+                        const float *gsrc = row_ptr(P_lane, fu[t], KPAD * 4);
 #pragma unroll
                         for (int c = 0; c < Frag<E>::NV; ++c)
-                            cp_async<Frag<E>::V * 4>(dst + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
+                            cp_async<Frag<E>::V * 4>(fdst + t * KPAD + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
                     }
                 };
                 lap(0);
                 cp_async_wait<kQuadsAhead - 2>();   // the four rows of this quad have landed
                 __syncwarp();                       // ... and the bias copies / lane 0's stores are visible
                 lap(1);
-                const uint32_t g = chunk_seq + c_here;
-                const int4 *qsrc = reinterpret_cast<const int4 *>(ring + (g % kStages) * kChunk + (rel % kChunk));
+                const int4 *qsrc = reinterpret_cast<const int4 *>(quad_rec(x));
                 const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
                 lap(2);
+                const uint32_t slot0 = (x & (kQuadsAhead - 1)) * 4;
                 const int u4[4] = {a.x & kIdMask, a.w & kIdMask, b.z & kIdMask, c2.y & kIdMask};
                 const int f4[4] = {a.y, b.x, b.w, c2.z};   // item ids with the packer's hint bits
                 const int i4[4] = {a.y & kIdMask, b.x & kIdMask, b.w & kIdMask, c2.z & kIdMask};
                 const float r4[4] = {__int_as_float(a.z), __int_as_float(b.y), __int_as_float(c2.x), __int_as_float(c2.w)};
                 const int qtype = (a.x >> kQuadShift) & 3;
                 if (qtype == kQuadIndep) {
-                    indep_quad(rel, u4, i4, r4, fetch_row);
+                    indep_quad(slot0, u4, i4, r4, fetch_row);
                 } else if (qtype == kQuadChain) {
                     bool skip = false;
                     if constexpr (TIMING) skip = (prm.exp & 32) != 0;   // experiment: chains cost nothing
                     if (skip) { fetch_row(0); fetch_row(1); fetch_row(2); fetch_row(3); }
-                    else chain_quad(rel, u4, i4[0], r4, fetch_row);
+                    else chain_quad(slot0, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
-                    clean_quad(rel, u4, i4, f4, r4, fetch_row);
+                    clean_quad(slot0, u4, i4, f4, r4, fetch_row);
                 } else {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        if (!(f4[t] & kFlagPad)) update_one(rel + t, u4[t], i4[t], r4[t], (f4[t] & kFlagStale) != 0);
+                        if (!(f4[t] & kFlagPad)) update_one(slot0 + t, u4[t], i4[t], r4[t], (f4[t] & kFlagStale) != 0);
                         fetch_row(t);
                     }
                 }
-                if (fvalid && lane < 4) cp_async<4>(pbias + fslot0 + lane, prm.ub + (fsrc[lane].u & kIdMask));
+                if (fvalid && lane < 4) {
+                    const uint32_t ul = *reinterpret_cast<const uint32_t *>(frec + 12 * lane) & kIdMask;
+                    cp_async<4>(pbias + fslot0 + lane, row_ptr(prm.ub, ul, 4));
+                }
                 cp_async_commit();
                 lap(3);
             }

@@ -190,16 +190,17 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
         return se
 
     launches0 = ctx.launch_count
-    for _ in range(args.warmup):
-        one_epoch()
-    ctx.sync()
-    torch.cuda.synchronize()
-    dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ses = []
-    del marks[:]
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:   # started before the warm-up: see its docstring
+        for _ in range(args.warmup):
+            one_epoch()
+        ctx.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        del marks[:]
         launches1 = ctx.launch_count
+        clocks.begin()
         ev0.record(be.stream)
         for _ in range(args.steps):
             ses.append(one_epoch())
@@ -207,6 +208,7 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
         ctx.sync()
         torch.cuda.synchronize()
         dist.barrier()
+        clocks.end()
     if tracing:
         import sys
         kern = exch = 0.0
