@@ -168,6 +168,22 @@ __device__ __forceinline__ void frag_store(const Frag<E> &f, float *row, int lan
     }
 }
 
+// the same with a pointer that already includes the lane's offset (row + lane * V)
+template <int E>
+__device__ __forceinline__ void frag_store_lane(const Frag<E> &f, float *p)
+{
+    constexpr int V = Frag<E>::V, NV = Frag<E>::NV;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        if constexpr (V == 4)
+            *reinterpret_cast<float4 *>(p + c * 128) = make_float4(f.x[c * 4], f.x[c * 4 + 1], f.x[c * 4 + 2], f.x[c * 4 + 3]);
+        else if constexpr (V == 2)
+            *reinterpret_cast<float2 *>(p) = make_float2(f.x[0], f.x[1]);
+        else
+            *p = f.x[0];
+    }
+}
+
 // asynchronous global -> shared copy of one row, same lane <-> column mapping as frag_load
 template <int E>
 __device__ __forceinline__ void row_cp_async(float *dst_row, const float *src_row, int lane)
@@ -443,10 +459,24 @@ sgd_block_kernel(const SgdParams prm)
                 q.x[e] = fmaf(gli, pe, a_i * qe);
             }
         };
+        auto store_p_row = [&](int u, const Frag<E> &pu) {
+            if constexpr (TIMING) { if (prm.exp & 1) return; }
+            frag_store_lane<E>(pu, row_ptr(P_lane, (uint32_t)u, KPAD * 4));
+        };
         auto store_p = [&](int u, const Frag<E> &pu, float bu) {
             if constexpr (TIMING) { if (prm.exp & 1) return; }
-            frag_store<E>(pu, row_ptr(prm.P, (uint32_t)u, KPAD * 4), lane);
+            store_p_row(u, pu);
             if (lane == 0) *row_ptr(prm.ub, (uint32_t)u, 4) = bu;
+        };
+        // the four user biases of a quad in one predicated store: lane t writes rating t's (its
+        // user id comes straight from the record).  keep bit t clear = rating t + 1 is the same
+        // user and writes the newer value.
+        auto store_bias_quad = [&](const int (&u4)[4], const float (&b4)[4], uint32_t keep) {
+            if constexpr (TIMING) { if (prm.exp & 1) return; }
+            const bool lo = (lane & 2) == 0, even = (lane & 1) == 0;
+            const int ul = lo ? (even ? u4[0] : u4[1]) : (even ? u4[2] : u4[3]);
+            const float v = lo ? (even ? b4[0] : b4[1]) : (even ? b4[2] : b4[3]);
+            if (lane < 4 && ((keep >> lane) & 1u)) *row_ptr(prm.ub, (uint32_t)ul, 4) = v;
         };
         auto store_q = [&](int it, const Frag<E> &q, float bi) {
             if constexpr (TIMING) { if (prm.exp & 2) return; }
@@ -498,7 +528,7 @@ sgd_block_kernel(const SgdParams prm)
             }
         };
         // kQuadChain: one item; its row stays in registers and is stored once
-        auto chain_quad = [&](uint32_t slot0, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
+        auto chain_quad = [&](const char *rec, uint32_t slot0, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
             load_quad_p(slot0, p4, b4);
@@ -511,8 +541,9 @@ sgd_block_kernel(const SgdParams prm)
                 const int isum = warp_sum_fx(dot_fx(p4[t], cq));
                 hook(t);
                 apply(isum, r4[t], p4[t], b4[t], cq, cbi);
-                store_p(u4[t], p4[t], b4[t]);
+                store_p_row(u4[t], p4[t]);
             }
+            store_bias_quad(u4, b4, 0xfu);
             store_q(it, cq, cbi);
 #pragma unroll
             for (int e = 0; e < E; ++e) cp.x[e] = p4[3].x[e];
@@ -523,7 +554,7 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadIndep: four ratings that share neither a user nor an item: their order does not
         // matter, so all loads, the four reductions and the four updates are issued side by side
         // (four independent dependency chains for the scheduler instead of one)
-        auto indep_quad = [&](uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
+        auto indep_quad = [&](const char *rec, uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4], q4[4];
             float b4[4], c4[4];
             load_quad_p(slot0, p4, b4);
@@ -544,8 +575,9 @@ sgd_block_kernel(const SgdParams prm)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 store_q(i4[t], q4[t], c4[t]);
-                store_p(u4[t], p4[t], b4[t]);
+                store_p_row(u4[t], p4[t]);
             }
+            store_bias_quad(u4, b4, 0xfu);
 #pragma unroll
             for (int e = 0; e < E; ++e) { cp.x[e] = p4[3].x[e]; cq.x[e] = q4[3].x[e]; }
             cbu = b4[3];
@@ -556,7 +588,7 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadClean: any items; an item row equal to the previous rating's stays in registers
         // (predicated loads, no branch), every updated row goes back to the shared-memory tile
         // (a later rating of the quad may reuse an item: program order through the tile is exact)
-        auto clean_quad = [&](uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
+        auto clean_quad = [&](const char *rec, uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
                               const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
@@ -577,7 +609,13 @@ sgd_block_kernel(const SgdParams prm)
                 hook(t);
                 apply(isum, r4[t], p4[t], b4[t], cq, cbi);
                 store_q(i4[t], cq, cbi);
-                store_p(u4[t], p4[t], b4[t]);
+                store_p_row(u4[t], p4[t]);
+            }
+            {
+                uint32_t keep = 0x8u;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) keep |= (f4[t + 1] & kFlagAdjUser) ? 0u : (1u << t);
+                store_bias_quad(u4, b4, keep);
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) cp.x[e] = p4[3].x[e];
@@ -639,7 +677,8 @@ sgd_block_kernel(const SgdParams prm)
                 cp_async_wait<kQuadsAhead - 2>();   // the four rows of this quad have landed
                 __syncwarp();                       // ... and the bias copies / lane 0's stores are visible
                 lap(1);
-                const int4 *qsrc = reinterpret_cast<const int4 *>(quad_rec(x));
+                const char *const qrec = quad_rec(x);
+                const int4 *qsrc = reinterpret_cast<const int4 *>(qrec);
                 const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
                 lap(2);
                 const uint32_t slot0 = (x & (kQuadsAhead - 1)) * 4;
@@ -649,14 +688,14 @@ sgd_block_kernel(const SgdParams prm)
                 const float r4[4] = {__int_as_float(a.z), __int_as_float(b.y), __int_as_float(c2.x), __int_as_float(c2.w)};
                 const int qtype = (a.x >> kQuadShift) & 3;
                 if (qtype == kQuadIndep) {
-                    indep_quad(slot0, u4, i4, r4, fetch_row);
+                    indep_quad(qrec, slot0, u4, i4, r4, fetch_row);
                 } else if (qtype == kQuadChain) {
                     bool skip = false;
                     if constexpr (TIMING) skip = (prm.exp & 32) != 0;   // experiment: chains cost nothing
                     if (skip) { fetch_row(0); fetch_row(1); fetch_row(2); fetch_row(3); }
-                    else chain_quad(slot0, u4, i4[0], r4, fetch_row);
+                    else chain_quad(qrec, slot0, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
-                    clean_quad(slot0, u4, i4, f4, r4, fetch_row);
+                    clean_quad(qrec, slot0, u4, i4, f4, r4, fetch_row);
                 } else {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
