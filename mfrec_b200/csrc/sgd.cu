@@ -528,7 +528,7 @@ sgd_block_kernel(const SgdParams prm)
             }
         };
         // kQuadChain: one item; its row stays in registers and is stored once
-        auto chain_quad = [&](const char *rec, uint32_t slot0, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
+        auto chain_quad = [&](uint32_t slot0, const int (&u4)[4], int it, const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
             load_quad_p(slot0, p4, b4);
@@ -554,7 +554,7 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadIndep: four ratings that share neither a user nor an item: their order does not
         // matter, so all loads, the four reductions and the four updates are issued side by side
         // (four independent dependency chains for the scheduler instead of one)
-        auto indep_quad = [&](const char *rec, uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
+        auto indep_quad = [&](uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4], q4[4];
             float b4[4], c4[4];
             load_quad_p(slot0, p4, b4);
@@ -588,7 +588,7 @@ sgd_block_kernel(const SgdParams prm)
         // kQuadClean: any items; an item row equal to the previous rating's stays in registers
         // (predicated loads, no branch), every updated row goes back to the shared-memory tile
         // (a later rating of the quad may reuse an item: program order through the tile is exact)
-        auto clean_quad = [&](const char *rec, uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
+        auto clean_quad = [&](uint32_t slot0, const int (&u4)[4], const int (&i4)[4], const int (&f4)[4],
                               const float (&r4)[4], auto &&hook) {
             Frag<E> p4[4];
             float b4[4];
@@ -626,6 +626,11 @@ sgd_block_kernel(const SgdParams prm)
 
         const int32_t done_base = step * W;
         uint32_t x = 0;   // quad cursor over the whole stream, runs across the phases
+        int4 na = make_int4(0, 0, 0, 0), nb = na, nc = na;   // record of quad x, read ahead
+        if (nquads > 0) {   // (its chunk was waited for by the prefetch above)
+            const int4 *nsrc = reinterpret_cast<const int4 *>(quad_rec(0));
+            na = nsrc[0]; nb = nsrc[1]; nc = nsrc[2];
+        }
         for (int p = 0; p < W; ++p) {
             const uint32_t xe = (uint32_t)(off_w[p + 1] - S0) >> 2;   // buckets are padded to quads
             if (p > 0) {
@@ -649,37 +654,36 @@ sgd_block_kernel(const SgdParams prm)
                         issue_chunk(nc);
                     }
                 }
-                // the quad whose rows are requested during this iteration
+                // the quad whose rows are requested during this iteration; past the end of the
+                // stream the last quad's rows are requested again into a free slot (never consumed),
+                // which keeps this straight-line code
                 const uint32_t fx = x + (kQuadsAhead - 1);
-                const bool fvalid = fx < nquads;
-                uint32_t fu[4] = {0, 0, 0, 0};
-                const char *frec = ring_b;
-                if (fvalid) {
-                    if ((fx & (kChunkQ - 1)) == 0) chunk_wait(fx / kChunkQ);   // first touch of a chunk
-                    frec = quad_rec(fx);
-                    fu[0] = *reinterpret_cast<const uint32_t *>(frec) & kIdMask;
-                    fu[1] = *reinterpret_cast<const uint32_t *>(frec + 12) & kIdMask;
-                    fu[2] = *reinterpret_cast<const uint32_t *>(frec + 24) & kIdMask;
-                    fu[3] = *reinterpret_cast<const uint32_t *>(frec + 36) & kIdMask;
-                }
+                if ((fx & (kChunkQ - 1)) == 0 && fx < nquads) chunk_wait(fx / kChunkQ);   // first touch of a chunk
+                const char *const frec = quad_rec(min(fx, nquads - 1));
+                const uint32_t fu[4] = {*reinterpret_cast<const uint32_t *>(frec) & kIdMask,
+                                        *reinterpret_cast<const uint32_t *>(frec + 12) & kIdMask,
+                                        *reinterpret_cast<const uint32_t *>(frec + 24) & kIdMask,
+                                        *reinterpret_cast<const uint32_t *>(frec + 36) & kIdMask};
                 const uint32_t fslot0 = (fx & (kQuadsAhead - 1)) * 4;
                 float *const fdst = prow_lane + fslot0 * KPAD;
                 auto fetch_row = [&](int t) {
                     if constexpr (TIMING) { if (prm.exp & 8) return; }
-                    if (fvalid) {
-                        const float *gsrc = row_ptr(P_lane, fu[t], KPAD * 4);
+                    const float *gsrc = row_ptr(P_lane, fu[t], KPAD * 4);
 #pragma unroll
-                        for (int c = 0; c < Frag<E>::NV; ++c)
-                            cp_async<Frag<E>::V * 4>(fdst + t * KPAD + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
-                    }
+                    for (int c = 0; c < Frag<E>::NV; ++c)
+                        cp_async<Frag<E>::V * 4>(fdst + t * KPAD + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
                 };
                 lap(0);
                 cp_async_wait<kQuadsAhead - 2>();   // the four rows of this quad have landed
                 __syncwarp();                       // ... and the bias copies / lane 0's stores are visible
                 lap(1);
-                const char *const qrec = quad_rec(x);
-                const int4 *qsrc = reinterpret_cast<const int4 *>(qrec);
-                const int4 a = qsrc[0], b = qsrc[1], c2 = qsrc[2];
+                // this quad's record was read one iteration ago (its decode would otherwise sit in
+                // front of everything else with a shared-memory latency); read the next one now
+                const int4 a = na, b = nb, c2 = nc;
+                {
+                    const int4 *nsrc = reinterpret_cast<const int4 *>(quad_rec(x + 1));
+                    na = nsrc[0]; nb = nsrc[1]; nc = nsrc[2];
+                }
                 lap(2);
                 const uint32_t slot0 = (x & (kQuadsAhead - 1)) * 4;
                 const int u4[4] = {a.x & kIdMask, a.w & kIdMask, b.z & kIdMask, c2.y & kIdMask};
@@ -688,14 +692,14 @@ sgd_block_kernel(const SgdParams prm)
                 const float r4[4] = {__int_as_float(a.z), __int_as_float(b.y), __int_as_float(c2.x), __int_as_float(c2.w)};
                 const int qtype = (a.x >> kQuadShift) & 3;
                 if (qtype == kQuadIndep) {
-                    indep_quad(qrec, slot0, u4, i4, r4, fetch_row);
+                    indep_quad(slot0, u4, i4, r4, fetch_row);
                 } else if (qtype == kQuadChain) {
                     bool skip = false;
                     if constexpr (TIMING) skip = (prm.exp & 32) != 0;   // experiment: chains cost nothing
                     if (skip) { fetch_row(0); fetch_row(1); fetch_row(2); fetch_row(3); }
-                    else chain_quad(qrec, slot0, u4, i4[0], r4, fetch_row);
+                    else chain_quad(slot0, u4, i4[0], r4, fetch_row);
                 } else if (qtype == kQuadClean) {
-                    clean_quad(qrec, slot0, u4, i4, f4, r4, fetch_row);
+                    clean_quad(slot0, u4, i4, f4, r4, fetch_row);
                 } else {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -703,9 +707,12 @@ sgd_block_kernel(const SgdParams prm)
                         fetch_row(t);
                     }
                 }
-                if (fvalid && lane < 4) {
-                    const uint32_t ul = *reinterpret_cast<const uint32_t *>(frec + 12 * lane) & kIdMask;
-                    cp_async<4>(pbias + fslot0 + lane, row_ptr(prm.ub, ul, 4));
+                {
+                    // lane t < 4 requests the bias of row t; ids picked from registers (a load from
+                    // the record here would put its latency at the end of every iteration)
+                    const bool lo = (lane & 2) == 0, even = (lane & 1) == 0;
+                    const uint32_t ul = lo ? (even ? fu[0] : fu[1]) : (even ? fu[2] : fu[3]);
+                    if (lane < 4) cp_async<4>(pbias + fslot0 + lane, row_ptr(prm.ub, ul, 4));
                 }
                 cp_async_commit();
                 lap(3);
