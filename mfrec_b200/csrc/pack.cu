@@ -320,18 +320,20 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     cudaStream_t st = ctx->stream;
     Tracer tr("pack", st);
     const int G = (opts && opts->n_slabs > 0) ? opts->n_slabs : 1;
-    int W = (opts && opts->workers > 0) ? opts->workers : 8;
-    if (W > 16) W = 16;  // the SGD kernel is built for at most 16 warps per CTA
+    // Concurrency P = B * W warps needs P^2 buckets per slab.  Measured on the Netflix shape
+    // (DESIGN.md section 5): ~40 ratings per bucket is the sweet spot -- a sub-epoch costs a fixed
+    // hand-over (ticket, tile load, write-back) plus the spread of its blocks' work, so with G
+    // slabs (G times fewer ratings per sub-epoch) less concurrency wins -- and for a given P it is
+    // better to keep one CTA on every SM with fewer warps than full CTAs on some of the SMs.
+    int W = (opts && opts->workers > 0) ? opts->workers : 0;
     int B = (opts && opts->row_blocks > 0) ? opts->row_blocks : 0;
-    if (B == 0) {
-        // ~40 ratings per bucket, never more row blocks than SMs.  Measured on the Netflix shape
-        // (DESIGN.md section 5): a sub-epoch costs a fixed hand-over (ticket, tile load, write-back)
-        // plus the spread of its blocks' work, so with G slabs -- G times fewer ratings per
-        // sub-epoch -- fewer, larger sub-epochs win even though they leave SMs idle.
-        double per_slab = (double)nnz / G;
-        B = (int)(sqrt(per_slab / 40.0) / W);
-        B = std::max(1, std::min(B, ctx->sm_count));
+    const double want_p = sqrt((double)nnz / G / 40.0);
+    if (W == 0) {
+        W = B > 0 ? (int)lround(want_p / B) : (int)lround(want_p / ctx->sm_count);
+        W = std::max(4, std::min(W, 8));
     }
+    if (W > 16) W = 16;  // the SGD kernel is built for at most 16 warps per CTA
+    if (B == 0) B = std::max(1, std::min((int)(want_p / W), ctx->sm_count));
     B = (int)std::max<int64_t>(1, std::min<int64_t>(B, std::min<int64_t>(nu, ni / G) / W));
     const uint64_t seed = opts ? opts->seed : 0;
     const bool keep_order = opts && opts->keep_order;
