@@ -102,7 +102,8 @@ def test_ratings_layout_is_bit_exact(native, small_problem, B, W, G):
 
 
 @pytest.mark.parametrize("kernel", ["linear", "logistic"])
-@pytest.mark.parametrize("k,B,W", [(12, 3, 4), (40, 2, 8), (128, 4, 2), (200, 2, 4), (20, 1, 1)])
+@pytest.mark.parametrize("k,B,W", [(12, 3, 4), (40, 2, 8), (128, 4, 2), (200, 2, 4), (20, 1, 1),
+                                   (64, 3, 5), (32, 2, 6), (16, 0, 0)])   # odd warp counts; 0 = the packer's own choice
 def test_stratified_matches_oracle_replay(native, small_problem, kernel, k, B, W):
     """The parallel schedule is equivalent to SOME sequential order; replaying exactly that
     order with the float64 oracle must give the same factors up to fp32 round-off."""
