@@ -16,6 +16,7 @@
 // redundantly.  The item scalars of the column block live in shared memory.  The
 // `while rmse <= rmse_last - min_improvement` control of the reference (rmse carried across
 // features, max_epochs ignored) runs on the host, one device reduction per pass.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -50,6 +51,8 @@ struct FunkParams {
     const int64_t *bucket_off;
     const int32_t *bucket_cnt;
     const int32_t *col_start;
+    const int32_t *row_start;   // [B*W + 1] first packed user id of every row group
+    int user_rows;              // shared-memory slots for the user scalars of a row block
     double *uf;          // [ni] item scalars of feature f, packed order
     double *vf;          // [nu] user scalars
     const double *ibp;   // [ni] item biases, packed order (variant > 0)
@@ -77,7 +80,23 @@ __device__ __forceinline__ void funk_st_release(int32_t *p, int v)
 
 // One launch = sub-epochs [s_begin, s_end) of one training pass.  With `ticks` the launch is
 // persistent and cooperative (all B sub-epochs): column blocks pass from CTA to CTA through
-// release / acquire counters exactly as in sgd.cu, instead of one kernel boundary per sub-epoch.
+// release / acquire counters exactly as in sgd.cu, instead of one kernel boundary per sub-epoch,
+// and inside a CTA column groups pass from warp to warp through shared-memory counters instead of
+// a CTA-wide barrier per phase.
+//
+// A row block's user scalars stay in shared memory for the whole launch (8 bytes per user: 26 KB
+// at Netflix shape), next to the column block's item scalars: the replay loop then touches no
+// global memory and needs none of the packer's stale-prefetch hints -- a re-read of a scalar that
+// was just written is an ordinary in-order shared-memory access.  A batch of 32 ratings is staged
+// in shared memory with coalesced loads (two broadcast loads per rating in the replay), the next
+// batch is loaded while the current one is replayed, and the scalars of a run of equal items /
+// equal users are forwarded in registers so that the serial chain of a hot item is ~10 dependent
+// float64 operations per rating and nothing else.
+struct FunkStage {          // one staged rating, 32 bytes
+    int u, i;               // user / item index relative to the row block / column block
+    double r, c, b;         // rating, cached partial prediction, baseline
+};
+
 __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -86,12 +105,21 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
     const int rb = blockIdx.x;
     double *ufs = reinterpret_cast<double *>(smem_raw);
     double *ibs = ufs + prm.tile_rows;
-    double *se_s = ibs + prm.tile_rows;
-    int64_t *boff = reinterpret_cast<int64_t *>(se_s + W);
+    double *vfs = ibs + prm.tile_rows;
+    double *se_s = vfs + prm.user_rows;
+    FunkStage *stage_all = reinterpret_cast<FunkStage *>(se_s + W);
+    int64_t *boff = reinterpret_cast<int64_t *>(stage_all + (size_t)W * 32);
     int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
+    volatile int32_t *phase_done = reinterpret_cast<volatile int32_t *>(bcnt + ((W * W + 2) & ~1));
+    FunkStage *stage = stage_all + warp * 32;
     const double lr = prm.lr, K = prm.K;
     double se = 0.0;
+    if (threadIdx.x < W) phase_done[threadIdx.x] = 0;
+    // this row block's user scalars (no other CTA touches them during the launch)
+    const int us0 = prm.row_start[rb * W], nub = prm.row_start[(rb + 1) * W] - us0;
+    for (int i = threadIdx.x; i < nub; i += blockDim.x) vfs[i] = prm.vf[us0 + i];
     for (int s = prm.s_begin; s < prm.s_end; ++s) {
+        const int step = s - prm.s_begin;
         const int cbl = (rb + s) % prm.B;
         const int cs = prm.col_start[cbl * W];
         const int nq = prm.col_start[(cbl + 1) * W] - cs;
@@ -102,68 +130,88 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
         }
         if (prm.ticks && threadIdx.x == 0)
             while (funk_ld_acquire(prm.ticks + cbl) < s) __nanosleep(64);
-        __syncthreads();   // the column block is ours; descriptors visible
+        __syncthreads();   // the column block is ours; descriptors (and, first time, vfs) visible
         // item scalars: L2 loads (another SM wrote them; L1 may hold a stale line)
         for (int i = threadIdx.x; i < nq; i += blockDim.x) {
             ufs[i] = __ldcg(prm.uf + cs + i);
             ibs[i] = prm.variant ? prm.ibp[cs + i] : 0.0;
         }
         __syncthreads();
+        const int32_t done_base = step * W;
         for (int p = 0; p < W; ++p) {
             const int64_t a = boff[warp * W + p];
             const int n = bcnt[warp * W + p];
-            int prev_u = -1;
-            double vf_cur = 0.0;
-            for (int base = 0; base < n; base += 32) {
-                const int j = base + lane;
-                PackedRating rt;
-                rt.u = 0; rt.i = cs; rt.r = 0.f;
-                double c = 0.0, vfu = 0.0, bb = 1.0;
-                if (j < n) {
-                    rt = prm.packed[a + j];
-                    rt.u &= kIdMask;   // the packer's hint bits (common.cuh) stay in rt.i until the replay
-                    c = prm.cache[a + j];
-                    vfu = prm.vf[rt.u];
-                    // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
-                    bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[(rt.i & kIdMask) - cs]), prm.ubp[rt.u])
-                                     : 1.0;
+            // first batch: triple, cache value, user bias (nothing of this is written by the pass)
+            PackedRating rt;
+            rt.u = us0; rt.i = cs; rt.r = 0.f;
+            double c = 0.0, ubv = 0.0;
+            if (lane < n) {
+                rt = prm.packed[a + lane];
+                c = prm.cache[a + lane];
+                if (prm.variant) ubv = prm.ubp[rt.u & kIdMask];
+            }
+            if (p > 0) {
+                // column group (warp + p) mod W comes from warp + 1, which used it in phase p - 1
+                const volatile int32_t *flag = phase_done + (warp + 1 == W ? 0 : warp + 1);
+                if (lane == 0) {
+                    while (*flag < done_base + p) __nanosleep(32);
+                    __threadfence_block();
                 }
+                __syncwarp();
+            }
+            int prev_u = -1, prev_i = -1;
+            double vf_cur = 0.0, uf_cur = 0.0;
+            for (int base = 0; base < n; base += 32) {
                 const int cnt = min(32, n - base);
-                for (int t = 0; t < cnt; ++t) {
-                    const int u_t = __shfl_sync(0xffffffffu, rt.u, t);
-                    const int if_t = __shfl_sync(0xffffffffu, rt.i, t);
-                    const int i_t = if_t & kIdMask;
-                    const double r_t = (double)__shfl_sync(0xffffffffu, rt.r, t);
-                    const double c_t = __shfl_sync(0xffffffffu, c, t);
-                    double v_t = __shfl_sync(0xffffffffu, vfu, t);
-                    const double b_t = __shfl_sync(0xffffffffu, bb, t);
-                    if (u_t == prev_u) {
-                        v_t = vf_cur;                                  // same user as the last rating
-                    } else {
-                        if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
-                        if (if_t & (kFlagStale | kFlagAdjUser)) {
-                            // the user occurred among the 32 preceding ratings: the staged scalar may
-                            // predate that update; lane 0 has written it back, read it again
-                            __syncwarp();
-                            v_t = prm.vf[u_t];
-                        }
+                __syncwarp();   // the previous batch has been replayed by every lane
+                {
+                    const int il = (rt.i & kIdMask) - cs;
+                    FunkStage st;
+                    st.u = (rt.u & kIdMask) - us0; st.i = il; st.r = (double)rt.r; st.c = c;
+                    // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
+                    st.b = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[il]), ubv) : 1.0;
+                    stage[lane] = st;
+                }
+                // next batch's inputs, in flight during the replay
+                {
+                    const int j = base + 32 + lane;
+                    rt.u = us0; rt.i = cs; rt.r = 0.f;
+                    c = 0.0; ubv = 0.0;
+                    if (j < n) {
+                        rt = prm.packed[a + j];
+                        c = prm.cache[a + j];
+                        if (prm.variant) ubv = prm.ubp[rt.u & kIdMask];
                     }
-                    const double mf = ufs[i_t - cs];
-                    const double pr = funk_estimate(mf, v_t, c_t, b_t, prm.trail, 1);
-                    const double err = __dadd_rn(r_t, -pr);
+                }
+                __syncwarp();
+#pragma unroll 2
+                for (int t = 0; t < cnt; ++t) {
+                    const FunkStage x = stage[t];   // broadcast loads
+                    const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
+                    const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
+                    const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
+                    const double err = __dadd_rn(x.r, -pr);
                     se = __dadd_rn(se, __dmul_rn(err, err));
-                    const double cf = v_t;
-                    if (prm.update_items)
-                        ufs[i_t - cs] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
+                    uf_cur = prm.update_items
+                                 ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
+                                 : mf;
                     vf_cur = prm.update_users
                                  ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
                                  : cf;
-                    prev_u = u_t;
+                    ufs[x.i] = uf_cur;     // every lane writes the same value
+                    vfs[x.u] = vf_cur;
+                    prev_u = x.u;
+                    prev_i = x.i;
                 }
             }
-            if (prev_u >= 0 && lane == 0) prm.vf[prev_u] = vf_cur;
-            __syncthreads();   // phase boundary (also orders lane 0's stores before the next loads)
+            // hand the column group over: item scalars written above, then the counter
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                phase_done[warp] = done_base + p + 1;
+            }
         }
+        __syncthreads();   // every warp is done with the tile
         for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.uf[cs + i] = ufs[i];
         if (prm.ticks) {
             __threadfence();
@@ -173,6 +221,7 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
             __syncthreads();
         }
     }
+    for (int i = threadIdx.x; i < nub; i += blockDim.x) prm.vf[us0 + i] = vfs[i];
     if (lane == 0) se_s[warp] = se;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -267,9 +316,10 @@ __global__ void funk_sequential_kernel(int variant, int min_epochs, double min_i
     }
 }
 
-size_t funk_smem_bytes(int tile_rows, int W)
+size_t funk_smem_bytes(int tile_rows, int user_rows, int W)
 {
-    return (size_t)tile_rows * 16 + (size_t)W * 8 + (size_t)(W * W + 1) * 8 + (size_t)(W * W + 2) * 4 + 64;
+    return (size_t)tile_rows * 16 + (size_t)user_rows * 8 + (size_t)W * 8 + (size_t)W * 32 * sizeof(FunkStage) +
+           (size_t)(W * W + 1) * 8 + (size_t)(W * W + 4) * 4 + (size_t)(W + 4) * 4 + 64;
 }
 
 }  // namespace
@@ -342,9 +392,20 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
         mfrec_ratings *R = nullptr;
         MF_TRY(mfrec_ratings_pack(ctx, ratings_index, ratings, 0, 0, nnz, ni, nu, nullptr, &o, &R));
         struct Guard { mfrec_ratings *r; ~Guard() { mfrec_ratings_destroy(r); } } guard{R};
-        const size_t smem = funk_smem_bytes(R->max_cb_items, R->W);
+        // user scalars of a row block live in shared memory: widest row block (users)
+        int user_rows = 0;
+        for (int b = 0; b < R->B; ++b)
+            user_rows = std::max(user_rows, R->h_row_start[(size_t)(b + 1) * R->W] - R->h_row_start[(size_t)b * R->W]);
+        user_rows = (user_rows + 1) & ~1;
+        const size_t smem = funk_smem_bytes(R->max_cb_items, user_rows, R->W);
         if (smem > ctx->smem_optin)
-            return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_train_funk: tile needs %zu B shared memory", smem);
+            return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                                   "mfrec_train_funk: %d item and %d user scalars per block need %zu B shared memory (> %zu)",
+                                   R->max_cb_items, user_rows, smem, ctx->smem_optin);
+        DevBuf<int32_t> row_start;
+        MF_CUDA(ctx, row_start.alloc(R->h_row_start.size(), ctx->stream));
+        MF_CUDA(ctx, cudaMemcpyAsync(row_start.p, R->h_row_start.data(), R->h_row_start.size() * 4,
+                                     cudaMemcpyHostToDevice, st));
         MF_CUDA(ctx, cudaFuncSetAttribute(funk_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         DevBuf<double> cache, ufp, vfp, ibp, ubp, se_part, se_tot;
         MF_CUDA(ctx, cache.alloc((size_t)R->packed_len + 1, ctx->stream));
@@ -367,6 +428,8 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
         FunkParams prm;
         prm.packed = R->packed; prm.bucket_off = R->bucket_off; prm.bucket_cnt = R->bucket_cnt;
         prm.col_start = R->col_start;
+        prm.row_start = row_start.p;
+        prm.user_rows = user_rows;
         prm.uf = ufp.p; prm.vf = vfp.p; prm.ibp = ibp.p; prm.ubp = ubp.p; prm.cache = cache.p;
         prm.B = R->B; prm.W = R->W; prm.tile_rows = R->max_cb_items; prm.variant = variant;
         prm.lr = learning_rate; prm.K = K; prm.overall = overall_avg;
