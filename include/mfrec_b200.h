@@ -121,6 +121,46 @@ int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int max_epochs
                      const double *users_bias, int update_users, int update_items,
                      const mfrec_opts *opts, int32_t *feature_epochs, double *feature_rmse);
 
+/* ---- development variants of the Funk loop (mfrec_b200/csrc/funk_dev.cu) ----
+ * They run in the reference's own order (one device thread, float64, unfused) and are
+ * bit-identical to the reference; the dense `user + item * nbr_users` rating cache of the
+ * reference limits them to toy sizes here as there (MFREC_ERR_UNSUPPORTED above 2^29 cells).
+ *
+ * Replaces estimator_loop  mfrec/lib/gd_estimator.pyx:210-303 (call site gradient_descent.py:596):
+ * honours max_epochs, carries `improvement` across features, records
+ * rmse_hist[epoch + f*max_epochs + batch*max_epochs*k] (only those entries are written).
+ * With max_epochs < 0 it is estimator_loop2 (:308-395): the control of
+ * estimator_loop_without_bias, no history (rmse_hist may be NULL). */
+int mfrec_funk_loop_dev(mfrec_ctx *ctx, int min_epochs, int max_epochs, double min_improvement,
+                        int k, double f_init, double learning_rate, double K, double *u, double *v,
+                        const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                        int32_t ni, int32_t nu, int batch, double *rmse_hist,
+                        int32_t *feature_epochs, double *feature_rmse);
+
+/* Replaces estimator_subloop  gd_estimator.pyx:903-962 (gradient_descent.py:322): one pass of
+ * feature f with the caller's dense cache float64 [ni*nu] (read only); *rmse_out = its rmse. */
+int mfrec_funk_subloop(mfrec_ctx *ctx, int f, int k, double f_init, double learning_rate, double K,
+                       double *u, double *v, const int32_t *ratings_index, const double *ratings,
+                       int64_t nnz, int32_t ni, int32_t nu, const double *rating_cache,
+                       double *rmse_out);
+
+/* Replaces predictor_subloop  gd_estimator.pyx:967-995 (gradient_descent.py:327): refreshes the
+ * caller's dense cache for feature f (rating_cache is read and written). */
+int mfrec_funk_predictor_subloop(mfrec_ctx *ctx, int f, int k, double f_init, const double *u,
+                                 const double *v, const int32_t *ratings_index, int64_t nnz,
+                                 int32_t ni, int32_t nu, double *rating_cache);
+
+/* Replaces estimator_loop_with_learned_bias  gd_estimator.pyx:401-483 (gradient_descent.py:501):
+ * full clamped k-dot per rating, updates feature f and both biases (items_bias / users_bias are
+ * written). */
+int mfrec_train_funk_learned_bias(mfrec_ctx *ctx, int min_epochs, double min_improvement, int k,
+                                  double f_init, double learning_rate, double learning_rate_users,
+                                  double learning_rate_items, double K_feature, double K_bias,
+                                  double overall_avg, double *u, double *v,
+                                  const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                                  int32_t ni, int32_t nu, double *items_bias, double *users_bias,
+                                  int32_t *feature_epochs, double *feature_rmse);
+
 /* Replaces the per-pair Python loop of metrics.test_predict_rating (metrics.py:58-67)
  * over the predictors above.  pairs: int32 [n][2] = (user, item).  out: float64 [n]. */
 int mfrec_predict_pairs(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,

@@ -32,7 +32,8 @@ PREDICTORS = {
 EXPORTS = (
     "mfrec_abi_version", "mfrec_ctx_create", "mfrec_ctx_destroy", "mfrec_last_error",
     "mfrec_ctx_stream", "mfrec_ctx_sync", "mfrec_ctx_launch_count", "mfrec_train_kmf",
-    "mfrec_train_funk", "mfrec_train_als_wrmf", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn", "mfrec_topn_sweep",
+    "mfrec_train_funk", "mfrec_funk_loop_dev", "mfrec_funk_subloop", "mfrec_funk_predictor_subloop",
+    "mfrec_train_funk_learned_bias", "mfrec_train_als_wrmf", "mfrec_predict_pairs", "mfrec_rmse_pairs", "mfrec_topn", "mfrec_topn_sweep",
     "mfrec_bias_stats", "mfrec_ratings_pack", "mfrec_ratings_destroy", "mfrec_ratings_info",
     "mfrec_ratings_quad_types", "mfrec_ratings_perm", "mfrec_ratings_order", "mfrec_ratings_offsets", "mfrec_ratings_packed",
     "mfrec_ratings_slab_items", "mfrec_model_create", "mfrec_model_read", "mfrec_model_destroy",
@@ -182,6 +183,57 @@ def train_funk(variant, min_epochs, max_epochs, min_improvement, k, f_init, lr, 
         C.c_int64(ratings.shape[0]), C.c_int32(u.shape[1]), C.c_int32(v.shape[1]),
         _ptr(items_bias), _ptr(users_bias), C.c_int(update_users), C.c_int(update_items),
         C.byref(o), _ptr(fe), _ptr(fr)), ctx.handle)
+    return fe, fr
+
+
+def funk_loop_dev(min_epochs, max_epochs, min_improvement, k, f_init, lr, K, u, v, ratings_index,
+                  ratings, batch=0, rmse_hist=None, ctx=None):
+    """estimator_loop (max_epochs >= 0, rmse_hist written) / estimator_loop2 (max_epochs < 0):
+    gd_estimator.pyx:210-303 / :308-395, reference order.  Returns (epochs, rmse) per feature."""
+    ctx = ctx or default_context()
+    fe = np.zeros(k, dtype=np.int32)
+    fr = np.zeros(k, dtype=np.float64)
+    _check(lib().mfrec_funk_loop_dev(
+        ctx.handle, C.c_int(min_epochs), C.c_int(max_epochs), C.c_double(min_improvement), C.c_int(k),
+        C.c_double(f_init), C.c_double(lr), C.c_double(K), _ptr(u), _ptr(v), _ptr(ratings_index),
+        _ptr(ratings), C.c_int64(ratings.shape[0]), C.c_int32(u.shape[1]), C.c_int32(v.shape[1]),
+        C.c_int(batch), _ptr(rmse_hist) if rmse_hist is not None else None, _ptr(fe), _ptr(fr)), ctx.handle)
+    return fe, fr
+
+
+def funk_subloop(f, k, f_init, lr, K, u, v, ratings_index, ratings, rating_cache, ctx=None):
+    """estimator_subloop (gd_estimator.pyx:903-962): one pass of feature f, returns its rmse."""
+    ctx = ctx or default_context()
+    out = C.c_double(0.0)
+    _check(lib().mfrec_funk_subloop(
+        ctx.handle, C.c_int(f), C.c_int(k), C.c_double(f_init), C.c_double(lr), C.c_double(K), _ptr(u),
+        _ptr(v), _ptr(ratings_index), _ptr(ratings), C.c_int64(ratings.shape[0]), C.c_int32(u.shape[1]),
+        C.c_int32(v.shape[1]), _ptr(rating_cache), C.byref(out)), ctx.handle)
+    return float(out.value)
+
+
+def funk_predictor_subloop(f, k, f_init, u, v, ratings_index, rating_cache, ctx=None):
+    """predictor_subloop (gd_estimator.pyx:967-995): cache refresh of feature f, in place."""
+    ctx = ctx or default_context()
+    _check(lib().mfrec_funk_predictor_subloop(
+        ctx.handle, C.c_int(f), C.c_int(k), C.c_double(f_init), _ptr(u), _ptr(v), _ptr(ratings_index),
+        C.c_int64(ratings_index.shape[0]), C.c_int32(u.shape[1]), C.c_int32(v.shape[1]),
+        _ptr(rating_cache)), ctx.handle)
+
+
+def train_funk_learned_bias(min_epochs, min_improvement, k, f_init, lr, lr_users, lr_items, K_feature,
+                            K_bias, overall_avg, u, v, ratings_index, ratings, items_bias, users_bias,
+                            ctx=None):
+    """estimator_loop_with_learned_bias (gd_estimator.pyx:401-483), reference order, in place."""
+    ctx = ctx or default_context()
+    fe = np.zeros(k, dtype=np.int32)
+    fr = np.zeros(k, dtype=np.float64)
+    _check(lib().mfrec_train_funk_learned_bias(
+        ctx.handle, C.c_int(min_epochs), C.c_double(min_improvement), C.c_int(k), C.c_double(f_init),
+        C.c_double(lr), C.c_double(lr_users), C.c_double(lr_items), C.c_double(K_feature),
+        C.c_double(K_bias), C.c_double(overall_avg), _ptr(u), _ptr(v), _ptr(ratings_index), _ptr(ratings),
+        C.c_int64(ratings.shape[0]), C.c_int32(u.shape[1]), C.c_int32(v.shape[1]), _ptr(items_bias),
+        _ptr(users_bias), _ptr(fe), _ptr(fr)), ctx.handle)
     return fe, fr
 
 

@@ -88,6 +88,51 @@ def funk_train(variant, min_epochs, min_improvement, dim, f_init, lr, K, u, v, r
     return int(passes), fe, fr
 
 
+def funk_loop_dev(min_epochs, max_epochs, min_improvement, dim, f_init, lr, K, u, v, ratings_index,
+                  ratings, batch=0, rmse_hist=None):
+    """estimator_loop (max_epochs >= 0, rmse_hist required) / estimator_loop2 (max_epochs < 0).
+    Returns (epochs_per_feature, rmse_per_feature)."""
+    fe = np.zeros(dim, dtype=np.int32)
+    fr = np.zeros(dim, dtype=np.float64)
+    lib().oracle_funk_loop_dev(
+        C.c_int(min_epochs), C.c_int(max_epochs), C.c_double(min_improvement), C.c_int(dim),
+        C.c_double(f_init), C.c_double(lr), C.c_double(K), _p(u, np.float64), _p(v, np.float64),
+        _p(ratings_index, np.int32), _p(ratings, np.float64), C.c_int64(ratings.shape[0]),
+        C.c_int64(u.shape[1]), C.c_int64(v.shape[1]), C.c_int(batch),
+        _p(rmse_hist, np.float64) if rmse_hist is not None else None, _p(fe, np.int32), _p(fr, np.float64))
+    return fe, fr
+
+
+def funk_subloop(f, dim, f_init, lr, K, u, v, ratings_index, ratings, rating_cache):
+    fn = lib().oracle_funk_subloop
+    fn.restype = C.c_double
+    return float(fn(C.c_int(f), C.c_int(dim), C.c_double(f_init), C.c_double(lr), C.c_double(K),
+                    _p(u, np.float64), _p(v, np.float64), _p(ratings_index, np.int32),
+                    _p(ratings, np.float64), C.c_int64(ratings.shape[0]), C.c_int64(u.shape[1]),
+                    C.c_int64(v.shape[1]), _p(rating_cache, np.float64)))
+
+
+def funk_predictor_subloop(f, dim, f_init, u, v, ratings_index, rating_cache):
+    lib().oracle_funk_predictor_subloop(
+        C.c_int(f), C.c_int(dim), C.c_double(f_init), _p(u, np.float64), _p(v, np.float64),
+        _p(ratings_index, np.int32), C.c_int64(ratings_index.shape[0]), C.c_int64(u.shape[1]),
+        C.c_int64(v.shape[1]), _p(rating_cache, np.float64))
+
+
+def funk_learned_bias(min_epochs, min_improvement, dim, f_init, lr, lr_users, lr_items, K_feature,
+                      K_bias, overall_avg, u, v, ratings_index, ratings, items_bias, users_bias):
+    fe = np.zeros(dim, dtype=np.int32)
+    fr = np.zeros(dim, dtype=np.float64)
+    lib().oracle_funk_learned_bias(
+        C.c_int(min_epochs), C.c_double(min_improvement), C.c_int(dim), C.c_double(f_init),
+        C.c_double(lr), C.c_double(lr_users), C.c_double(lr_items), C.c_double(K_feature),
+        C.c_double(K_bias), C.c_double(overall_avg), _p(u, np.float64), _p(v, np.float64),
+        _p(ratings_index, np.int32), _p(ratings, np.float64), C.c_int64(ratings.shape[0]),
+        C.c_int64(u.shape[1]), C.c_int64(v.shape[1]), _p(items_bias, np.float64),
+        _p(users_bias, np.float64), _p(fe, np.int32), _p(fr, np.float64))
+    return fe, fr
+
+
 def _bias_args(u, v, mu, items_bias, users_bias):
     ib = _zeros_like_bias(u.shape[1], items_bias)
     ub = _zeros_like_bias(v.shape[1], users_bias)

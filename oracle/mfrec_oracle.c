@@ -186,6 +186,142 @@ int64_t oracle_funk_train(int variant, int min_epochs, double min_improvement, i
 }
 
 /*
+ * A3 development variants of the Funk loop; all share the training pass
+ * of estimator_loop_without_bias and the `estimator` above.  Their rating cache is a DENSE
+ * array indexed `user + item * nbr_users` (gd_estimator.pyx:250-255): toy sizes only.
+ *
+ * ---- mfrec/lib/gd_estimator.pyx:210-303 `estimator_loop` (feature_training_dev,
+ *      gradient_descent.py:596): the only loop that honours max_epochs (:264) and records
+ *      rmse_hist[epoch + f*max_epochs + batch*max_epochs*dim] (:285); `improvement` (0.0) carries
+ *      across features like rmse / rmse_last; user factor written before the item factor
+ *      (:281-282), both from the old values.
+ * ---- :308-395 `estimator_loop2`: same with the control of estimator_loop_without_bias (no
+ *      history, no max_epochs) -- pass max_epochs < 0 and rmse_hist = NULL.
+ */
+void oracle_funk_loop_dev(int min_epochs, int max_epochs, double min_improvement, int dim,
+                          double f_init, double lr, double K, double *u, double *v,
+                          const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                          int64_t ni, int64_t nu, int batch, double *rmse_hist,
+                          int32_t *feature_epochs, double *feature_rmse)
+{
+    double rmse = 2.0, rmse_last = 0.0, improvement = 0.0;
+    const int hist = max_epochs >= 0;
+    double *cache = (double *)calloc((size_t)(ni * nu > 0 ? ni * nu : 1), sizeof(double));
+    for (int f = 0; f < dim; ++f) {
+        double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
+        int epoch = 0;
+        while (hist ? ((epoch < min_epochs || improvement >= min_improvement) && epoch < max_epochs)
+                    : (epoch < min_epochs || rmse <= rmse_last - min_improvement)) {
+            double se = 0.0;
+            rmse_last = rmse;
+            for (int64_t n = 0; n < nnz; ++n) {
+                const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+                const double p = funk_estimate(uf[item], vf[user], f, dim, f_init,
+                                               cache[user + (int64_t)item * nu], 1, 1.0, 0.0, 0.0);
+                const double err = 1.0 * ratings[n] - p;
+                se += err * err;
+                const double cf = vf[user], mf = uf[item];
+                vf[user] += lr * (err * mf - K * cf);
+                uf[item] += lr * (err * cf - K * mf);
+            }
+            rmse = sqrt(se / (double)nnz);
+            if (hist) {
+                rmse_hist[epoch + (int64_t)f * max_epochs + (int64_t)batch * max_epochs * dim] = rmse;
+                improvement = rmse_last - rmse;
+            }
+            ++epoch;
+        }
+        if (feature_epochs) feature_epochs[f] = epoch;
+        if (feature_rmse) feature_rmse[f] = rmse;
+        for (int64_t n = 0; n < nnz; ++n) {
+            const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+            double *c = &cache[user + (int64_t)item * nu];
+            *c = funk_estimate(uf[item], vf[user], f, dim, f_init, *c, 0, 1.0, 0.0, 0.0);
+        }
+    }
+    free(cache);
+}
+
+/* ---- mfrec/lib/gd_estimator.pyx:903-962 `estimator_subloop` (feature_training2,
+ *      gradient_descent.py:322): exactly one pass of feature f with the caller's dense cache
+ *      (read only); returns the rmse -- the only native function with a return value. */
+double oracle_funk_subloop(int f, int dim, double f_init, double lr, double K, double *u, double *v,
+                           const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                           int64_t ni, int64_t nu, const double *rating_cache)
+{
+    double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
+    double se = 0.0;
+    for (int64_t n = 0; n < nnz; ++n) {
+        const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+        const double p = funk_estimate(uf[item], vf[user], f, dim, f_init,
+                                       rating_cache[user + (int64_t)item * nu], 1, 1.0, 0.0, 0.0);
+        const double err = 1.0 * ratings[n] - p;
+        se += err * err;
+        const double cf = vf[user], mf = uf[item];
+        vf[user] += lr * (err * mf - K * cf);
+        uf[item] += lr * (err * cf - K * mf);
+    }
+    return sqrt(se / (double)nnz);
+}
+
+/* ---- mfrec/lib/gd_estimator.pyx:967-995 `predictor_subloop` (gradient_descent.py:327): the
+ *      cache refresh of feature f on the caller's dense cache (written). */
+void oracle_funk_predictor_subloop(int f, int dim, double f_init, const double *u, const double *v,
+                                   const int32_t *ratings_index, int64_t nnz, int64_t ni, int64_t nu,
+                                   double *rating_cache)
+{
+    const double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
+    for (int64_t n = 0; n < nnz; ++n) {
+        const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+        double *c = &rating_cache[user + (int64_t)item * nu];
+        *c = funk_estimate(uf[item], vf[user], f, dim, f_init, *c, 0, 1.0, 0.0, 0.0);
+    }
+}
+
+/* ---- mfrec/lib/gd_estimator.pyx:401-483 `estimator_loop_with_learned_bias`
+ *      (feature_training_bias, gradient_descent.py:501) with its `full_estimator` :115-148:
+ *      a full clamped k-dot per rating (overall + b_i + b_u + sum_f, clamp, trailing term, clamp;
+ *      no cache), but only feature f and the two biases are updated -- biases first, with their
+ *      own learning rates and the freshly updated value inside the regulariser (`+=` re-reads the
+ *      element), then the item factor, then the user factor, both from the old values. */
+void oracle_funk_learned_bias(int min_epochs, double min_improvement, int dim, double f_init,
+                              double lr, double lr_users, double lr_items, double K_feature,
+                              double K_bias, double overall_avg, double *u, double *v,
+                              const int32_t *ratings_index, const double *ratings, int64_t nnz,
+                              int64_t ni, int64_t nu, double *items_bias, double *users_bias,
+                              int32_t *feature_epochs, double *feature_rmse)
+{
+    double rmse = 2.0, rmse_last = 0.0;
+    for (int f = 0; f < dim; ++f) {
+        double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
+        int epoch = 0;
+        while (epoch < min_epochs || rmse <= rmse_last - min_improvement) {
+            double se = 0.0;
+            rmse_last = rmse;
+            for (int64_t n = 0; n < nnz; ++n) {
+                const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+                double s = overall_avg + items_bias[item] + users_bias[user];
+                for (int g = 0; g < dim; ++g) s += u[(int64_t)g * ni + item] * v[(int64_t)g * nu + user];
+                s = clamp15(s);
+                s += (dim - f - 1) * f_init * f_init;
+                s = clamp15(s);
+                const double err = ratings[n] - s;
+                se += err * err;
+                const double cf = vf[user], mf = uf[item];
+                users_bias[user] += lr_users * (err - K_bias * users_bias[user]);
+                items_bias[item] += lr_items * (err - K_bias * items_bias[item]);
+                uf[item] += lr * (err * cf - K_feature * mf);
+                vf[user] += lr * (err * mf - K_feature * cf);
+            }
+            rmse = sqrt(se / (double)nnz);
+            ++epoch;
+        }
+        if (feature_epochs) feature_epochs[f] = epoch;
+        if (feature_rmse) feature_rmse[f] = rmse;
+    }
+}
+
+/*
  * Predictors (one k-dot + affine / logistic map), by id:
  *   0  GDRecommender.predict_rating            gradient_descent.py:621-631   dot + 1.0
  *   1  GDRecommender.predict_rating_with_bias  gradient_descent.py:637-648   dot + (mu + (b_i + b_u))

@@ -84,6 +84,38 @@ def main():
                             min_improvement=0.0005, mu=mu, bi=bi, bu=bu, update_users=gates[0],
                             update_items=gates[1])
 
+    # ---- A3: development variants (gd_estimator.pyx:210-303, 308-395, 903-995, 401-483)
+    kd = 3
+    hist = np.zeros(2 * 7 * kd)
+    u = np.zeros((kd, ni)) + f_init
+    v = np.zeros((kd, nu)) + f_init
+    gd.estimator_loop(3, 7, 0.0005, kd, f_init, lr, K, u, v, idx, r, 1, hist, nu, ni, 0)
+    out = dict(idx=idx, r=r, k=kd, f_init=f_init, lr=lr, K=K, loop_u=u, loop_v=v, loop_hist=hist,
+               loop_min_epochs=3, loop_max_epochs=7, loop_min_improvement=0.0005, loop_batch=1)
+    u = np.zeros((kd, ni)) + f_init
+    v = np.zeros((kd, nu)) + f_init
+    gd.estimator_loop2(4, 99, 0.0005, kd, f_init, lr, K, u, v, idx, r, np.zeros(ni), nu, ni, 0)
+    out.update(loop2_u=u, loop2_v=v, loop2_min_epochs=4, loop2_min_improvement=0.0005)
+    u = np.zeros((kd, ni)) + f_init
+    v = np.zeros((kd, nu)) + f_init
+    cache = np.zeros(nu * ni)
+    rmses = []
+    for f in range(2):
+        for _ in range(3):
+            rmses.append(gd.estimator_subloop(f, 1, 0.0, kd, f_init, lr, K, u, v, idx, r, cache, nu, ni, 0))
+        gd.predictor_subloop(f, 1, kd, f_init, u, v, idx, r, cache, nu, ni)
+    cells = idx[:, 0].astype(np.int64) + idx[:, 1].astype(np.int64) * nu
+    out.update(sub_u=u, sub_v=v, sub_rmse=np.array(rmses), sub_cache_cells=cells, sub_cache_values=cache[cells],
+               sub_cache_sum=cache.sum())
+    u = np.zeros((kd, ni)) + f_init
+    v = np.zeros((kd, nu)) + f_init
+    lb, lub = bi.copy(), bu.copy()
+    gd.estimator_loop_with_learned_bias(3, 99, 0.0005, kd, f_init, lr, 0.004, 0.003, K, 0.01, mu, u, v, idx, r,
+                                        lb, lub, nu, ni, 0)
+    out.update(lb_u=u, lb_v=v, lb_ib0=bi, lb_ub0=bu, lb_ib=lb, lb_ub=lub, lb_mu=mu, lb_min_epochs=3,
+               lb_min_improvement=0.0005, lb_lr_users=0.004, lb_lr_items=0.003, lb_K_bias=0.01)
+    np.savez_compressed(os.path.join(HERE, "funk_dev.npz"), **out)
+
     # ---- predictors + RMSE (the reference's numpy one-liners)
     u, v = synth.init_factors(nu, ni, k, seed=7)
     rng = np.random.Generator(np.random.PCG64(8))

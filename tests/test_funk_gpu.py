@@ -91,3 +91,52 @@ def test_funk_dropin_converges_ml100k(native, ml100k_problem):
     sg, _ = cpu.rmse_pairs("predict_rating", u1, v1, p["probe_idx"], p["probe_r"])
     assert abs(gd_estimator.last_feature_rmse[-1] - fr[-1]) / fr[-1] < 5e-3
     assert abs(sg[0] - so[0]) / so[0] < 5e-3, (sg[0], so[0])
+
+
+def test_dev_variants_match_reference_golden(native):
+    """A3 development loops through the drop-in module (reference signatures): equal, bit for
+    bit, to vectors made by the reference's own kernels."""
+    from mfrec_b200.lib import gd_estimator
+    d = dict(np.load(os.path.join(GOLD, "funk_dev.npz")))
+    idx, r = d["idx"], d["r"]
+    k, f_init, lr, K = int(d["k"]), float(d["f_init"]), float(d["lr"]), float(d["K"])
+    ni, nu = d["loop_u"].shape[1], d["loop_v"].shape[1]
+
+    def fresh():
+        return np.zeros((k, ni)) + f_init, np.zeros((k, nu)) + f_init
+
+    u, v = fresh()
+    hist = np.zeros_like(d["loop_hist"])
+    assert gd_estimator.estimator_loop(int(d["loop_min_epochs"]), int(d["loop_max_epochs"]),
+                                       float(d["loop_min_improvement"]), k, f_init, lr, K, u, v, idx, r,
+                                       int(d["loop_batch"]), hist, nu, ni, 0) is None
+    assert np.array_equal(u, d["loop_u"]) and np.array_equal(v, d["loop_v"]) and np.array_equal(hist, d["loop_hist"])
+
+    u, v = fresh()
+    gd_estimator.estimator_loop2(int(d["loop2_min_epochs"]), 99, float(d["loop2_min_improvement"]), k, f_init,
+                                 lr, K, u, v, idx, r, np.zeros(ni), nu, ni, 0)
+    assert np.array_equal(u, d["loop2_u"]) and np.array_equal(v, d["loop2_v"])
+
+    u, v = fresh()
+    cache = np.zeros(nu * ni)
+    rm = []
+    for f in range(2):
+        for _ in range(3):
+            rm.append(gd_estimator.estimator_subloop(f, 1, 0.0, k, f_init, lr, K, u, v, idx, r, cache, nu, ni, 0))
+        gd_estimator.predictor_subloop(f, 1, k, f_init, u, v, idx, r, cache, nu, ni)
+    assert np.array_equal(np.array(rm), d["sub_rmse"])
+    assert np.array_equal(u, d["sub_u"]) and np.array_equal(v, d["sub_v"])
+    assert np.array_equal(cache[d["sub_cache_cells"]], d["sub_cache_values"]) and cache.sum() == float(d["sub_cache_sum"])
+
+    u, v = fresh()
+    ib, ub = d["lb_ib0"].copy(), d["lb_ub0"].copy()
+    gd_estimator.estimator_loop_with_learned_bias(
+        int(d["lb_min_epochs"]), 99, float(d["lb_min_improvement"]), k, f_init, lr, float(d["lb_lr_users"]),
+        float(d["lb_lr_items"]), K, float(d["lb_K_bias"]), float(d["lb_mu"]), u, v, idx, r, ib, ub, nu, ni, 0)
+    assert np.array_equal(u, d["lb_u"]) and np.array_equal(v, d["lb_v"])
+    assert np.array_equal(ib, d["lb_ib"]) and np.array_equal(ub, d["lb_ub"])
+
+    with pytest.raises(NotImplementedError):
+        gd_estimator.estimator_loop_with_implicit_feedback()
+    with pytest.raises(ValueError):   # the dense cache is indexed with nbr_users: it must be v's width
+        gd_estimator.estimator_subloop(0, 1, 0.0, k, f_init, lr, K, u, v, idx, r, cache, nu + 1, ni, 0)

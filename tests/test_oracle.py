@@ -167,3 +167,45 @@ def test_als_wrmf_port_matches_reference_kernel():
     np.testing.assert_allclose(u1, u0, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(v1, v0, rtol=1e-9, atol=1e-12)
     assert not np.array_equal(v0[:, :5], np.zeros((k, 5)))
+
+
+def test_funk_dev_variants_golden():
+    """A3 development loops (gd_estimator.pyx:210-303, 308-395, 903-995, 401-483): the C
+    restatement against vectors made by the reference's own kernels, bit for bit."""
+    d = dict(np.load(os.path.join(GOLD, "funk_dev.npz")))
+    idx, r = d["idx"], d["r"]
+    k, f_init, lr, K = int(d["k"]), float(d["f_init"]), float(d["lr"]), float(d["K"])
+    ni, nu = d["loop_u"].shape[1], d["loop_v"].shape[1]
+
+    def fresh():
+        return np.zeros((k, ni)) + f_init, np.zeros((k, nu)) + f_init
+
+    u, v = fresh()
+    hist = np.zeros_like(d["loop_hist"])
+    cpu.funk_loop_dev(int(d["loop_min_epochs"]), int(d["loop_max_epochs"]), float(d["loop_min_improvement"]),
+                      k, f_init, lr, K, u, v, idx, r, int(d["loop_batch"]), hist)
+    assert np.array_equal(u, d["loop_u"]) and np.array_equal(v, d["loop_v"]) and np.array_equal(hist, d["loop_hist"])
+
+    u, v = fresh()
+    cpu.funk_loop_dev(int(d["loop2_min_epochs"]), -1, float(d["loop2_min_improvement"]), k, f_init, lr, K,
+                      u, v, idx, r)
+    assert np.array_equal(u, d["loop2_u"]) and np.array_equal(v, d["loop2_v"])
+
+    u, v = fresh()
+    cache = np.zeros(nu * ni)
+    rm = []
+    for f in range(2):
+        for _ in range(3):
+            rm.append(cpu.funk_subloop(f, k, f_init, lr, K, u, v, idx, r, cache))
+        cpu.funk_predictor_subloop(f, k, f_init, u, v, idx, cache)
+    assert np.array_equal(np.array(rm), d["sub_rmse"])
+    assert np.array_equal(u, d["sub_u"]) and np.array_equal(v, d["sub_v"])
+    assert np.array_equal(cache[d["sub_cache_cells"]], d["sub_cache_values"]) and cache.sum() == float(d["sub_cache_sum"])
+
+    u, v = fresh()
+    ib, ub = d["lb_ib0"].copy(), d["lb_ub0"].copy()
+    cpu.funk_learned_bias(int(d["lb_min_epochs"]), float(d["lb_min_improvement"]), k, f_init, lr,
+                          float(d["lb_lr_users"]), float(d["lb_lr_items"]), K, float(d["lb_K_bias"]),
+                          float(d["lb_mu"]), u, v, idx, r, ib, ub)
+    assert np.array_equal(u, d["lb_u"]) and np.array_equal(v, d["lb_v"])
+    assert np.array_equal(ib, d["lb_ib"]) and np.array_equal(ub, d["lb_ub"])
