@@ -214,7 +214,7 @@ def run_native(args):
     # ---------------- device-resident arm: K epochs, CUDA events on the library stream ------
     R = _native.Ratings(None, None, ni, nu, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
                         nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
-                        workers=args.workers, n_slabs=G)
+                        workers=args.workers, n_slabs=(G if G > 1 else 0))
     M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
     layout_desc = ("stratified B=%d W=%d sub-epochs/epoch=%d max_bucket=%d widest_column_block=%d items"
                    % (R.B, R.W, R.launches_per_epoch, R.max_bucket, R.max_cb_items))
