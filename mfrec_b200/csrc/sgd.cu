@@ -203,6 +203,32 @@ __device__ __forceinline__ float *row_ptr(float *base, uint32_t idx, uint32_t st
     return reinterpret_cast<float *>(a);
 }
 
+// Packed fp32 pairs (sm_100: FMUL2 / FFMA2 take two independent IEEE operations per instruction;
+// each half rounds exactly like the scalar instruction).  The hot loop is bound by the number of
+// instructions a warp issues, so the row updates and the dot product run on pairs.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
@@ -297,6 +323,7 @@ sgd_block_kernel(const SgdParams prm)
     const float a_i = upd_i ? 1.f - prm.lr * prm.Ki : 1.f;
     const float a_u = upd_u ? 1.f - prm.lr * prm.Ku : 1.f;
     const float a_b = 1.f - prm.lr * prm.Kb;
+    const unsigned long long a_i2 = pack2(a_i, a_i), a_u2 = pack2(a_u, a_u);
     const bool upd_bu = (KERNEL == MFREC_KERNEL_LINEAR) || upd_u;
     const bool upd_bi = (KERNEL == MFREC_KERNEL_LINEAR) || upd_i;
     const float fx_scale = prm.fx_scale, fx_inv = prm.fx_inv;
@@ -430,9 +457,19 @@ sgd_block_kernel(const SgdParams prm)
             return __reduce_add_sync(FULL, v);
         };
         auto dot_fx = [&](const Frag<E> &pu, const Frag<E> &q) {
-            float part = pu.x[0] * q.x[0];
+            float part;
+            if constexpr (E >= 2) {
+                // two interleaved partial sums (even / odd elements), one packed FMA per pair
+                unsigned long long acc = mul2(pack2(pu.x[0], pu.x[1]), pack2(q.x[0], q.x[1]));
 #pragma unroll
-            for (int e = 1; e < E; ++e) part = fmaf(pu.x[e], q.x[e], part);
+                for (int e = 2; e < E; e += 2)
+                    acc = fma2(pack2(pu.x[e], pu.x[e + 1]), pack2(q.x[e], q.x[e + 1]), acc);
+                float lo, hi;
+                unpack2(acc, lo, hi);
+                part = lo + hi;
+            } else {
+                part = pu.x[0] * q.x[0];
+            }
             return __float2int_rn(part * fx_scale);
         };
         auto apply = [&](int isum, float r, Frag<E> &pu, float &bu, Frag<E> &q, float &bi) {
@@ -452,11 +489,18 @@ sgd_block_kernel(const SgdParams prm)
             bu = upd_bu ? fmaf(a_b, bu, gl) : bu;
             bi = upd_bi ? fmaf(a_b, bi, gl) : bi;
             const float gli = upd_i ? gl : 0.f, glu = upd_u ? gl : 0.f;
+            if constexpr (E >= 2) {
+                const unsigned long long glu2 = pack2(glu, glu), gli2 = pack2(gli, gli);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const float pe = pu.x[e], qe = q.x[e];
-                pu.x[e] = fmaf(glu, qe, a_u * pe);
-                q.x[e] = fmaf(gli, pe, a_i * qe);
+                for (int e = 0; e < E; e += 2) {
+                    const unsigned long long pe = pack2(pu.x[e], pu.x[e + 1]), qe = pack2(q.x[e], q.x[e + 1]);
+                    unpack2(fma2(glu2, qe, mul2(a_u2, pe)), pu.x[e], pu.x[e + 1]);
+                    unpack2(fma2(gli2, pe, mul2(a_i2, qe)), q.x[e], q.x[e + 1]);
+                }
+            } else {
+                const float pe = pu.x[0], qe = q.x[0];
+                pu.x[0] = fmaf(glu, qe, a_u * pe);
+                q.x[0] = fmaf(gli, pe, a_i * qe);
             }
         };
         auto store_p_row = [&](int u, const Frag<E> &pu) {
