@@ -22,6 +22,13 @@ int main(int argc, char **argv)
     mfrec_part::partition_ids(deg, sorted, nblocks, W, slabs, group, perm, start);
     mfrec_part::partition_ids(deg, sorted, nblocks, W, slabs, group2, perm2, start2);
     if (group != group2 || perm != perm2 || start != start2) { puts("FAIL not deterministic"); return 0; }
+    {   // the threaded second level with a reused workspace must give the same partition
+        mfrec_part::Workspace ws;
+        for (int rep = 0; rep < 2; ++rep) {
+            mfrec_part::partition_ids(deg, sorted, nblocks, W, slabs, group2, perm2, start2, ws, 4);
+            if (group != group2 || perm != perm2 || start != start2) { puts("FAIL threads change the result"); return 0; }
+        }
+    }
     const int ng = nblocks * W;
     if ((int)start.size() != ng + 1 || start[0] != 0 || start[ng] != n) { puts("FAIL start"); return 0; }
     std::vector<char> seen(n, 0);
