@@ -60,7 +60,6 @@ static_assert(4 * kDepth <= kChunk, "the prefetch cursor may run at most one chu
 struct SgdParams {
     const PackedRating *packed;
     const int64_t *bucket_off;
-    const int32_t *bucket_cnt;
     const int32_t *col_start;
     float *Q, *ib, *P, *ub;
     double *se_part;  // [B] per-CTA sums of this launch
@@ -300,8 +299,7 @@ sgd_block_kernel(const SgdParams prm)
     PackedRating *ring_all = reinterpret_cast<PackedRating *>(pbias_all + (size_t)W * kDepth);
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring_all + (size_t)W * kRing);
     int64_t *boff = reinterpret_cast<int64_t *>(bars + 1 + kStages * W);
-    int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
-    double *se_s = reinterpret_cast<double *>(bcnt + ((W * W + 1) & ~1));
+    double *se_s = reinterpret_cast<double *>(boff + W * W + 2);
     volatile int32_t *phase_done = reinterpret_cast<volatile int32_t *>(se_s + W);
 
     float *prow = prow_all + (size_t)warp * kDepth * KPAD;
@@ -353,10 +351,7 @@ sgd_block_kernel(const SgdParams prm)
 
         // this CTA's W*W bucket descriptors (worker-major: index w * W + phase) + end sentinel
         const int64_t bucket_base = (((int64_t)prm.slab * prm.B + rb) * prm.B + cbl) * W * W;
-        for (int i = threadIdx.x; i <= W * W; i += blockDim.x) {
-            boff[i] = prm.bucket_off[bucket_base + i];
-            if (i < W * W) bcnt[i] = prm.bucket_cnt[bucket_base + i];
-        }
+        for (int i = threadIdx.x; i <= W * W; i += blockDim.x) boff[i] = prm.bucket_off[bucket_base + i];
         // Q tile: one elected thread takes the column block over and issues the bulk copies
         if (threadIdx.x == 0) {
             if (prm.ticks) {
@@ -878,8 +873,7 @@ size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W)
     b += (size_t)W * kDepth * 4;                           // user-bias rings
     b += (size_t)W * kRing * sizeof(PackedRating);         // rating rings
     b += (size_t)(1 + kStages * W) * 8;                    // mbarriers
-    b += (size_t)(W * W + 1) * 8;                          // bucket offsets
-    b += (size_t)((W * W + 1) & ~1) * 4;                   // bucket counts
+    b += (size_t)(W * W + 2) * 8;                          // bucket offsets (padded quads make counts redundant)
     b += (size_t)W * 8;                                    // per-warp squared error
     b += (size_t)((W + 3) & ~3) * 4;                       // per-warp phase counters
     return b + 128;
@@ -983,7 +977,6 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     SgdParams prm;
     prm.packed = r->packed;
     prm.bucket_off = r->bucket_off;
-    prm.bucket_cnt = r->bucket_cnt;
     prm.col_start = r->col_start;
     prm.Q = m->Q; prm.ib = m->ib; prm.P = m->P; prm.ub = m->ub;
     prm.B = r->B; prm.W = r->W;
