@@ -71,8 +71,10 @@ enum { MFREC_SCHED_STRATIFIED = 0, /* conflict-free block schedule, fp32, all SM
 /* Optional knobs; pass NULL for defaults.  Zero in any field means "choose for me". */
 typedef struct mfrec_opts {
     int32_t schedule;     /* MFREC_SCHED_*                                                  */
-    int32_t row_blocks;   /* B: CTA-level row/column blocks per device (default: from nnz)   */
-    int32_t workers;      /* W: warps per CTA = warp-level row/column groups (default 8)     */
+    int32_t row_blocks;   /* B: CTA-level row/column blocks per device; 0 = chosen with W so
+                             that a bucket holds ~40 ratings and B <= #SMs where the Q tile
+                             of a column block fits in shared memory         */
+    int32_t workers;      /* W: warps per CTA = warp-level row/column groups; 0 = 4..8       */
     int32_t n_slabs;      /* G: item slabs (one per GPU of a DSGD ring); 1 on a single GPU   */
     int32_t keep_order;   /* keep packed-position -> input-index map for mfrec_ratings_order */
     int32_t k_hint;       /* number of features the layout will be trained with (sizes the
