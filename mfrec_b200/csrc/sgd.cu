@@ -329,6 +329,7 @@ sgd_block_kernel(const SgdParams prm)
 
     double se = 0.0;          // fp64 total of fp32 per-bucket partials, over the whole launch
     uint32_t chunk_seq = 0;   // chunks this warp has pulled so far (ring stage + mbarrier parity)
+    bool chunks_issued = false;   // the first chunks of the coming sub-epoch are already on their way
     // opt-in section timer (cycles per warp): 0 bookkeeping + prefetch issue, 1 cp.async wait,
     // 2 quad load, 3 updates, 4 phase hand-over wait, 5 sub-epoch set-up (ticket + tile), 6 tail
     unsigned long long tsec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -400,7 +401,10 @@ sgd_block_kernel(const SgdParams prm)
                 bulk_g2s(ring + (g % kStages) * kChunk, stream + (size_t)c * kChunk, cnt * 12u, bar);
             }
         };
-        for (uint32_t c = 0; c < nchunks && c < (uint32_t)kStages; ++c) issue_chunk(c);
+        // (the first chunks of every sub-epoch but the first were requested at the end of the
+        // previous one, see below)
+        if (!chunks_issued)
+            for (uint32_t c = 0; c < nchunks && c < (uint32_t)kStages; ++c) issue_chunk(c);
 
         // Prefetch: one cp.async group per quad, so group index == quad index.  The first
         // kQuadsAhead - 1 quads are fetched here; after that the rows of quad x + kQuadsAhead - 1
@@ -767,6 +771,27 @@ sgd_block_kernel(const SgdParams prm)
         }
         cp_async_wait<0>();
         chunk_seq += nchunks;
+        // This warp's rating ring is free: request the first chunks of its next sub-epoch's stream
+        // now, so that they cross while the CTA waits for its last warp, writes the tile back and
+        // waits for the next column block (the stream does not depend on any other CTA).
+        chunks_issued = false;
+        if (s + 1 < prm.s_end) {
+            const int ncbl = (rb + s + 1) % prm.B;
+            const int64_t nbase = ((((int64_t)prm.slab * prm.B + rb) * prm.B + ncbl) * W + warp) * W;
+            const int64_t nS0 = __ldg(prm.bucket_off + nbase);
+            const uint32_t nslen = (uint32_t)(__ldg(prm.bucket_off + nbase + W) - nS0);
+            const uint32_t nn = min((nslen + kChunk - 1) / kChunk, (uint32_t)kStages);
+            if (lane == 0) {
+                for (uint32_t c = 0; c < nn; ++c) {
+                    const uint32_t cnt = min((uint32_t)kChunk, nslen - c * kChunk);
+                    const uint32_t g = chunk_seq + c;
+                    uint64_t *bar = my_bar + (g % kStages);
+                    mbar_expect_tx(bar, cnt * 12u);
+                    bulk_g2s(ring + (g % kStages) * kChunk, prm.packed + nS0 + (size_t)c * kChunk, cnt * 12u, bar);
+                }
+            }
+            chunks_issued = true;
+        }
         __syncthreads();   // every warp is done with the tile
         lap(4);
         // write the Q tile back and pass the column block on
