@@ -208,7 +208,7 @@ def run_native(args):
         ni = ni * G
     idx_d, r_d = gpu_synth(torch, dev, nu, ni, nnz, seed=0, item_tiles=G)
     torch.cuda.synchronize()
-    ctx = _native.Context(local)
+    ctx = _native.default_context(local)   # the context the drop-in modules use as well: one stream, one pool
     u0, v0 = synth.init_factors(nu, ni, k, seed=2)
 
     # ---------------- device-resident arm: K epochs, CUDA events on the library stream ------
@@ -297,9 +297,13 @@ def run_native(args):
                                           HP["K_bias"], 0.0, un, vn, idxn, rn, ibn, ubn)
             return kmf_train.last_rmse[-1]
 
-        # warm-up calls: the library's stream-ordered memory pool reaches its steady-state size
-        # only after the second call (the first two grow it, which costs hundreds of ms)
-        for _ in range(max(args.warmup, 3)):
+        # warm-up calls: the device's stream-ordered memory pool reaches its steady state after two
+        # calls (445 / 76 / 70 / 70 ... ms in a fresh process, tools/e2e_probe.py).  The drop-in
+        # uses the same library context as the device-resident arm above (two contexts = two
+        # streams sharing one pool made single calls take 0.1 - 2.4 s at random).  ms_per_call
+        # lists every timed call.
+        e2e_warm = max(args.warmup, 3)
+        for _ in range(e2e_warm):
             one_call()
         torch.cuda.synchronize()
         per_call = []
@@ -314,7 +318,7 @@ def run_native(args):
         d2h = un.nbytes + vn.nbytes + ibn.nbytes + ubn.nbytes + 8
         e2e = {"value": nnz * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3 / args.e2e_steps,
-               "steps": args.e2e_steps, "warmup_calls": max(args.warmup, 3), "ms_per_call": per_call,
+               "steps": args.e2e_steps, "warmup_calls": e2e_warm, "ms_per_call": per_call,
                "epochs_per_call": 1, "last_rmse": float(last)}
 
     cpu_baseline = None
@@ -346,7 +350,7 @@ def run_topn(args):
     torch.cuda.set_device(local)
     nu, ni, _nnz, k = synth.SHAPES["netflix"]
     N = 100
-    ctx = _native.Context(local)
+    ctx = _native.default_context(local)   # the context the drop-in modules use as well: one stream, one pool
     u0, v0 = synth.init_factors(nu, ni, k, seed=2)
     u_h, v_h = torch.from_numpy(u0).pin_memory(), torch.from_numpy(v0).pin_memory()
     items = torch.empty((nu, N), dtype=torch.int32).pin_memory()

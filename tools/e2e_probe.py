@@ -15,7 +15,7 @@ u0, v0 = synth.init_factors(nu, ni, k, seed=2)
 u_h = torch.from_numpy(u0); v_h = torch.from_numpy(v0)
 if pinned: u_h, v_h = u_h.pin_memory(), v_h.pin_memory()
 ib = np.zeros(ni); ub = np.zeros(nu)
-for it in range(3):
+for it in range(int(os.environ.get("CALLS", "3"))):
     t0 = time.perf_counter()
     kmf_train.train_linear_kernel(1, k, 0.1, 0.005, 0.0, 0.0, 0.05, 0.05, 0.007, 0.0, u_h.numpy(), v_h.numpy(), idx_h.numpy(), r_h.numpy(), ib, ub)
     print("call %d: %.1f ms rmse %.5f" % (it, (time.perf_counter() - t0) * 1e3, kmf_train.last_rmse[-1]), flush=True)
