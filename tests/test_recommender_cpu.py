@@ -80,3 +80,35 @@ def test_parameters_and_labels():
     assert k.items_index['matrix'] == 5 and 'item5' not in k.items_index
     k.set_item_by_label('user1', 'matrix', 4)
     assert k.relationship_matrix[1, 5] == 4.0
+
+
+def test_funk_dev_shims_validate_before_touching_the_device():
+    """The A3 drop-ins (gd_estimator.pyx:210-303, 308-395, 401-483, 903-995) raise the reference's
+    exception types for bad buffers, and ValueError where the reference would index out of
+    bounds, before any device work."""
+    import numpy as np
+    import pytest
+    from mfrec_b200.lib import gd_estimator as gd
+    k, ni, nu = 2, 5, 4
+    u, v = np.zeros((k, ni)) + 0.1, np.zeros((k, nu)) + 0.1
+    idx = np.array([[0, 1], [3, 4]], dtype=np.int32)
+    r = np.array([3.0, 5.0])
+    hist = np.zeros(1 * 3 * k)
+    with pytest.raises(ValueError):     # dtype mismatch, like Cython's buffer check
+        gd.estimator_loop(1, 3, 0.0, k, 0.1, 0.01, 0.02, u.astype(np.float32), v, idx, r, 0, hist, nu, ni)
+    with pytest.raises(ValueError):     # rmse_hist too short for batch 1
+        gd.estimator_loop(1, 3, 0.0, k, 0.1, 0.01, 0.02, u, v, idx, r, 1, hist, nu, ni)
+    with pytest.raises(ValueError):     # the dense cache is indexed with nbr_users: must be v's width
+        gd.estimator_loop2(1, 3, 0.0, k, 0.1, 0.01, 0.02, u, v, idx, r, np.zeros(ni), nu + 1, ni)
+    with pytest.raises(ValueError):     # dense cache smaller than nbr_users * nbr_items
+        gd.estimator_subloop(0, 1, 0.0, k, 0.1, 0.01, 0.02, u, v, idx, r, np.zeros(3), nu, ni)
+    with pytest.raises(IndexError):
+        gd.predictor_subloop(k, 1, k, 0.1, u, v, idx, r, np.zeros(nu * ni), nu, ni)
+    with pytest.raises(ValueError):     # read-only bias array where the loop writes it
+        ib = np.zeros(ni)
+        ib.setflags(write=False)
+        gd.estimator_loop_with_learned_bias(1, 9, 0.0, k, 0.1, 0.01, 0.01, 0.01, 0.02, 0.01, 3.0, u, v, idx, r,
+                                            ib, np.zeros(nu), nu, ni)
+    with pytest.raises(NotImplementedError):
+        gd.estimator_loop_with_implicit_feedback()
+    assert np.all(u == 0.1) and np.all(v == 0.1)
