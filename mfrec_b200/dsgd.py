@@ -12,7 +12,6 @@ and warps inside one GPU.  After G steps every rank holds its own slab again.
 The ring logic is backend-neutral (``Ring``): the GPU backend drives libmfrec_b200, the tests
 drive the same class over gloo with the CPU oracle as the per-block update.
 """
-import numpy as np
 
 
 def slab_at(rank, step, world):
