@@ -58,6 +58,7 @@ struct mfrec_ctx {
     } staged;                               // mfrec_model_create converts from these instead of copying
     int refs = 1;                  // the creator + every live mfrec_ratings / mfrec_model
     std::shared_ptr<void> pack_host;   // host scratch of mfrec_ratings_pack, reused across calls
+    std::shared_ptr<void> stager;      // pinned bounce buffers for large pageable host arrays (runtime.cu)
     std::string err;
 };
 // Objects allocate from the context's stream-ordered pool and free into it, so they keep the
@@ -201,6 +202,13 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W);
 
 // runtime.cu
+// Host <-> device copies of caller-owned arrays.  Page-locked memory goes straight to
+// cudaMemcpyAsync; a large PAGEABLE array is staged through pinned bounce buffers by four host
+// threads (the runtime's own pageable path is a single-threaded memcpy: ~3x slower).  h2d returns
+// when every chunk is enqueued on `st` (the host array may then be reused), d2h when the data
+// is in `dst_host`.
+int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
+int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st);
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
                         const int32_t *perm_dev, float *dst_nk, const double *staged_dev = nullptr);
 int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,

@@ -349,9 +349,8 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     if (!is_device && nnz > 0) {
         MF_CUDA(ctx, idx_stage.alloc((size_t)nnz * 2, ctx->stream));
         MF_CUDA(ctx, r_stage.alloc((size_t)nnz * rsz, ctx->stream));
-        MF_CUDA(ctx, cudaMemcpyAsync(idx_stage.p, ratings_index, (size_t)nnz * 8,
-                                     cudaMemcpyHostToDevice, st));
-        MF_CUDA(ctx, cudaMemcpyAsync(r_stage.p, ratings, (size_t)nnz * rsz, cudaMemcpyHostToDevice, st));
+        MF_TRY(mfrec_copy_h2d(ctx, idx_stage.p, ratings_index, (size_t)nnz * 8, st));
+        MF_TRY(mfrec_copy_h2d(ctx, r_stage.p, ratings, (size_t)nnz * rsz, st));
         d_idx = idx_stage.p;
         d_r = r_stage.p;
     }

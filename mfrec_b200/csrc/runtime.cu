@@ -1,8 +1,11 @@
 // Context, error reporting, resident model and the boundary layout conversion
 // ([k][n] float64 host  <->  [n][kpad] float32 device, optionally row-permuted).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <mutex>
+#include <thread>
 
 #include "common.cuh"
 
@@ -209,6 +212,150 @@ __global__ void vec_from_dev_kernel(const float *__restrict__ src, int32_t n,
     if (j < n) dst[j] = (double)src[perm ? perm[j] : j];
 }
 
+// ---- staged copies of large pageable host arrays ----------------------------------------------
+namespace {
+
+struct HostStager {
+    static constexpr int T = 4, NB = 2;
+    static constexpr size_t CH = (size_t)16 << 20;
+    char *buf[T][NB] = {};
+    cudaEvent_t ev[T][NB] = {};
+    bool ready = false;
+    std::mutex mu;   // one staged copy at a time per context
+    ~HostStager()
+    {
+        for (int t = 0; t < T; ++t)
+            for (int b = 0; b < NB; ++b) {
+                if (ev[t][b]) cudaEventDestroy(ev[t][b]);
+                if (buf[t][b]) cudaFreeHost(buf[t][b]);
+            }
+    }
+    cudaError_t init()
+    {
+        if (ready) return cudaSuccess;
+        for (int t = 0; t < T; ++t)
+            for (int b = 0; b < NB; ++b) {
+                cudaError_t e = cudaHostAlloc((void **)&buf[t][b], CH, cudaHostAllocDefault);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[t][b], cudaEventDisableTiming);
+                if (e != cudaSuccess) return e;
+            }
+        ready = true;
+        return cudaSuccess;
+    }
+};
+
+size_t stage_min_bytes()
+{
+    const char *s = getenv("MFREC_STAGE_MIN_BYTES");   // tests lower it to reach the staged path
+    return s ? (size_t)atoll(s) : ((size_t)8 << 20);
+}
+
+bool host_is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+HostStager *stager_of(mfrec_ctx *ctx)
+{
+    if (!ctx->stager) ctx->stager = std::make_shared<HostStager>();
+    return static_cast<HostStager *>(ctx->stager.get());
+}
+
+}  // namespace
+
+int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return MFREC_OK;
+    if (bytes < stage_min_bytes() || !host_is_pageable(src_host)) {
+        MF_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        return MFREC_OK;
+    }
+    HostStager *S = stager_of(ctx);
+    std::lock_guard<std::mutex> lock(S->mu);
+    MF_CUDA(ctx, S->init());
+    const size_t CH = HostStager::CH;
+    const size_t nchunks = (bytes + CH - 1) / CH;
+    const int device = ctx->device;
+    cudaError_t errs[HostStager::T];
+    std::thread workers[HostStager::T];
+    for (int t = 0; t < HostStager::T; ++t) {
+        errs[t] = cudaSuccess;
+        workers[t] = std::thread([=, &errs]() {
+            cudaError_t e = cudaSetDevice(device);
+            size_t i = 0;
+            for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += HostStager::T, ++i) {
+                const int b = (int)(i % HostStager::NB);
+                const size_t off = c * CH, n = std::min(CH, bytes - off);
+                e = cudaEventSynchronize(S->ev[t][b]);   // the buffer's previous transfer is done
+                if (e != cudaSuccess) break;
+                memcpy(S->buf[t][b], static_cast<const char *>(src_host) + off, n);
+                e = cudaMemcpyAsync(static_cast<char *>(dst_dev) + off, S->buf[t][b], n, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(S->ev[t][b], st);
+            }
+            errs[t] = e;
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (cudaError_t e : errs) MF_CUDA(ctx, e);
+    return MFREC_OK;
+}
+
+int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return MFREC_OK;
+    if (bytes < stage_min_bytes() || !host_is_pageable(dst_host)) {
+        MF_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        MF_CUDA(ctx, cudaStreamSynchronize(st));
+        return MFREC_OK;
+    }
+    HostStager *S = stager_of(ctx);
+    std::lock_guard<std::mutex> lock(S->mu);
+    MF_CUDA(ctx, S->init());
+    // what precedes on `st` (the kernels that produce src_dev) is ordered before the copies below
+    // because they are enqueued on the same stream
+    const size_t CH = HostStager::CH;
+    const size_t nchunks = (bytes + CH - 1) / CH;
+    const int device = ctx->device;
+    cudaError_t errs[HostStager::T];
+    std::thread workers[HostStager::T];
+    for (int t = 0; t < HostStager::T; ++t) {
+        errs[t] = cudaSuccess;
+        workers[t] = std::thread([=, &errs]() {
+            cudaError_t e = cudaSetDevice(device);
+            // two chunks in flight per worker: the transfer of chunk i + 1 runs while chunk i is
+            // copied out of its bounce buffer
+            size_t pend_off[HostStager::NB] = {0, 0}, pend_n[HostStager::NB] = {0, 0};
+            bool pend[HostStager::NB] = {false, false};
+            size_t i = 0;
+            auto drain = [&](int b) {
+                if (!pend[b] || e != cudaSuccess) return;
+                e = cudaEventSynchronize(S->ev[t][b]);
+                if (e == cudaSuccess) memcpy(static_cast<char *>(dst_host) + pend_off[b], S->buf[t][b], pend_n[b]);
+                pend[b] = false;
+            };
+            for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += HostStager::T, ++i) {
+                const int b = (int)(i % HostStager::NB);
+                drain(b);   // the buffer still holds an earlier chunk: copy it out first
+                if (e != cudaSuccess) break;
+                const size_t off = c * CH, n = std::min(CH, bytes - off);
+                e = cudaMemcpyAsync(S->buf[t][b], static_cast<const char *>(src_dev) + off, n, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaEventRecord(S->ev[t][b], st);
+                pend_off[b] = off; pend_n[b] = n; pend[b] = e == cudaSuccess;
+            }
+            for (int b = 0; b < HostStager::NB; ++b) drain(b);
+            errs[t] = e;
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (cudaError_t e : errs) MF_CUDA(ctx, e);
+    return MFREC_OK;
+}
+
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
                         const int32_t *perm_dev, float *dst_nk, const double *staged_dev)
 {
@@ -221,8 +368,7 @@ int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, 
     const double *src = staged_dev;
     if (!src) {
         MF_CUDA(ctx, stage.alloc((size_t)k * n, ctx->stream));
-        MF_CUDA(ctx, cudaMemcpyAsync(stage.p, host_kn, (size_t)k * n * sizeof(double),
-                                     cudaMemcpyHostToDevice, ctx->stream));
+        MF_TRY(mfrec_copy_h2d(ctx, stage.p, host_kn, (size_t)k * n * sizeof(double), ctx->stream));
         src = stage.p;
     }
     dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
@@ -241,9 +387,7 @@ int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, 
     dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
     rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(src_nk, k, kpad, n, perm_dev, stage.p);
     MF_LAUNCH_CHECK(ctx);
-    MF_CUDA(ctx, cudaMemcpyAsync(host_kn, stage.p, (size_t)k * n * sizeof(double),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-    MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MF_TRY(mfrec_copy_d2h(ctx, host_kn, stage.p, (size_t)k * n * sizeof(double), ctx->stream));
     return MFREC_OK;
 }
 

@@ -1183,13 +1183,15 @@ extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k
     // copy blocks the host until everything queued before it on its stream has drained
     MF_CUDA(ctx, cudaMemcpyAsync(d_ib.p, items_bias, (size_t)ni * 8, cudaMemcpyHostToDevice, sa));
     MF_CUDA(ctx, cudaMemcpyAsync(d_ub.p, users_bias, (size_t)nu * 8, cudaMemcpyHostToDevice, sa));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_idx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, sa));
+    // (mfrec_copy_h2d: page-locked arrays go straight to cudaMemcpyAsync and everything below
+    // overlaps with the packer; large pageable arrays are staged by four host threads first)
+    MF_TRY(mfrec_copy_h2d(ctx, d_idx.p, ratings_index, (size_t)nnz * 8, sa));
     MF_CUDA(ctx, cudaEventRecord(ev_idx, sa));
     MF_CUDA(ctx, cudaStreamWaitEvent(sb, ev_idx, 0));   // (also orders the pool allocations before sb's use)
-    MF_CUDA(ctx, cudaMemcpyAsync(d_r.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, sb));
+    MF_TRY(mfrec_copy_h2d(ctx, d_r.p, ratings, (size_t)nnz * 8, sb));
     MF_CUDA(ctx, cudaEventRecord(ev_val, sb));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_v.p, v, (size_t)k * nu * 8, cudaMemcpyHostToDevice, sb));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_u.p, u, (size_t)k * ni * 8, cudaMemcpyHostToDevice, sb));
+    MF_TRY(mfrec_copy_h2d(ctx, d_v.p, v, (size_t)k * nu * 8, sb));
+    MF_TRY(mfrec_copy_h2d(ctx, d_u.p, u, (size_t)k * ni * 8, sb));
     MF_CUDA(ctx, cudaEventRecord(ev_fac, sb));
     ctx->values_ready = ev_val;
     MF_TRY(mfrec_ratings_pack(ctx, d_idx.p, d_r.p, 0, 1, nnz, ni, nu, nullptr, &o, &R));

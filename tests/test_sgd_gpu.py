@@ -287,3 +287,22 @@ def test_quad_fast_paths_match_oracle_replay(native, k, nu, ni, nnz, B, W):
         assert qt["chain"] > qt["clean"] + qt["independent"], qt
     if ni == 400:
         assert qt["independent"] + qt["clean"] > qt["chain"], qt
+
+
+def test_staged_pageable_copies_change_nothing(native, small_problem, monkeypatch):
+    """Large pageable host arrays go through pinned bounce buffers filled by host threads
+    (runtime.cu); with the size threshold lowered the same call must give the same bits."""
+    from mfrec_b200.lib import kmf_train
+    p = small_problem
+    k = 24
+
+    def run():
+        u, v, ib, ub = _fresh(p["nu"], p["ni"], k)
+        kmf_train.train_linear_kernel(2, k, 0.1, LR, 0.0, 0.0, KU, KI, KB, 0.0, u, v, p["idx"], p["r"], ib, ub)
+        return u, v, ib, ub
+
+    ref = run()
+    monkeypatch.setenv("MFREC_STAGE_MIN_BYTES", "4096")
+    got = run()
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
