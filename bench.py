@@ -440,10 +440,21 @@ def time_reference(workload, nnz_sample, epochs=1):
         t0 = time.perf_counter()
         cpu.kmf_train("linear", epochs, k, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"], u, v, idx, r, ib, ub)
         dt = time.perf_counter() - t0
+    # the same arithmetic on ROW-major float32 factors (the GPU path's layout), one core: how much of
+    # the gap is the reference's feature-major float64 layout (SURVEY 8(d) "fair-layout CPU figure")
+    P = np.ascontiguousarray(v.T, dtype=np.float32)
+    Q = np.ascontiguousarray(u.T, dtype=np.float32)
+    t0 = time.perf_counter()
+    cpu.kmf_epoch_rowmajor_f32(k, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"], P, Q,
+                               np.zeros(nu, dtype=np.float32), np.zeros(ni, dtype=np.float32), idx,
+                               r.astype(np.float32))
+    dt_fair = time.perf_counter() - t0
     return {"value": n * epochs / dt, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": "%d-rating sample of the %s workload, full-size factor matrices (%dx%d, k=%d), %d epoch, %.1f s"
                       % (n, workload, nu, ni, k, epochs, dt),
-            "host_cores_available": os.cpu_count()}
+            "host_cores_available": os.cpu_count(),
+            "fair_layout": {"value": n / dt_fair, "unit": UNIT, "cores": 1,
+                            "what": "same loop in C on row-major float32 factors (oracle/mfrec_oracle.c), same sample"}}
 
 
 def run_reference(args):

@@ -88,6 +88,17 @@ def funk_train(variant, min_epochs, min_improvement, dim, f_init, lr, K, u, v, r
     return int(passes), fe, fr
 
 
+def kmf_epoch_rowmajor_f32(dim, lr, K_users, K_items, K_bias, P, Q, users_bias, items_bias, ratings_index,
+                           ratings):
+    """One epoch of the linear kernel's arithmetic on row-major float32 factors (measurement aid for
+    bench.py's fair-layout CPU figure); returns the sum of squared errors."""
+    fn = lib().oracle_kmf_epoch_rowmajor_f32
+    fn.restype = C.c_double
+    return float(fn(C.c_int(dim), C.c_float(lr), C.c_float(K_users), C.c_float(K_items), C.c_float(K_bias),
+                    _p(P, np.float32), _p(Q, np.float32), _p(users_bias, np.float32), _p(items_bias, np.float32),
+                    _p(ratings_index, np.int32), _p(ratings, np.float32), C.c_int64(ratings.shape[0])))
+
+
 def funk_loop_dev(min_epochs, max_epochs, min_improvement, dim, f_init, lr, K, u, v, ratings_index,
                   ratings, batch=0, rmse_hist=None):
     """estimator_loop (max_epochs >= 0, rmse_hist required) / estimator_loop2 (max_epochs < 0).

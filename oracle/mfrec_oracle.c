@@ -186,6 +186,37 @@ int64_t oracle_funk_train(int variant, int min_epochs, double min_improvement, i
 }
 
 /*
+ * "Fair layout" CPU figure: the arithmetic of train_linear_kernel
+ * (kmf_train.pyx:241-273, both sides updated) on ROW-major float32 factors -- the layout the GPU
+ * path uses -- so that bench.py can report how much of the GPU / reference ratio is the
+ * reference's feature-major float64 layout and how much is the device.  One thread, the input
+ * order; a measurement aid, not a parity oracle.  Returns the sum of squared errors.
+ */
+double oracle_kmf_epoch_rowmajor_f32(int dim, float lr, float K_users, float K_items, float K_bias,
+                                     float *P /* [nu][dim] */, float *Q /* [ni][dim] */,
+                                     float *users_bias, float *items_bias,
+                                     const int32_t *ratings_index, const float *ratings, int64_t nnz)
+{
+    double se = 0.0;
+    for (int64_t n = 0; n < nnz; ++n) {
+        const int user = ratings_index[2 * n], item = ratings_index[2 * n + 1];
+        float *p = P + (int64_t)user * dim, *q = Q + (int64_t)item * dim;
+        float s = items_bias[item] + users_bias[user];
+        for (int f = 0; f < dim; ++f) s += p[f] * q[f];
+        const float err = ratings[n] - s;
+        se += (double)err * err;
+        users_bias[user] += lr * (err - K_bias * users_bias[user]);
+        items_bias[item] += lr * (err - K_bias * items_bias[item]);
+        for (int f = 0; f < dim; ++f) {
+            const float cf = p[f], mf = q[f];
+            q[f] = mf + lr * (err * cf - K_items * mf);
+            p[f] = cf + lr * (err * mf - K_users * cf);
+        }
+    }
+    return se;
+}
+
+/*
  * A3 development variants of the Funk loop; all share the training pass
  * of estimator_loop_without_bias and the `estimator` above.  Their rating cache is a DENSE
  * array indexed `user + item * nbr_users` (gd_estimator.pyx:250-255): toy sizes only.
