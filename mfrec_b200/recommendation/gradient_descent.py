@@ -1,5 +1,6 @@
 """``GDRecommender``: Funk-SVD trained one feature at a time
-(reference: mfrec/recommendation/gradient_descent.py:30-120, 506-545, 621-648, 769-802, 879-905).
+(reference: mfrec/recommendation/gradient_descent.py:30-120, 299-329, 472-503, 506-545, 577-599,
+621-648, 769-802, 879-905).
 
 ``train`` (= ``feature_training``) calls ``mfrec_b200.lib.gd_estimator``, the drop-in for the
 reference's Cython module."""
@@ -72,6 +73,58 @@ class GDRecommender(MFRecommender):
                 ratings_index, ratings, self.nbr_users, self.nbr_items, int(verbose))
 
     train = feature_training
+
+    def _init_model(self, initialize_model):
+        if initialize_model:
+            self.svd_v = np.zeros([self.dimensionality, self.nbr_users]) + self.feature_init
+            self.svd_u = np.zeros([self.dimensionality, self.nbr_items]) + self.feature_init
+
+    # ---- development variants (gradient_descent.py:299-329, 472-503, 577-599) -------------------------
+    def feature_training2(self, initialize_model=True, verbose=False):
+        """One `estimator_subloop` call per epoch and a `predictor_subloop` per feature over a dense
+        users x items cache, the epoch control in Python (gradient_descent.py:299-329)."""
+        rmse, rmse_last = 2.0, 0.0
+        self._init_model(initialize_model)
+        ratings_cache = np.zeros(self.nbr_users * self.nbr_items, dtype=np.float64)
+        ratings_index, ratings = self.get_ratings()
+        for f in range(self.dimensionality):
+            epoch = 0
+            while epoch < self.min_epochs or rmse <= rmse_last - self.min_improvement:
+                rmse_last = rmse
+                rmse = gd_estimator.estimator_subloop(
+                    f, epoch, self.min_improvement, self.dimensionality, self.feature_init,
+                    self.learning_rate, self.K, self.svd_u, self.svd_v, ratings_index, ratings,
+                    ratings_cache, self.nbr_users, self.nbr_items, int(verbose))
+                epoch += 1
+            gd_estimator.predictor_subloop(f, epoch, self.dimensionality, self.feature_init, self.svd_u,
+                                           self.svd_v, ratings_index, ratings, ratings_cache,
+                                           self.nbr_users, self.nbr_items)
+
+    def feature_training_bias(self, initialize_model=True, handle_bias=False, verbose=False):
+        """Learned biases: `estimator_loop_with_learned_bias` started from the precomputed bias
+        statistics (gradient_descent.py:472-503); `handle_bias` is unused like in the reference."""
+        self._init_model(initialize_model)
+        ratings_index, ratings = self.get_ratings(randomize_order=True)
+        self.compute_overall_avg()
+        self.compute_items_bias_bk()
+        self.compute_users_bias_bk()
+        gd_estimator.estimator_loop_with_learned_bias(
+            self.min_epochs, self.max_epochs, self.min_improvement, self.dimensionality, self.feature_init,
+            self.learning_rate, self.learning_rate_users, self.learning_rate_items, self.K, self.K2,
+            self.overall_bias, self.svd_u, self.svd_v, ratings_index, ratings, self.items_bias,
+            self.users_bias, self.nbr_users, self.nbr_items, int(verbose))
+
+    def feature_training_dev(self, initialize_model=True, probe=None, verbose=False):
+        """`estimator_loop` with its per-epoch rmse history, which is returned
+        (gradient_descent.py:577-599)."""
+        rmse = np.zeros(self.max_epochs * self.dimensionality)
+        self._init_model(initialize_model)
+        ratings_index, ratings = self.get_ratings(randomize_order=True)
+        gd_estimator.estimator_loop(
+            self.min_epochs, self.max_epochs, self.min_improvement, self.dimensionality, self.feature_init,
+            self.learning_rate, self.K, self.svd_u, self.svd_v, ratings_index, ratings, 0, rmse,
+            self.nbr_users, self.nbr_items, int(verbose))
+        return rmse
 
     # ---- predictors (gradient_descent.py:621-648) ----------------------------------------------------
     def predict_rating(self, item_index, user_index):

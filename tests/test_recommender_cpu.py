@@ -112,3 +112,68 @@ def test_funk_dev_shims_validate_before_touching_the_device():
     with pytest.raises(NotImplementedError):
         gd.estimator_loop_with_implicit_feedback()
     assert np.all(u == 0.1) and np.all(v == 0.1)
+
+
+def test_gd_development_trainers_drive_the_native_loops_like_the_reference(monkeypatch):
+    """feature_training2 / feature_training_dev / feature_training_bias (gradient_descent.py:299-329,
+    577-599, 472-503): host control flow and argument mapping, with the CPU oracle standing in for
+    the device library (no GPU here)."""
+    from mfrec_b200.lib import gd_estimator
+    from mfrec_b200.recommendation import GDRecommender
+    from oracle import cpu
+    rng = np.random.default_rng(11)
+    nu, ni, n = 30, 20, 260
+    keys = rng.choice(nu * ni, n, replace=False)
+    idx = np.stack([keys // ni, keys % ni], axis=1).astype(np.int32)
+    r = rng.integers(1, 6, n).astype(np.float64)
+    params = {'nbr_features': 3, 'min_epochs': 2, 'max_epochs': 5, 'min_improvement': 0.001,
+              'learning_rate': 0.01, 'regularization_model': 0.02}
+
+    def make():
+        rec = GDRecommender(nu, ni, dict(params))
+        rec.set_ratings(idx, r)
+        return rec
+
+    # feature_training2: Python epoch loop over estimator_subloop + predictor_subloop == estimator_loop2
+    monkeypatch.setattr(gd_estimator, "estimator_subloop",
+                        lambda f, ep, mi, dim, fi, lr, K, u, v, ri, ra, cache, nbu, nbi, verbose=0:
+                        cpu.funk_subloop(f, dim, fi, lr, K, u, v, ri, ra, cache))
+    monkeypatch.setattr(gd_estimator, "predictor_subloop",
+                        lambda f, ep, dim, fi, u, v, ri, ra, cache, nbu, nbi:
+                        cpu.funk_predictor_subloop(f, dim, fi, u, v, ri, cache))
+    rec = make()
+    rec.feature_training2()
+    ri, ra = rec.get_ratings()
+    u = np.zeros((3, ni)) + 0.1
+    v = np.zeros((3, nu)) + 0.1
+    cpu.funk_loop_dev(2, -1, 0.001, 3, 0.1, 0.01, 0.02, u, v, ri, ra)
+    assert np.array_equal(rec.svd_u, u) and np.array_equal(rec.svd_v, v)
+
+    # feature_training_dev: estimator_loop with batch 0 and a max_epochs * dim history, returned
+    seen = {}
+
+    def fake_loop(mn, mx, mi, dim, fi, lr, K, u, v, ri, ra, batch, hist, nbu, nbi, verbose=0):
+        seen.update(batch=batch, hist_len=hist.shape[0], nbu=nbu, nbi=nbi)
+        cpu.funk_loop_dev(mn, mx, mi, dim, fi, lr, K, u, v, ri, ra, batch, hist)
+
+    monkeypatch.setattr(gd_estimator, "estimator_loop", fake_loop)
+    np.random.seed(5)
+    rec = make()
+    hist = rec.feature_training_dev()
+    assert seen == {"batch": 0, "hist_len": 5 * 3, "nbu": nu, "nbi": ni}
+    assert hist.shape == (15,) and (hist.reshape(3, 5)[:, :2] > 0).all()
+
+    # feature_training_bias: bias statistics first, then the learned-bias loop with K -> K_feature, K2 -> K_bias
+    def fake_lb(mn, mx, mi, dim, fi, lr, lru, lri, Kf, Kb, mu, u, v, ri, ra, ib, ub, nbu, nbi, verbose=0):
+        seen.update(Kf=Kf, Kb=Kb, mu=mu, ib0=ib.copy())
+        cpu.funk_learned_bias(mn, mi, dim, fi, lr, lru, lri, Kf, Kb, mu, u, v, ri, ra, ib, ub)
+
+    monkeypatch.setattr(gd_estimator, "estimator_loop_with_learned_bias", fake_lb)
+    from mfrec_b200 import _native
+    monkeypatch.setattr(_native, "bias_stats", lambda idx_, r_, ni_, nu_, K2=0.01, K3=0.01, ctx=None:
+                        cpu.bias_stats(idx_, r_, ni_, nu_, K2, K3))
+    np.random.seed(5)
+    rec = make()
+    rec.feature_training_bias()
+    assert seen["Kf"] == rec.K and seen["Kb"] == rec.K2 and abs(seen["mu"] - r.mean()) < 1e-12
+    assert seen["ib0"].any() and not np.array_equal(seen["ib0"], rec.items_bias)   # biases were learned in place
