@@ -283,6 +283,47 @@ int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_model *m, int 
                     double learning_rate, double K_users, double K_items, double K_bias,
                     int update_users, int update_items, int32_t slab, double *sq_err_out);
 
+/* ---- multi-GPU: DSGD ring --------------------------------------------
+ * `world` ranks = `world` user slices x `world` item slabs; rank r trains its own users (their
+ * ratings packed with opts.n_slabs = world and the GLOBAL item degrees, so every rank computes
+ * the same item partition) and in step t of an epoch holds slab (r + t) mod world.  One
+ * persistent launch per rank runs any number of epochs; a finished column block (<= 62 KB of Q
+ * rows) is written straight into the next rank's copy of Q through peer memory (NVLink) and its
+ * counter released at system scope -- no kernel boundary, staging copy or collective per step.
+ * The reference has no counterpart (single process, kmf_train.pyx:241-273 is the sequential
+ * semantics every schedule here is equivalent to).
+ *
+ * One process per GPU: create, exchange the 64-byte mfrec_ring_handle of every rank by any
+ * means (bench.py: torch.distributed.all_gather), mfrec_ring_connect.  One process driving
+ * several GPUs: mfrec_ring_connect_local(ring r, ring r-1).
+ * After the last epoch every rank has slab `rank` in hand: mfrec_ring_sync_model copies the
+ * ring's item side back into the model (the caller then gathers the slabs, e.g. ncclBroadcast). */
+typedef struct mfrec_ring mfrec_ring;
+int mfrec_ring_create(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_model *m, int rank, int world,
+                      mfrec_ring **out);
+void mfrec_ring_destroy(mfrec_ring *ring);
+/* handle64: 64 bytes (a cudaIpcMemHandle_t) naming this rank's item-side block. */
+int mfrec_ring_handle(mfrec_ring *ring, void *handle64);
+/* handles: [world][64] bytes, entry i from rank i's mfrec_ring_handle. */
+int mfrec_ring_connect(mfrec_ring *ring, const void *handles);
+/* Same process: `next` must be rank (ring.rank - 1) mod world (the rank that takes over every
+ * slab this one finishes); devices may be equal (tests) or peers. */
+int mfrec_ring_connect_local(mfrec_ring *ring, mfrec_ring *next);
+/* n_epochs epochs in ONE launch, asynchronous on the context stream.  sq_err_out: nullable
+ * DEVICE pointer to n_epochs doubles = this rank's sum of squared errors per epoch.
+ * A hand-over that does not arrive within MFREC_RING_TIMEOUT_MS (default 20000) aborts the
+ * launch: its error sums are NaN and mfrec_ring_wait reports MFREC_ERR_CUDA. */
+int mfrec_ring_epochs(mfrec_ring *ring, int kernel, double learning_rate, double K_users,
+                      double K_items, double K_bias, int n_epochs, double *sq_err_out);
+/* All `world` ranks on ONE device as a single cooperative launch (world * B CTAs): the
+ * schedule, counters and hand-over of the ring without a second GPU (tests).  sq_err_out:
+ * n_epochs doubles, summed over the ranks. */
+int mfrec_ring_epochs_one_device(mfrec_ring *const *rings, int world, int kernel,
+                                 double learning_rate, double K_users, double K_items,
+                                 double K_bias, int n_epochs, double *sq_err_out);
+int mfrec_ring_wait(mfrec_ring *ring);
+int mfrec_ring_sync_model(mfrec_ring *ring);
+
 /* Batched predict / RMSE on a resident model; pairs and outputs are DEVICE pointers when
  * is_device != 0.  out float64 [n] nullable; stats_out double[4] (host) nullable
  * = { sum err^2, sum |err|, sum err^2 of |err| (for var), n_valid } raw sums. */
@@ -290,6 +331,21 @@ int mfrec_model_predict(mfrec_ctx *ctx, const mfrec_model *m, int predictor,
                         const int32_t *pairs, const void *real, int real_is_f32, int64_t n,
                         int is_device, double mu, double min_rating, double max_rating,
                         double *out, double stats_out[4]);
+
+/* mfrec_topn / mfrec_topn_sweep on a RESIDENT model in identity layout (mfrec_model_create with
+ * layout == NULL): what MFRecommender keeps between calls, so that find_recommended_items
+ * (mf.py:144-193), similar_items and metrics.precision_recall (metrics.py:85-130, one
+ * find_recommended_items call per test user in the reference) do not upload the factor matrices
+ * again for every user. */
+int mfrec_model_topn(mfrec_ctx *ctx, const mfrec_model *m, int predictor, const int32_t *users,
+                     int32_t n_users, int32_t n_candidates, const int64_t *rated_indptr,
+                     const int32_t *rated_items, double mu, double min_rating, double max_rating,
+                     int32_t N, int32_t *out_items, double *out_scores, int32_t *out_counts);
+int mfrec_model_topn_sweep(mfrec_ctx *ctx, const mfrec_model *m, int predictor, const int32_t *users,
+                           int32_t n_users, int32_t n_candidates, const int64_t *rated_indptr,
+                           const int32_t *rated_items, double mu, double min_rating,
+                           double max_rating, int32_t N, int32_t *out_items, double *out_scores,
+                           int32_t *out_counts, double stats[8]);
 
 #ifdef __cplusplus
 }

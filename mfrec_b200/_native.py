@@ -38,6 +38,9 @@ EXPORTS = (
     "mfrec_ratings_quad_types", "mfrec_ratings_perm", "mfrec_ratings_order", "mfrec_ratings_offsets", "mfrec_ratings_packed",
     "mfrec_ratings_slab_items", "mfrec_model_create", "mfrec_model_read", "mfrec_model_destroy",
     "mfrec_model_device_ptrs", "mfrec_sgd_epoch", "mfrec_model_predict",
+    "mfrec_ring_create", "mfrec_ring_destroy", "mfrec_ring_handle", "mfrec_ring_connect",
+    "mfrec_ring_connect_local", "mfrec_ring_epochs", "mfrec_ring_epochs_one_device", "mfrec_ring_wait",
+    "mfrec_ring_sync_model", "mfrec_model_topn", "mfrec_model_topn_sweep",
 )
 
 
@@ -81,6 +84,8 @@ def lib():
             L.mfrec_ratings_destroy.argtypes = [C.c_void_p]
             L.mfrec_model_destroy.restype = None
             L.mfrec_model_destroy.argtypes = [C.c_void_p]
+            L.mfrec_ring_destroy.restype = None
+            L.mfrec_ring_destroy.argtypes = [C.c_void_p]
             _lib = L
     return _lib
 
@@ -435,16 +440,18 @@ class Ratings(object):
         _check(lib().mfrec_ratings_slab_items(self._h, C.c_int32(slab), C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def replay_order(self):
+    def replay_order(self, by_slab=False):
         """Input indices in one sequential order equivalent to the stratified schedule:
-        slab, sub-epoch, row block, phase, worker, bucket order (sgd.cu header)."""
+        slab, sub-epoch, row block, phase, worker, bucket order (sgd.cu header).  by_slab: a list
+        with one such array per slab (a DSGD rank visits the slabs in its own ring order)."""
         order = self.order()
         off, cnt = self.offsets()
         B, W, G = self.B, self.W, self.G
         off = off[:-1].reshape(G, B, B, W * W)
         cnt = cnt.reshape(G, B, B, W * W)
-        out = []
+        slabs = []
         for g in range(G):
+            out = []
             for s in range(B):
                 for rb in range(B):
                     cb = (rb + s) % B
@@ -453,7 +460,10 @@ class Ratings(object):
                             a, n = off[g, rb, cb, w * W + ph], cnt[g, rb, cb, w * W + ph]
                             if n:
                                 out.append(order[a:a + n])
-        return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+            slabs.append(np.concatenate(out) if out else np.zeros(0, dtype=np.int64))
+        if by_slab:
+            return slabs
+        return np.concatenate(slabs) if slabs else np.zeros(0, dtype=np.int64)
 
 
 class Model(object):
@@ -527,3 +537,110 @@ class Model(object):
             C.c_int(0), C.c_int64(pairs.shape[0]), C.c_int(0), C.c_double(mu),
             C.c_double(min_rating), C.c_double(max_rating), _ptr(out), _ptr(stats)), self.ctx.handle)
         return out, stats
+
+
+def _model_topn(self, predictor, users, n_candidates, rated_indptr, rated_items, N, mu=0.0, min_rating=1.0,
+                max_rating=5.0, sweep=False, out=None):
+    """Top-N on this RESIDENT model (identity layout): nothing but the user list, the rated-item
+    CSR and the results cross PCIe.  sweep=True: the tensor-core path for many users.  Returns
+    (items, scores, counts[, stats])."""
+    if users is None:
+        users = np.arange(self.nu, dtype=np.int32)
+    users = _as(users, np.int32).reshape(-1)
+    indptr = _as(rated_indptr, np.int64)
+    rated = _as(rated_items, np.int32)
+    n_users = users.shape[0]
+    if out is None:
+        items = np.full((n_users, N), -1, dtype=np.int32)
+        scores = np.zeros((n_users, N), dtype=np.float64)
+        counts = np.zeros(n_users, dtype=np.int32)
+    else:
+        items, scores, counts = out
+    if sweep:
+        stats = np.zeros(8, dtype=np.float64)
+        _check(lib().mfrec_model_topn_sweep(
+            self.ctx.handle, self._h, C.c_int(PREDICTORS[predictor]), _ptr(users), C.c_int32(n_users),
+            C.c_int32(n_candidates), _ptr(indptr), _ptr(rated), C.c_double(mu), C.c_double(min_rating),
+            C.c_double(max_rating), C.c_int32(N), _ptr(items), _ptr(scores), _ptr(counts), _ptr(stats)),
+            self.ctx.handle)
+        return items, scores, counts, stats
+    _check(lib().mfrec_model_topn(
+        self.ctx.handle, self._h, C.c_int(PREDICTORS[predictor]), _ptr(users), C.c_int32(n_users),
+        C.c_int32(n_candidates), _ptr(indptr), _ptr(rated), C.c_double(mu), C.c_double(min_rating),
+        C.c_double(max_rating), C.c_int32(N), _ptr(items), _ptr(scores), _ptr(counts)), self.ctx.handle)
+    return items, scores, counts
+
+
+Model.topn = _model_topn
+
+
+def array_fingerprint(a):
+    """Cheap identity of a numpy array's CONTENTS for cache invalidation: address, shape and a
+    hash of ~4k strided samples (a full checksum of a 0.5 GB factor matrix would cost more than
+    the call it guards).  In-place edits of single elements between the samples go unnoticed:
+    code that pokes the arrays directly calls ``invalidate_model()``."""
+    if a is None:
+        return None
+    flat = a.reshape(-1)
+    step = max(1, flat.shape[0] // 4096)
+    return (a.ctypes.data, a.shape, a.dtype.str, hash(flat[::step].tobytes()))
+
+
+class PeerRing(object):
+    """One rank of the DSGD ring (``mfrec_ring``): persistent launches that hand finished column
+    blocks to the next rank through peer memory."""
+
+    def __init__(self, ratings, model, rank, world, ctx=None):
+        self.ctx = ctx or ratings.ctx
+        self.ratings, self.model = ratings, model     # keep them alive: the ring borrows both
+        self.rank, self.world = int(rank), int(world)
+        self._h = C.c_void_p()
+        _check(lib().mfrec_ring_create(self.ctx.handle, ratings.handle, model.handle, C.c_int(self.rank),
+                                       C.c_int(self.world), C.byref(self._h)), self.ctx.handle)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mfrec_ring_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def export_handle(self):
+        """64 bytes naming this rank's item-side block (a cudaIpcMemHandle_t)."""
+        buf = (C.c_ubyte * 64)()
+        _check(lib().mfrec_ring_handle(self._h, buf), self.ctx.handle)
+        return bytes(buf)
+
+    def connect(self, handles):
+        """handles: list of ``world`` 64-byte strings, entry i exported by rank i."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        _check(lib().mfrec_ring_connect(self._h, C.c_char_p(blob)), self.ctx.handle)
+
+    def connect_local(self, next_ring):
+        _check(lib().mfrec_ring_connect_local(self._h, next_ring.handle), self.ctx.handle)
+
+    def epochs(self, kernel, lr, K_users, K_items, K_bias, n_epochs=1, sq_err_ptr=0):
+        """Asynchronous; sq_err_ptr: device pointer to n_epochs doubles (or 0)."""
+        _check(lib().mfrec_ring_epochs(
+            self._h, C.c_int(kernel), C.c_double(lr), C.c_double(K_users), C.c_double(K_items),
+            C.c_double(K_bias), C.c_int(int(n_epochs)), C.c_void_p(int(sq_err_ptr) or None)), self.ctx.handle)
+
+    def wait(self):
+        _check(lib().mfrec_ring_wait(self._h), self.ctx.handle)
+
+    def sync_model(self):
+        _check(lib().mfrec_ring_sync_model(self._h), self.ctx.handle)
+
+
+def ring_epochs_one_device(rings, kernel, lr, K_users, K_items, K_bias, n_epochs=1, sq_err_ptr=0):
+    """All ranks of a ring that live on ONE device, as a single cooperative launch (tests)."""
+    arr = (C.c_void_p * len(rings))(*[r.handle for r in rings])
+    ctx = rings[0].ctx
+    _check(lib().mfrec_ring_epochs_one_device(
+        arr, C.c_int(len(rings)), C.c_int(kernel), C.c_double(lr), C.c_double(K_users), C.c_double(K_items),
+        C.c_double(K_bias), C.c_int(int(n_epochs)), C.c_void_p(int(sq_err_ptr) or None)), ctx.handle)

@@ -201,6 +201,13 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // sgd.cu
 size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W);
 
+// topn.cu: the exact top-N on a resident model (M may be NULL only when nothing is scored; ni / nu are
+// read only then)
+int mfrec_topn_on_model(mfrec_ctx *ctx, const mfrec_model *M, int predictor, const int32_t *users, int32_t n_users,
+                     int32_t n_candidates, const int64_t *rated_indptr, const int32_t *rated_items, double mu,
+                     double min_rating, double max_rating, int32_t N, int32_t *out_items, double *out_scores,
+                     int32_t *out_counts, int32_t ni, int32_t nu);
+
 // runtime.cu
 // Host <-> device copies of caller-owned arrays.  Page-locked memory goes straight to
 // cudaMemcpyAsync; a large PAGEABLE array is staged through pinned bounce buffers by four host

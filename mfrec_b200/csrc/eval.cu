@@ -7,7 +7,10 @@
 //   GDRecommender.predict_rating[_with_bias]  gradient_descent.py:621-648
 //   KMFRecommender.predict_{logistic,linear,linear_neg}  kmf.py:79-103
 //   compute_overall_avg base.py:504-508, compute_{items,users}_bias_bk mf.py:78-121
+#include <algorithm>
 #include <cmath>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -135,36 +138,94 @@ __global__ void sum_ratings_kernel(const double *__restrict__ r, int64_t nnz, do
     if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
 }
 
-__global__ void item_bias_acc_kernel(const int32_t *__restrict__ idx, const double *__restrict__ r,
-                                     int64_t nnz, double mu, int32_t ni, int32_t nu,
-                                     double *__restrict__ acc_i, int32_t *__restrict__ cnt_i,
-                                     int32_t *__restrict__ bad)
+// Deterministic segmented sums (no floating-point atomics: the result must not depend on
+// scheduling -- SURVEY T7 asks for run-to-run identical results for a fixed seed).  Ratings are
+// stably sorted by segment id (item, then user), so each segment's terms sit in input order;
+// one warp sums a segment with a fixed lane-strided order and a shuffle tree.
+__global__ void seg_key_kernel(const int32_t *__restrict__ idx, int64_t nnz, int which, int32_t ni, int32_t nu,
+                               uint32_t *__restrict__ keys, uint32_t *__restrict__ pos,
+                               int32_t *__restrict__ cnt, int32_t *__restrict__ bad)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnz; n += stride) {
         const int2 ui = reinterpret_cast<const int2 *>(idx)[n];
-        if (ui.x < 0 || ui.x >= nu || ui.y < 0 || ui.y >= ni) { atomicOr(bad, 1); continue; }
-        atomicAdd(&acc_i[ui.y], r[n] - mu);
-        atomicAdd(&cnt_i[ui.y], 1);
+        if (ui.x < 0 || ui.x >= nu || ui.y < 0 || ui.y >= ni) {
+            atomicOr(bad, 1);
+            keys[n] = 0;
+            pos[n] = (uint32_t)n;
+            continue;
+        }
+        const int32_t key = which ? ui.x : ui.y;
+        keys[n] = (uint32_t)key;
+        pos[n] = (uint32_t)n;
+        atomicAdd(&cnt[key], 1);   // integer: exact whatever the order
     }
 }
 
-__global__ void finish_bias_kernel(double *__restrict__ acc, const int32_t *__restrict__ cnt, int32_t n, double K)
+__global__ void __launch_bounds__(256)
+seg_bias_kernel(const uint32_t *__restrict__ pos_sorted, const int64_t *__restrict__ seg_off, int32_t n_seg,
+                const int32_t *__restrict__ idx, const double *__restrict__ r, double mu,
+                const double *__restrict__ bias_i,   // null: item pass (terms r - mu); else user pass (r - mu - b_i)
+                double K, double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= n_seg) return;
+    const int64_t a = seg_off[warp], b = seg_off[warp + 1];
+    double acc = 0.0;
+    for (int64_t j = a + lane; j < b; j += 32) {
+        const uint32_t n = pos_sorted[j];
+        double t = r[n] - mu;
+        if (bias_i) t -= bias_i[idx[2 * (int64_t)n + 1]];
+        acc += t;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[warp] = b > a ? acc / (K + (double)(b - a)) : 0.0;
+}
+
+__global__ void cnt_to_i64_kernel(const int32_t *__restrict__ cnt, int32_t n, int64_t *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) acc[i] = cnt[i] > 0 ? acc[i] / (K + (double)cnt[i]) : 0.0;
+    if (i <= n) out[i] = i < n ? cnt[i] : 0;
 }
 
-__global__ void user_bias_acc_kernel(const int32_t *__restrict__ idx, const double *__restrict__ r,
-                                     int64_t nnz, double mu, const double *__restrict__ bias_i,
-                                     double *__restrict__ acc_u, int32_t *__restrict__ cnt_u)
+// bias[seg] = sum over the segment's ratings of (r - mu [- b_i]) / (K + count), segments = items
+// (which = 0) or users (which = 1)
+int segmented_bias(mfrec_ctx *ctx, const int32_t *d_idx, const double *d_r, int64_t nnz, int32_t ni, int32_t nu,
+                   int which, double mu, const double *bias_i, double K, double *d_out, int32_t *d_bad)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnz; n += stride) {
-        const int2 ui = reinterpret_cast<const int2 *>(idx)[n];
-        atomicAdd(&acc_u[ui.x], r[n] - mu - bias_i[ui.y]);
-        atomicAdd(&cnt_u[ui.x], 1);
-    }
+    cudaStream_t st = ctx->stream;
+    const int32_t n_seg = which ? nu : ni;
+    const int grid = ctx->sm_count * 8;
+    DevBuf<uint32_t> ka, kb, va, vb;
+    DevBuf<int32_t> cnt;
+    DevBuf<int64_t> cnt64, off;
+    MF_CUDA(ctx, ka.alloc(nnz, st)); MF_CUDA(ctx, kb.alloc(nnz, st));
+    MF_CUDA(ctx, va.alloc(nnz, st)); MF_CUDA(ctx, vb.alloc(nnz, st));
+    MF_CUDA(ctx, cnt.alloc((size_t)n_seg + 1, st));
+    MF_CUDA(ctx, cnt64.alloc((size_t)n_seg + 1, st));
+    MF_CUDA(ctx, off.alloc((size_t)n_seg + 1, st));
+    MF_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, ((size_t)n_seg + 1) * 4, st));
+    seg_key_kernel<<<grid, 256, 0, st>>>(d_idx, nnz, which, ni, nu, ka.p, va.p, cnt.p, d_bad);
+    MF_LAUNCH_CHECK(ctx);
+    int bits = 1;
+    while ((1ll << bits) < n_seg) ++bits;
+    cub::DoubleBuffer<uint32_t> dk(ka.p, kb.p), dv(va.p, vb.p);
+    size_t tmp_bytes = 0, tmp2 = 0;
+    MF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, nnz, 0, bits, st));
+    MF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp2, cnt64.p, off.p, n_seg + 1, st));
+    DevBuf<char> tmp;
+    MF_CUDA(ctx, tmp.alloc(std::max(tmp_bytes, tmp2), st));
+    MF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, nnz, 0, bits, st));   // stable (LSD)
+    cnt_to_i64_kernel<<<(n_seg + 256) / 256, 256, 0, st>>>(cnt.p, n_seg, cnt64.p);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp2, cnt64.p, off.p, n_seg + 1, st));
+    ctx->launches += (bits + 7) / 8 * 2 + 3;
+    seg_bias_kernel<<<(unsigned)ceil_div64((int64_t)n_seg * 32, 256), 256, 0, st>>>(dv.Current(), off.p, n_seg, d_idx,
+                                                                                   d_r, mu, bias_i, K, d_out);
+    MF_LAUNCH_CHECK(ctx);
+    MF_CUDA(ctx, cudaStreamSynchronize(st));   // scratch goes back to the pool on return
+    return MFREC_OK;
 }
 
 }  // namespace
@@ -247,6 +308,68 @@ extern "C" int mfrec_model_predict(mfrec_ctx *ctx, const mfrec_model *m, int pre
     return MFREC_OK;
 }
 
+namespace {
+
+// A call that scores a handful of pairs (metrics.test_predict_rating's default is nbr_samples = 10)
+// must not upload both factor matrices (0.5 GB at Netflix shape): gather the rows the pairs name
+// into compact [k][m] arrays on the host and build a model of just those.
+constexpr int64_t kSmallPairs = 4096;
+
+struct CompactModel {
+    std::vector<double> u, v, ib, ub;
+    std::vector<int32_t> pairs;   // remapped to compact ids
+    int32_t mi = 0, mu = 0;
+};
+
+// false: out of range index (the caller lets the full path report it)
+bool gather_small(int k, const double *u, const double *v, int32_t ni, int32_t nu, const int32_t *pairs, int64_t n,
+                  const double *items_bias, const double *users_bias, CompactModel &c)
+{
+    std::vector<int32_t> us(n), is(n);
+    for (int64_t j = 0; j < n; ++j) {
+        us[j] = pairs[2 * j];
+        is[j] = pairs[2 * j + 1];
+        if (us[j] < 0 || us[j] >= nu || is[j] < 0 || is[j] >= ni) return false;
+    }
+    std::vector<int32_t> uu(us), ii(is);
+    std::sort(uu.begin(), uu.end());
+    uu.erase(std::unique(uu.begin(), uu.end()), uu.end());
+    std::sort(ii.begin(), ii.end());
+    ii.erase(std::unique(ii.begin(), ii.end()), ii.end());
+    c.mu = (int32_t)uu.size();
+    c.mi = (int32_t)ii.size();
+    c.u.resize((size_t)k * c.mi);
+    c.v.resize((size_t)k * c.mu);
+    for (int f = 0; f < k; ++f) {
+        for (int32_t a = 0; a < c.mi; ++a) c.u[(size_t)f * c.mi + a] = u[(size_t)f * ni + ii[a]];
+        for (int32_t a = 0; a < c.mu; ++a) c.v[(size_t)f * c.mu + a] = v[(size_t)f * nu + uu[a]];
+    }
+    if (items_bias) { c.ib.resize(c.mi); for (int32_t a = 0; a < c.mi; ++a) c.ib[a] = items_bias[ii[a]]; }
+    if (users_bias) { c.ub.resize(c.mu); for (int32_t a = 0; a < c.mu; ++a) c.ub[a] = users_bias[uu[a]]; }
+    c.pairs.resize((size_t)2 * n);
+    for (int64_t j = 0; j < n; ++j) {
+        c.pairs[2 * j] = (int32_t)(std::lower_bound(uu.begin(), uu.end(), us[j]) - uu.begin());
+        c.pairs[2 * j + 1] = (int32_t)(std::lower_bound(ii.begin(), ii.end(), is[j]) - ii.begin());
+    }
+    return true;
+}
+
+// model for a one-shot call: compact when the pairs are few, the whole matrices otherwise
+int model_for_pairs(mfrec_ctx *ctx, int k, const double *u, const double *v, int32_t ni, int32_t nu,
+                    const int32_t *&pairs, int64_t n, const double *items_bias, const double *users_bias,
+                    CompactModel &c, mfrec_model **M)
+{
+    if (n > 0 && n <= kSmallPairs && (int64_t)ni + nu > 8 * n && pairs &&
+        gather_small(k, u, v, ni, nu, pairs, n, items_bias, users_bias, c)) {
+        pairs = c.pairs.data();
+        return mfrec_model_create(ctx, nullptr, k, c.mi, c.mu, c.u.data(), c.v.data(),
+                                  items_bias ? c.ib.data() : nullptr, users_bias ? c.ub.data() : nullptr, M);
+    }
+    return mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, M);
+}
+
+}  // namespace
+
 extern "C" int mfrec_predict_pairs(mfrec_ctx *ctx, int predictor, int k, const double *u, const double *v,
                                    int32_t ni, int32_t nu, const int32_t *pairs, int64_t n, double mu,
                                    const double *items_bias, const double *users_bias,
@@ -254,7 +377,8 @@ extern "C" int mfrec_predict_pairs(mfrec_ctx *ctx, int predictor, int k, const d
 {
     if (!ctx || !u || !v || !out) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_predict_pairs: NULL argument");
     mfrec_model *M = nullptr;
-    MF_TRY(mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, &M));
+    CompactModel compact;
+    MF_TRY(model_for_pairs(ctx, k, u, v, ni, nu, pairs, n, items_bias, users_bias, compact, &M));
     const int rc = mfrec_model_predict(ctx, M, predictor, pairs, nullptr, 0, n, 0, mu, min_rating, max_rating, out, nullptr);
     mfrec_model_destroy(M);
     return rc;
@@ -268,7 +392,8 @@ extern "C" int mfrec_rmse_pairs(mfrec_ctx *ctx, int predictor, int k, const doub
     if (!ctx || !u || !v || !stats || (n > 0 && !real))
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_rmse_pairs: NULL argument");
     mfrec_model *M = nullptr;
-    MF_TRY(mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, &M));
+    CompactModel compact;
+    MF_TRY(model_for_pairs(ctx, k, u, v, ni, nu, pairs, n, items_bias, users_bias, compact, &M));
     double raw[4] = {0, 0, 0, 0};
     const int rc = mfrec_model_predict(ctx, M, predictor, pairs, real, 0, n, 0, mu, min_rating, max_rating,
                                        errors_out, raw);
@@ -299,26 +424,22 @@ extern "C" int mfrec_bias_stats(mfrec_ctx *ctx, const int32_t *ratings_index, co
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_bias_stats: bad argument");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    if (nnz >= (1ll << 32)) return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_bias_stats: nnz >= 2^32");
     if (nnz == 0) {
         *mu_out = NAN;
         for (int32_t i = 0; i < ni; ++i) items_bias[i] = 0.0;
         for (int32_t j = 0; j < nu; ++j) users_bias[j] = 0.0;
         return MFREC_OK;
     }
-    DevBuf<int32_t> d_idx, cnt_i, cnt_u, bad;
+    DevBuf<int32_t> d_idx, bad;
     DevBuf<double> d_r, acc_i, acc_u, part;
     const int grid = ctx->sm_count * 8;
     MF_CUDA(ctx, d_idx.alloc((size_t)nnz * 2, ctx->stream));
     MF_CUDA(ctx, d_r.alloc((size_t)nnz, ctx->stream));
-    MF_CUDA(ctx, cnt_i.alloc(ni)); MF_CUDA(ctx, cnt_u.alloc(nu, ctx->stream));
-    MF_CUDA(ctx, acc_i.alloc(ni)); MF_CUDA(ctx, acc_u.alloc(nu, ctx->stream));
-    MF_CUDA(ctx, part.alloc(grid)); MF_CUDA(ctx, bad.alloc(1, ctx->stream));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_idx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(d_r.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-    MF_CUDA(ctx, cudaMemsetAsync(cnt_i.p, 0, (size_t)ni * 4, st));
-    MF_CUDA(ctx, cudaMemsetAsync(cnt_u.p, 0, (size_t)nu * 4, st));
-    MF_CUDA(ctx, cudaMemsetAsync(acc_i.p, 0, (size_t)ni * 8, st));
-    MF_CUDA(ctx, cudaMemsetAsync(acc_u.p, 0, (size_t)nu * 8, st));
+    MF_CUDA(ctx, acc_i.alloc(ni, ctx->stream)); MF_CUDA(ctx, acc_u.alloc(nu, ctx->stream));
+    MF_CUDA(ctx, part.alloc(grid, ctx->stream)); MF_CUDA(ctx, bad.alloc(1, ctx->stream));
+    MF_TRY(mfrec_copy_h2d(ctx, d_idx.p, ratings_index, (size_t)nnz * 8, st));
+    MF_TRY(mfrec_copy_h2d(ctx, d_r.p, ratings, (size_t)nnz * 8, st));
     MF_CUDA(ctx, cudaMemsetAsync(bad.p, 0, 4, st));
     sum_ratings_kernel<<<grid, 256, 0, st>>>(d_r.p, nnz, part.p);
     MF_LAUNCH_CHECK(ctx);
@@ -326,20 +447,14 @@ extern "C" int mfrec_bias_stats(mfrec_ctx *ctx, const int32_t *ratings_index, co
     MF_CUDA(ctx, cudaMemcpyAsync(h_part.data(), part.p, (size_t)grid * 8, cudaMemcpyDeviceToHost, st));
     MF_CUDA(ctx, cudaStreamSynchronize(st));
     double tot = 0.0;
-    for (double x : h_part) tot += x;
+    for (double x : h_part) tot += x;   // fixed grid, fixed order
     const double mu = tot / (double)nnz;
-    item_bias_acc_kernel<<<grid, 256, 0, st>>>(d_idx.p, d_r.p, nnz, mu, ni, nu, acc_i.p, cnt_i.p, bad.p);
-    MF_LAUNCH_CHECK(ctx);
+    MF_TRY(segmented_bias(ctx, d_idx.p, d_r.p, nnz, ni, nu, 0, mu, nullptr, K3, acc_i.p, bad.p));
     int32_t h_bad = 0;
     MF_CUDA(ctx, cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
     MF_CUDA(ctx, cudaStreamSynchronize(st));
     if (h_bad) return mfrec_set_error(ctx, MFREC_ERR_INDEX, "mfrec_bias_stats: index out of range");
-    finish_bias_kernel<<<(ni + 255) / 256, 256, 0, st>>>(acc_i.p, cnt_i.p, ni, K3);
-    MF_LAUNCH_CHECK(ctx);
-    user_bias_acc_kernel<<<grid, 256, 0, st>>>(d_idx.p, d_r.p, nnz, mu, acc_i.p, acc_u.p, cnt_u.p);
-    MF_LAUNCH_CHECK(ctx);
-    finish_bias_kernel<<<(nu + 255) / 256, 256, 0, st>>>(acc_u.p, cnt_u.p, nu, K2);
-    MF_LAUNCH_CHECK(ctx);
+    MF_TRY(segmented_bias(ctx, d_idx.p, d_r.p, nnz, ni, nu, 1, mu, acc_i.p, K2, acc_u.p, bad.p));
     MF_CUDA(ctx, cudaMemcpyAsync(items_bias, acc_i.p, (size_t)ni * 8, cudaMemcpyDeviceToHost, st));
     MF_CUDA(ctx, cudaMemcpyAsync(users_bias, acc_u.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, st));
     MF_CUDA(ctx, cudaStreamSynchronize(st));

@@ -327,13 +327,24 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     // better to keep one CTA on every SM with fewer warps than full CTAs on some of the SMs.
     int W = (opts && opts->workers > 0) ? opts->workers : 0;
     int B = (opts && opts->row_blocks > 0) ? opts->row_blocks : 0;
-    const double want_p = sqrt((double)nnz / G / 40.0);
+    // A DSGD rank (item_degree given) holds one user slice of the matrix, and every rank of the
+    // ring must arrive at the SAME B and W (they exchange Q rows by packed position): plan with the
+    // average slice, total ratings / G, which every rank computes from the global degrees, not with
+    // this rank's own count.  (dsgd.check_layout_agreement verifies the outcome.)
+    double nnz_plan = (double)nnz;
+    if (item_degree && G > 1) {
+        double tot = 0.0;
+        for (int32_t i = 0; i < ni; ++i) tot += (double)item_degree[i];
+        nnz_plan = tot / G;
+    }
+    const double want_p = sqrt(nnz_plan / G / 40.0);
     if (W == 0) {
         W = B > 0 ? (int)lround(want_p / B) : (int)lround(want_p / ctx->sm_count);
         W = std::max(4, std::min(W, 8));
     }
     if (W > 16) W = 16;  // the SGD kernel is built for at most 16 warps per CTA
     if (B == 0) B = std::max(1, std::min((int)(want_p / W), ctx->sm_count));
+    // (a slice with fewer users than B * W only arises in toy cases; ring callers then pass row_blocks)
     B = (int)std::max<int64_t>(1, std::min<int64_t>(B, std::min<int64_t>(nu, ni / G) / W));
     const uint64_t seed = opts ? opts->seed : 0;
     const bool keep_order = opts && opts->keep_order;

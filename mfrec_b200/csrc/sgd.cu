@@ -35,6 +35,7 @@
 // Sequential schedule (MFREC_SCHED_SEQUENTIAL): one thread, fp64, no FMA contraction, the
 // reference's exact order on the reference's own [k][n] layout.  Bit-exact with the reference
 // for the linear kernel; used for verification and for tiny fold-in calls.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -57,21 +58,40 @@ constexpr int kRing = kChunk * kStages;
 static_assert(kChunk % 4 == 0, "chunks must be 16-byte multiples");
 static_assert(4 * kDepth <= kChunk, "the prefetch cursor may run at most one chunk ahead");
 
-struct SgdParams {
+// Per-rank arguments.  One per launch on a real device; the ring test on ONE device passes one per
+// emulated rank (CTA group g = blockIdx.x / B acts as rank g, see mfrec_ring_epochs).
+struct SgdRank {
     const PackedRating *packed;
     const int64_t *bucket_off;
     const int32_t *col_start;
-    float *Q, *ib, *P, *ub;
-    double *se_part;  // [B] per-CTA sums of this launch
-    int32_t *ticks;   // [B] sub-epochs finished on each column block in this launch, or null
-                      // (null: no hand-over, the launch must cover exactly one sub-epoch)
-    int B, W, slab, s_begin, s_end;
-    int tile_rows;    // shared-memory rows reserved for the Q tile
+    float *Q, *ib, *P, *ub;   // Q / ib: this rank's copy of the item side (all slabs; only the slab in hand is current)
+    double *se_part;          // [epochs of the launch][B] per-CTA sums of squared errors
+    int32_t *ticks;           // [G*B] uses completed on each column block as seen by this rank, or null
+                              // (null: no hand-over, the launch must cover exactly one sub-epoch)
+    // ring (world > 1): where the LAST sub-epoch of a step leaves a column block -- the copy of the
+    // rank that works on this slab next -- and that rank's counters
+    float *peer_Q, *peer_ib;
+    int32_t *peer_ticks;
+    int32_t *abort;           // [1] != 0: a hand-over wait timed out somewhere, give up
+    int rank;
+};
+
+struct SgdParams {
+    SgdRank self;             // the arguments when ranks == null
+    const SgdRank *ranks;     // device array, one per CTA group of B (ring launches only)
+    // Iterations [it_begin, it_end) of the flattened (epoch, step, sub-epoch) space:
+    //   it = (epoch * G + step) * B + s,   slab of a step = (rank + step) mod G
+    int64_t it_begin, it_end;
+    int64_t e_base;           // epoch whose sums go to se_part[0 .. B)
+    int se_stride;            // doubles between two epochs' sums in se_part (B, or ranks * B in the ring test)
+    int B, W, G, world;       // world > 1: slabs move around a ring of `world` = G ranks
+    int tile_rows;            // shared-memory rows reserved for the Q tile
     float lr, Ku, Ki, Kb;
     int update_users, update_items;
     float fx_scale, fx_inv;       // fixed-point scale of the warp reduction (power of two)
     unsigned long long *timing;   // debug (MFREC_SGD_TIMING=1): [B][W][8] cycle counters, or null
     int exp;                      // debug (MFREC_SGD_EXP, timing build only): knock-out experiments, results are WRONG
+    unsigned long long wait_ns;   // ring: give up a hand-over wait after this long (0 = never)
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) + cp.async ------------
@@ -245,6 +265,23 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// system scope: the counter (and the data it guards) was written by / is read by another GPU
+__device__ __forceinline__ int ld_acquire_sys(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ------------------------------------------------------------------------------------------
 // The stratified kernel.  grid = B CTAs (one per SM, cooperative launch), block = W warps,
@@ -279,8 +316,9 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int v)
 // takes the generic path, which picks each row's source (registers / prefetch ring / global
 // memory) with warp-uniform branches.
 // ------------------------------------------------------------------------------------------
-template <int E, int KERNEL, bool TIMING, int MAXT, bool GATED>   // MAXT: 256 (W <= 8: 255 registers per thread) or 512;
-                                                                    // GATED: honour update_users / update_items (else both on)
+template <int E, int KERNEL, bool TIMING, int MAXT, bool GATED, bool RING>
+// MAXT: 256 (W <= 8: 255 registers per thread) or 512; GATED: honour update_users / update_items
+// (else both on); RING: slabs move between ranks (DSGD), counters and hand-over at system scope
 __global__ void __launch_bounds__(MAXT, 1)
 sgd_block_kernel(const SgdParams prm)
 {
@@ -289,7 +327,10 @@ sgd_block_kernel(const SgdParams prm)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = prm.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rb = blockIdx.x;
+    const int rb = RING ? (int)(blockIdx.x % (unsigned)prm.B) : (int)blockIdx.x;
+    // (RING = false: every R.x below is a load from the kernel's parameter bank)
+    const SgdRank R = RING ? prm.ranks[blockIdx.x / (unsigned)prm.B] : prm.self;
+    __shared__ int abort_s;
 
     // shared-memory carve-up (every section is a multiple of 16 bytes)
     float *Qs = reinterpret_cast<float *>(smem_raw);
@@ -312,6 +353,7 @@ sgd_block_kernel(const SgdParams prm)
         mbar_init(tile_bar, 1);
         for (int i = 0; i < kStages * W; ++i) mbar_init(bars + 1 + i, 1);
         for (int i = 0; i < W; ++i) phase_done[i] = 0;
+        abort_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -325,10 +367,13 @@ sgd_block_kernel(const SgdParams prm)
     const bool upd_bu = (KERNEL == MFREC_KERNEL_LINEAR) || upd_u;
     const bool upd_bi = (KERNEL == MFREC_KERNEL_LINEAR) || upd_i;
     const float fx_scale = prm.fx_scale, fx_inv = prm.fx_inv;
-    float *const P_lane = prm.P + lane * Frag<E>::V;   // this lane's column of every P row
+    float *const P_lane = R.P + lane * Frag<E>::V;   // this lane's column of every P row
+    float *const ub_g = R.ub;
+    const int64_t steps_per_epoch = (int64_t)prm.G * prm.B;
 
     double se = 0.0;          // fp64 total of fp32 per-bucket partials, over the whole launch
     uint32_t chunk_seq = 0;   // chunks this warp has pulled so far (ring stage + mbarrier parity)
+    uint32_t tile_seq = 0;    // Q tiles this CTA has pulled so far (mbarrier parity)
     bool chunks_issued = false;   // the first chunks of the coming sub-epoch are already on their way
     // opt-in section timer (cycles per warp): 0 bookkeeping + prefetch issue, 1 cp.async wait,
     // 2 quad load, 3 updates, 4 phase hand-over wait, 5 sub-epoch set-up (ticket + tile), 6 tail
@@ -343,40 +388,71 @@ sgd_block_kernel(const SgdParams prm)
         }
     };
 
-    for (int s = prm.s_begin; s < prm.s_end; ++s) {
-        const int step = s - prm.s_begin;
+    for (int64_t it = prm.it_begin; it < prm.it_end; ++it) {
+        const int step = (int)(it - prm.it_begin);
+        // it = (epoch * G + slab step) * B + sub-epoch; the slab of a step is (rank + step) mod G
+        const int64_t epoch = it / steps_per_epoch;
+        const int in_epoch = (int)(it - epoch * steps_per_epoch);
+        const int s = in_epoch % prm.B;
+        const int slab = (R.rank + in_epoch / prm.B) % prm.G;
         const int cbl = (rb + s) % prm.B;
-        const int cbg = prm.slab * prm.B + cbl;
-        const int cs = prm.col_start[cbg * W];
-        const int nq = prm.col_start[(cbg + 1) * W] - cs;
+        const int cbg = slab * prm.B + cbl;
+        const int cs = R.col_start[cbg * W];
+        const int nq = R.col_start[(cbg + 1) * W] - cs;
+        // uses of this column block that must be complete before this one: around a ring it is used
+        // in every step of every epoch (by one rank after the other), on one device once per epoch
+        const int tick_need = RING ? (int)it : (int)(epoch - prm.e_base) * prm.B + s;
 
         // this CTA's W*W bucket descriptors (worker-major: index w * W + phase) + end sentinel
-        const int64_t bucket_base = (((int64_t)prm.slab * prm.B + rb) * prm.B + cbl) * W * W;
-        for (int i = threadIdx.x; i <= W * W; i += blockDim.x) boff[i] = prm.bucket_off[bucket_base + i];
+        const int64_t bucket_base = (((int64_t)slab * prm.B + rb) * prm.B + cbl) * W * W;
+        for (int i = threadIdx.x; i <= W * W; i += blockDim.x) boff[i] = R.bucket_off[bucket_base + i];
         // Q tile: one elected thread takes the column block over and issues the bulk copies
         if (threadIdx.x == 0) {
-            if (prm.ticks) {
-                while (ld_acquire_gpu(prm.ticks + cbl) < s) __nanosleep(64);
+            if (R.ticks) {
+                if constexpr (RING) {
+                    // the previous user may be another GPU (it pushed the block into this rank's
+                    // copy of Q and then released the counter at system scope)
+                    const unsigned long long t0 = global_ns();
+                    uint32_t polls = 0;
+                    while (ld_acquire_sys(R.ticks + cbg) < tick_need) {
+                        __nanosleep(128);
+                        if ((++polls & 1023u) == 0) {
+                            if (*(volatile int32_t *)R.abort) { abort_s = 1; break; }
+                            if (prm.wait_ns && global_ns() - t0 > prm.wait_ns) {
+                                *(volatile int32_t *)R.abort = 1;
+                                abort_s = 1;
+                                break;
+                            }
+                        }
+                    }
+                } else {
+                    while (ld_acquire_gpu(R.ticks + cbg) < tick_need) __nanosleep(64);
+                }
                 // order the acquire (generic proxy) before the bulk reads (async proxy)
                 asm volatile("fence.proxy.async;" ::: "memory");
             }
-            if (nq > 0) {
+            bool go = nq > 0;
+            if constexpr (RING) go = go && !abort_s;
+            if (go) {
                 const uint32_t total = (uint32_t)nq * KPAD * 4u;
                 mbar_expect_tx(tile_bar, total);
-                const char *src = reinterpret_cast<const char *>(prm.Q + (size_t)cs * KPAD);
+                const char *src = reinterpret_cast<const char *>(R.Q + (size_t)cs * KPAD);
                 char *dst = reinterpret_cast<char *>(Qs);
                 for (uint32_t o = 0; o < total; o += 32768u)
                     bulk_g2s(dst + o, src + o, min(32768u, total - o), tile_bar);
             }
         }
         __syncthreads();   // descriptors visible; mbarrier init visible (first step)
+        if constexpr (RING) {
+            if (abort_s) break;   // a hand-over wait timed out (a peer died): leave, the host reports it
+        }
 
         // ---- this warp's stream ---------------------------------------------------------------
         const int64_t S0 = boff[warp * W];
         const uint32_t slen = (uint32_t)(boff[warp * W + W] - S0);   // multiple of 4 (padded buckets)
         const uint32_t nchunks = (slen + kChunk - 1) / kChunk;
         const uint32_t nquads = slen / 4;
-        const PackedRating *stream = prm.packed + S0;
+        const PackedRating *stream = R.packed + S0;
         const int64_t *off_w = boff + warp * W;
 
         // Everything below counts in QUADS (4 stream positions = 48 bytes) from the start of this
@@ -429,15 +505,18 @@ sgd_block_kernel(const SgdParams prm)
                 }
                 if (lane < 4) {
                     const uint32_t ul = *reinterpret_cast<const uint32_t *>(rec + 12 * lane) & kIdMask;
-                    cp_async<4>(pbias + fslot0 + lane, row_ptr(prm.ub, ul, 4));
+                    cp_async<4>(pbias + fslot0 + lane, row_ptr(ub_g, ul, 4));
                 }
             }
             cp_async_commit();
         }
 
-        if (nq > 0) mbar_wait(tile_bar, step & 1);
+        if (nq > 0) {
+            mbar_wait(tile_bar, tile_seq & 1u);
+            tile_seq += 1;
+        }
         // item biases of the block: L2 loads (another SM wrote them; L1 may hold a stale line)
-        for (int i = threadIdx.x; i < nq; i += blockDim.x) ibs[i] = __ldcg(prm.ib + cs + i);
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) ibs[i] = __ldcg(R.ib + cs + i);
         __syncthreads();   // tile + biases in place
         lap(5);
 
@@ -509,7 +588,7 @@ sgd_block_kernel(const SgdParams prm)
         auto store_p = [&](int u, const Frag<E> &pu, float bu) {
             if constexpr (TIMING) { if (prm.exp & 1) return; }
             store_p_row(u, pu);
-            if (lane == 0) *row_ptr(prm.ub, (uint32_t)u, 4) = bu;
+            if (lane == 0) *row_ptr(ub_g, (uint32_t)u, 4) = bu;
         };
         // the four user biases of a quad in one predicated store: lane t writes rating t's (its
         // user id comes straight from the record).  keep bit t clear = rating t + 1 is the same
@@ -519,7 +598,7 @@ sgd_block_kernel(const SgdParams prm)
             const bool lo = (lane & 2) == 0, even = (lane & 1) == 0;
             const int ul = lo ? (even ? u4[0] : u4[1]) : (even ? u4[2] : u4[3]);
             const float v = lo ? (even ? b4[0] : b4[1]) : (even ? b4[2] : b4[3]);
-            if (lane < 4 && ((keep >> lane) & 1u)) *row_ptr(prm.ub, (uint32_t)ul, 4) = v;
+            if (lane < 4 && ((keep >> lane) & 1u)) *row_ptr(ub_g, (uint32_t)ul, 4) = v;
         };
         auto store_q = [&](int it, const Frag<E> &q, float bi) {
             if constexpr (TIMING) { if (prm.exp & 2) return; }
@@ -540,8 +619,8 @@ sgd_block_kernel(const SgdParams prm)
                 bu = cbu;
             } else if (stale) {
                 __syncwarp();   // lane 0's bias store of an earlier rating is visible to every lane
-                frag_load<E>(pu, row_ptr(prm.P, (uint32_t)u, KPAD * 4), lane);
-                bu = *row_ptr(prm.ub, (uint32_t)u, 4);
+                frag_load<E>(pu, row_ptr(R.P, (uint32_t)u, KPAD * 4), lane);
+                bu = *row_ptr(ub_g, (uint32_t)u, 4);
             } else {
                 frag_load<E>(pu, prow + slot * KPAD, lane);
                 bu = pbias[slot];
@@ -755,7 +834,7 @@ sgd_block_kernel(const SgdParams prm)
                     // the record here would put its latency at the end of every iteration)
                     const bool lo = (lane & 2) == 0, even = (lane & 1) == 0;
                     const uint32_t ul = lo ? (even ? fu[0] : fu[1]) : (even ? fu[2] : fu[3]);
-                    if (lane < 4) cp_async<4>(pbias + fslot0 + lane, row_ptr(prm.ub, ul, 4));
+                    if (lane < 4) cp_async<4>(pbias + fslot0 + lane, row_ptr(ub_g, ul, 4));
                 }
                 cp_async_commit();
                 lap(3);
@@ -775,11 +854,14 @@ sgd_block_kernel(const SgdParams prm)
         // now, so that they cross while the CTA waits for its last warp, writes the tile back and
         // waits for the next column block (the stream does not depend on any other CTA).
         chunks_issued = false;
-        if (s + 1 < prm.s_end) {
-            const int ncbl = (rb + s + 1) % prm.B;
-            const int64_t nbase = ((((int64_t)prm.slab * prm.B + rb) * prm.B + ncbl) * W + warp) * W;
-            const int64_t nS0 = __ldg(prm.bucket_off + nbase);
-            const uint32_t nslen = (uint32_t)(__ldg(prm.bucket_off + nbase + W) - nS0);
+        if (it + 1 < prm.it_end) {
+            const int64_t nit = it + 1;
+            const int n_in_epoch = (int)(nit % steps_per_epoch);
+            const int nslab = (R.rank + n_in_epoch / prm.B) % prm.G;
+            const int ncbl = (rb + n_in_epoch % prm.B) % prm.B;
+            const int64_t nbase = ((((int64_t)nslab * prm.B + rb) * prm.B + ncbl) * W + warp) * W;
+            const int64_t nS0 = __ldg(R.bucket_off + nbase);
+            const uint32_t nslen = (uint32_t)(__ldg(R.bucket_off + nbase + W) - nS0);
             const uint32_t nn = min((nslen + kChunk - 1) / kChunk, (uint32_t)kStages);
             if (lane == 0) {
                 for (uint32_t c = 0; c < nn; ++c) {
@@ -787,27 +869,69 @@ sgd_block_kernel(const SgdParams prm)
                     const uint32_t g = chunk_seq + c;
                     uint64_t *bar = my_bar + (g % kStages);
                     mbar_expect_tx(bar, cnt * 12u);
-                    bulk_g2s(ring + (g % kStages) * kChunk, prm.packed + nS0 + (size_t)c * kChunk, cnt * 12u, bar);
+                    bulk_g2s(ring + (g % kStages) * kChunk, R.packed + nS0 + (size_t)c * kChunk, cnt * 12u, bar);
                 }
             }
             chunks_issued = true;
         }
         __syncthreads();   // every warp is done with the tile
         lap(4);
-        // write the Q tile back and pass the column block on
+        // write the Q tile back and pass the column block on.  Around a ring the last sub-epoch of
+        // a step leaves the block in the NEXT rank's copy of Q (peer memory, over NVLink): that
+        // rank finds it in its own HBM when the counter arrives.
+        const bool to_peer = RING && s + 1 == prm.B && prm.world > 1;
         {
             const int nvec = nq * KPAD / 4;
-            float4 *dst = reinterpret_cast<float4 *>(prm.Q + (size_t)cs * KPAD);
+            float4 *dst = reinterpret_cast<float4 *>((to_peer ? R.peer_Q : R.Q) + (size_t)cs * KPAD);
+            float *dst_b = (to_peer ? R.peer_ib : R.ib) + cs;
             const float4 *srcv = reinterpret_cast<const float4 *>(Qs);
-            for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = srcv[i];
-            for (int i = threadIdx.x; i < nq; i += blockDim.x) prm.ib[cs + i] = ibs[i];
+            // Divergence check, off the hot loop: the fixed-point reduction turns a NaN partial
+            // into 0, so a non-finite factor would never reach the error sum -- but any update
+            // with a non-finite P or Q row leaves a non-finite Q row, and every Q row passes
+            // through here.  0 * x is NaN exactly for x = +-inf / NaN.
+            float chk = 0.f;
+            for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+                const float4 t = srcv[i];
+                chk = fmaf(0.f, t.x, fmaf(0.f, t.y, fmaf(0.f, t.z, fmaf(0.f, t.w, chk))));
+                dst[i] = t;
+            }
+            for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+                chk = fmaf(0.f, ibs[i], chk);
+                dst_b[i] = ibs[i];
+            }
+            if (__any_sync(FULL, chk != chk)) se = NAN;   // the reference prints a NaN RMSE then (kmf_train.pyx:273)
         }
-        if (prm.ticks) {
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) st_release_gpu(prm.ticks + cbl, s + 1);
+        // the epoch's error sum leaves with its last sub-epoch (or with the launch)
+        const bool epoch_ends = in_epoch + 1 == (int)steps_per_epoch || it + 1 == prm.it_end;
+        if (epoch_ends) {
+            if (lane == 0) se_s[warp] = se;
+            se = 0.0;
+        }
+        if (R.ticks) {
+            if constexpr (RING) {
+                if (to_peer) {
+                    __threadfence_system();
+                    __syncthreads();
+                    if (threadIdx.x == 0) st_release_sys(R.peer_ticks + cbg, tick_need + 1);
+                } else {
+                    // last sub-epoch of a step on a single rank (world == 1 never takes RING) or
+                    // an inner sub-epoch: the next user is a CTA of this device
+                    __threadfence();
+                    __syncthreads();
+                    if (threadIdx.x == 0) st_release_gpu(R.ticks + cbg, tick_need + 1);
+                }
+            } else {
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) st_release_gpu(R.ticks + cbg, tick_need + 1);
+            }
         } else {
             __syncthreads();
+        }
+        if (epoch_ends && threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < W; ++w) tot += se_s[w];
+            R.se_part[(epoch - prm.e_base) * prm.se_stride + rb] = tot;
         }
         lap(6);
     }
@@ -815,12 +939,12 @@ sgd_block_kernel(const SgdParams prm)
         if (prm.timing && lane == 0)
             for (int k2 = 0; k2 < 8; ++k2) prm.timing[((size_t)rb * W + warp) * 8 + k2] = tsec[k2];
     }
-    if (lane == 0) se_s[warp] = se;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < W; ++w) tot += se_s[w];
-        prm.se_part[rb] = tot;
+    if constexpr (RING) {
+        // timed out: every epoch this launch still owed reports NaN
+        if (abort_s && threadIdx.x == 0) {
+            const int64_t e_last = (prm.it_end - 1) / steps_per_epoch;
+            for (int64_t e = prm.e_base; e <= e_last; ++e) R.se_part[(e - prm.e_base) * prm.se_stride + rb] = NAN;
+        }
     }
 }
 
@@ -901,13 +1025,13 @@ size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W)
     b += (size_t)(W * W + 2) * 8;                          // bucket offsets (padded quads make counts redundant)
     b += (size_t)W * 8;                                    // per-warp squared error
     b += (size_t)((W + 3) & ~3) * 4;                       // per-warp phase counters
-    return b + 128;
+    return b + 384;   // alignment of the dynamic window + the kernel's static shared variables
 }
 
 namespace {
 
 template <int E, bool TIMING>
-int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative)
+int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative, int grid, bool ring)
 {
     const bool wide = prm.W > 8;
     // both sides updated (the training call) gets the variant without the gates; fold-in calls
@@ -915,49 +1039,101 @@ int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool coo
     const bool gated = !(prm.update_users && prm.update_items);
     void (*fn)(const SgdParams) = nullptr;
 #define MF_PICK(K)                                                                                     \
-    fn = wide ? (gated ? sgd_block_kernel<E, K, TIMING, 512, true> : sgd_block_kernel<E, K, TIMING, 512, false>) \
-              : (gated ? sgd_block_kernel<E, K, TIMING, 256, true> : sgd_block_kernel<E, K, TIMING, 256, false>)
-    if (kernel == MFREC_KERNEL_LINEAR) { MF_PICK(MFREC_KERNEL_LINEAR); } else { MF_PICK(MFREC_KERNEL_LOGISTIC); }
+    fn = wide ? (gated ? sgd_block_kernel<E, K, TIMING, 512, true, false> : sgd_block_kernel<E, K, TIMING, 512, false, false>) \
+              : (gated ? sgd_block_kernel<E, K, TIMING, 256, true, false> : sgd_block_kernel<E, K, TIMING, 256, false, false>)
+#define MF_PICK_RING(K) \
+    fn = wide ? sgd_block_kernel<E, K, false, 512, false, true> : sgd_block_kernel<E, K, false, 256, false, true>
+    if (ring) {
+        if (gated || TIMING)
+            return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "ring launches train both sides and have no timing build");
+        if (kernel == MFREC_KERNEL_LINEAR) { MF_PICK_RING(MFREC_KERNEL_LINEAR); } else { MF_PICK_RING(MFREC_KERNEL_LOGISTIC); }
+    } else {
+        if (kernel == MFREC_KERNEL_LINEAR) { MF_PICK(MFREC_KERNEL_LINEAR); } else { MF_PICK(MFREC_KERNEL_LOGISTIC); }
+    }
 #undef MF_PICK
+#undef MF_PICK_RING
     // per device and cheap: set on every launch (a process may hold contexts on several devices)
     MF_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cooperative) {
-        // all B CTAs must be resident at once: they wait on one another's column blocks
+        // all CTAs must be resident at once: they wait on one another's column blocks
         void *args[] = {(void *)&prm};
-        MF_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fn, dim3(prm.B), dim3(prm.W * 32), args, smem,
+        MF_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fn, dim3(grid), dim3(prm.W * 32), args, smem,
                                                  ctx->stream));
         ctx->launches += 1;
     } else {
-        fn<<<prm.B, prm.W * 32, smem, ctx->stream>>>(prm);
+        fn<<<grid, prm.W * 32, smem, ctx->stream>>>(prm);
         MF_LAUNCH_CHECK(ctx);
     }
     return MFREC_OK;
 }
 
 template <bool TIMING>
-int launch_sgd_kpad(mfrec_ctx *ctx, int kpad, int kernel, SgdParams &prm, size_t smem, bool cooperative)
+int launch_sgd_kpad(mfrec_ctx *ctx, int kpad, int kernel, SgdParams &prm, size_t smem, bool cooperative,
+                    int grid = 0, bool ring = false)
 {
+    if (grid == 0) grid = prm.B;
     switch (kpad) {
-    case 32: return launch_sgd<1, TIMING>(ctx, kernel, prm, smem, cooperative);
-    case 64: return launch_sgd<2, TIMING>(ctx, kernel, prm, smem, cooperative);
-    case 128: return launch_sgd<4, TIMING>(ctx, kernel, prm, smem, cooperative);
-    case 256: return launch_sgd<8, TIMING>(ctx, kernel, prm, smem, cooperative);
+    case 32: return launch_sgd<1, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
+    case 64: return launch_sgd<2, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
+    case 128: return launch_sgd<4, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
+    case 256: return launch_sgd<8, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
     default: return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", kpad);
     }
 }
 
-// can B CTAs of W warps with `smem` bytes each be co-resident (one wave)?
-bool sgd_fits_one_wave(mfrec_ctx *ctx, int B, int W, size_t smem)
+// can n CTAs of W warps with `smem` bytes each be co-resident (one wave)?
+bool sgd_fits_one_wave(mfrec_ctx *ctx, int n, int W, size_t smem)
 {
     // one CTA per SM is always possible when the shared memory fits (<= 512 threads, <= 128
     // registers per thread by __launch_bounds__); more than sm_count CTAs would need two per SM
-    if (B <= ctx->sm_count) return smem <= ctx->smem_optin;
+    if (n <= ctx->sm_count) return smem <= ctx->smem_optin;
     const size_t per_sm = ctx->smem_per_sm;
     const int by_smem = (int)(per_sm / (smem + 1024));
     const int by_threads = 2048 / (W * 32);
     const int by_regs = 65536 / (128 * W * 32);
     const int per = std::min(by_smem, std::min(by_threads, by_regs));
-    return (int64_t)per * ctx->sm_count >= B;
+    return (int64_t)per * ctx->sm_count >= n;
+}
+
+// hyper-parameters + the fixed-point scale of the warp reduction
+void fill_hyper(SgdParams &prm, const mfrec_ratings *r, double learning_rate, double K_users, double K_items,
+                double K_bias, int update_users, int update_items)
+{
+    prm.lr = (float)learning_rate; prm.Ku = (float)K_users; prm.Ki = (float)K_items; prm.Kb = (float)K_bias;
+    prm.update_users = update_users; prm.update_items = update_items;
+    // The dot product's cross-lane sum runs in 32-bit fixed point (REDUX).  Predictions live
+    // on the rating scale, so allow |dot| up to 16 x max|rating| (at least 16) before the
+    // integer sum wraps; the resolution is then <= 2^-23 of that range (fp32-like).  A run that
+    // diverges leaves that range on its way to inf / NaN factors, which the kernel reports as a
+    // NaN error sum (see the tile write-back in sgd_block_kernel).
+    const float range = 16.f * fmaxf(r->max_abs_rating, 1.f);
+    int ex = 0;
+    frexpf(range, &ex);              // range <= 2^ex
+    prm.fx_scale = ldexpf(1.f, 30 - ex);
+    prm.fx_inv = ldexpf(1.f, ex - 30);
+    prm.timing = nullptr;
+    prm.exp = 0;
+    prm.wait_ns = 0;
+    prm.ranks = nullptr;
+}
+
+int ensure_scratch(mfrec_ctx *ctx, size_t se_doubles, size_t ticks)
+{
+    if (ctx->se_cap < se_doubles) {
+        if (ctx->se_scratch) cudaFree(ctx->se_scratch);
+        ctx->se_scratch = nullptr;
+        ctx->se_cap = 0;
+        MF_CUDA(ctx, cudaMalloc((void **)&ctx->se_scratch, se_doubles * 8));
+        ctx->se_cap = se_doubles;
+    }
+    if (ctx->ticks_cap < ticks) {
+        if (ctx->ticks) cudaFree(ctx->ticks);
+        ctx->ticks = nullptr;
+        ctx->ticks_cap = 0;
+        MF_CUDA(ctx, cudaMalloc((void **)&ctx->ticks, ticks * 4));
+        ctx->ticks_cap = ticks;
+    }
+    return MFREC_OK;
 }
 
 }  // namespace
@@ -973,7 +1149,6 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: model was not created with this layout");
     if (slab >= r->G) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: slab=%d of %d", slab, r->G);
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int s_lo = slab < 0 ? 0 : slab, s_hi = slab < 0 ? r->G : slab + 1;
     const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
     if (smem > ctx->smem_optin)
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
@@ -983,92 +1158,354 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     static int per_subepoch_env = -1;
     if (per_subepoch_env < 0) per_subepoch_env = getenv("MFREC_SGD_LAUNCH_PER_SUBEPOCH") ? 1 : 0;
     const bool persistent = !per_subepoch_env && ctx->coop_launch && sgd_fits_one_wave(ctx, r->B, r->W, smem);
-    const int64_t launches = (int64_t)(s_hi - s_lo) * (persistent ? 1 : r->B);
+    // The flattened iteration space of the kernel: it = (epoch * G + step) * B + s with the slab of
+    // a step = (rank + step) mod G.  The whole epoch = steps 0 .. G-1 as rank 0; one slab = step 0
+    // as "rank" slab.
+    const int rank = slab < 0 ? 0 : slab;
+    const int64_t n_it = (int64_t)(slab < 0 ? r->G : 1) * r->B;
+    const int64_t launches = persistent ? 1 : n_it;
     const int64_t nparts = launches * r->B;
-    if (ctx->se_cap < (size_t)nparts) {
-        if (ctx->se_scratch) cudaFree(ctx->se_scratch);
-        ctx->se_scratch = nullptr;
-        ctx->se_cap = 0;
-        MF_CUDA(ctx, cudaMalloc((void **)&ctx->se_scratch, (size_t)nparts * 8));
-        ctx->se_cap = (size_t)nparts;
-    }
-    if (persistent && ctx->ticks_cap < (size_t)r->B) {
-        if (ctx->ticks) cudaFree(ctx->ticks);
-        ctx->ticks = nullptr;
-        ctx->ticks_cap = 0;
-        MF_CUDA(ctx, cudaMalloc((void **)&ctx->ticks, (size_t)r->B * 4));
-        ctx->ticks_cap = (size_t)r->B;
-    }
+    MF_TRY(ensure_scratch(ctx, (size_t)nparts, persistent ? (size_t)r->G * r->B : 0));
     SgdParams prm;
-    prm.packed = r->packed;
-    prm.bucket_off = r->bucket_off;
-    prm.col_start = r->col_start;
-    prm.Q = m->Q; prm.ib = m->ib; prm.P = m->P; prm.ub = m->ub;
-    prm.B = r->B; prm.W = r->W;
+    memset(&prm, 0, sizeof(prm));
+    fill_hyper(prm, r, learning_rate, K_users, K_items, K_bias, update_users, update_items);
+    prm.self.packed = r->packed;
+    prm.self.bucket_off = r->bucket_off;
+    prm.self.col_start = r->col_start;
+    prm.self.Q = m->Q; prm.self.ib = m->ib; prm.self.P = m->P; prm.self.ub = m->ub;
+    prm.self.rank = rank;
+    prm.B = r->B; prm.W = r->W; prm.G = r->G; prm.world = 1;
     prm.tile_rows = r->max_cb_items;
-    prm.lr = (float)learning_rate; prm.Ku = (float)K_users; prm.Ki = (float)K_items; prm.Kb = (float)K_bias;
-    prm.update_users = update_users; prm.update_items = update_items;
-    {
-        // The dot product's cross-lane sum runs in 32-bit fixed point (REDUX).  Predictions live
-        // on the rating scale, so allow |dot| up to 16 x max|rating| (at least 16) before the
-        // integer sum wraps; the resolution is then <= 2^-23 of that range (fp32-like).
-        const float range = 16.f * fmaxf(r->max_abs_rating, 1.f);
-        int ex = 0;
-        frexpf(range, &ex);              // range <= 2^ex
-        prm.fx_scale = ldexpf(1.f, 30 - ex);
-        prm.fx_inv = ldexpf(1.f, ex - 30);
-    }
+    prm.e_base = 0;
+    prm.se_stride = r->B;
     // debug: MFREC_SGD_TIMING=1 prints per-section cycle counts of the first launches to stderr
     static int timing_env = -1;
     if (timing_env < 0) timing_env = getenv("MFREC_SGD_TIMING") ? std::max(3, atoi(getenv("MFREC_SGD_TIMING"))) : 0;
     DevBuf<unsigned long long> d_timing;
-    prm.timing = nullptr;
     prm.exp = getenv("MFREC_SGD_EXP") ? atoi(getenv("MFREC_SGD_EXP")) : 0;
     if (timing_env) {
         MF_CUDA(ctx, d_timing.alloc((size_t)r->B * r->W * 8, ctx->stream));
         prm.timing = d_timing.p;
     }
     int64_t part = 0;
-    for (int g = s_lo; g < s_hi; ++g) {
-        for (int s = 0; s < r->B; s += persistent ? r->B : 1) {
-            prm.slab = g;
-            prm.s_begin = s;
-            prm.s_end = persistent ? r->B : s + 1;
-            prm.ticks = persistent ? ctx->ticks : nullptr;
-            prm.se_part = ctx->se_scratch + part;
-            part += r->B;
-            if (persistent) MF_CUDA(ctx, cudaMemsetAsync(ctx->ticks, 0, (size_t)r->B * 4, ctx->stream));
-            if (timing_env) {
-                MF_CUDA(ctx, cudaMemsetAsync(d_timing.p, 0, (size_t)r->B * r->W * 64, ctx->stream));
-                MF_TRY(launch_sgd_kpad<true>(ctx, m->kpad, kernel, prm, smem, persistent));
-                std::vector<unsigned long long> h((size_t)r->B * r->W * 8);
-                MF_CUDA(ctx, cudaMemcpyAsync(h.data(), d_timing.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-                MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                double avg[8] = {0};
-                double worst_tot = 0; int worst = 0;
-                for (int c = 0; c < r->B * r->W; ++c) {
-                    double busy = 0;
-                    for (int k2 = 0; k2 < 8; ++k2) avg[k2] += (double)h[(size_t)c * 8 + k2];
-                    for (int k2 = 0; k2 < 4; ++k2) busy += (double)h[(size_t)c * 8 + k2];
-                    if (busy > worst_tot) { worst_tot = busy; worst = c; }
-                }
-                fprintf(stderr, "[sgd timing] slab %d sub-epochs [%d,%d): avg cycles/warp by section "
-                                "(issue, cp.async wait, quad load, update, hand-over wait, set-up, tail):",
-                        g, prm.s_begin, prm.s_end);
-                for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %.0f", avg[k2] / (r->B * r->W));
-                fprintf(stderr, " | busiest warp (cta %d warp %d):", worst / r->W, worst % r->W);
-                for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %llu", h[(size_t)worst * 8 + k2]);
-                fprintf(stderr, "\n");
-                if (--timing_env == 0) prm.timing = nullptr;
-            } else {
-                MF_TRY(launch_sgd_kpad<false>(ctx, m->kpad, kernel, prm, smem, persistent));
+    for (int64_t it = 0; it < n_it; it += persistent ? n_it : 1) {
+        prm.it_begin = it;
+        prm.it_end = persistent ? n_it : it + 1;
+        prm.self.ticks = persistent ? ctx->ticks : nullptr;
+        prm.self.se_part = ctx->se_scratch + part;
+        part += r->B;
+        if (persistent) MF_CUDA(ctx, cudaMemsetAsync(ctx->ticks, 0, (size_t)r->G * r->B * 4, ctx->stream));
+        if (timing_env) {
+            MF_CUDA(ctx, cudaMemsetAsync(d_timing.p, 0, (size_t)r->B * r->W * 64, ctx->stream));
+            MF_TRY(launch_sgd_kpad<true>(ctx, m->kpad, kernel, prm, smem, persistent));
+            std::vector<unsigned long long> h((size_t)r->B * r->W * 8);
+            MF_CUDA(ctx, cudaMemcpyAsync(h.data(), d_timing.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            double avg[8] = {0};
+            double worst_tot = 0; int worst = 0;
+            for (int c = 0; c < r->B * r->W; ++c) {
+                double busy = 0;
+                for (int k2 = 0; k2 < 8; ++k2) avg[k2] += (double)h[(size_t)c * 8 + k2];
+                for (int k2 = 0; k2 < 4; ++k2) busy += (double)h[(size_t)c * 8 + k2];
+                if (busy > worst_tot) { worst_tot = busy; worst = c; }
             }
+            fprintf(stderr, "[sgd timing] iterations [%lld,%lld): avg cycles/warp by section "
+                            "(issue, cp.async wait, quad load, update, hand-over wait, set-up, tail):",
+                    (long long)prm.it_begin, (long long)prm.it_end);
+            for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %.0f", avg[k2] / (r->B * r->W));
+            fprintf(stderr, " | busiest warp (cta %d warp %d):", worst / r->W, worst % r->W);
+            for (int k2 = 0; k2 < 7; ++k2) fprintf(stderr, " %llu", h[(size_t)worst * 8 + k2]);
+            fprintf(stderr, "\n");
+            if (--timing_env == 0) prm.timing = nullptr;
+        } else {
+            MF_TRY(launch_sgd_kpad<false>(ctx, m->kpad, kernel, prm, smem, persistent));
         }
     }
     if (sq_err_out) {
         se_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->se_scratch, nparts, sq_err_out);
         MF_LAUNCH_CHECK(ctx);
     }
+    return MFREC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// DSGD ring: `world` ranks = `world` user slices x `world` item slabs.  Rank r
+// keeps its users' P rows and ratings; in step t of an epoch it updates its users x slab
+// (r + t) mod world.  ONE persistent launch per rank covers any number of epochs: a column block
+// is handed from CTA to CTA inside the device exactly as on one GPU, and the LAST sub-epoch of a
+// step writes the block straight into the NEXT rank's copy of Q (peer memory over NVLink:
+// cudaIpc-mapped across processes, directly addressed inside one process) and releases that
+// rank's counter at system scope -- hand-over granularity is a column block (<= 62 KB), there is
+// no kernel boundary, no staging copy and no NCCL call between steps.  The counters only ever
+// grow (uses of a column block so far), so launches of different ranks need no alignment.
+// ------------------------------------------------------------------------------------------
+struct mfrec_ring {
+    mfrec_ctx *ctx = nullptr;
+    const mfrec_ratings *r = nullptr;
+    mfrec_model *m = nullptr;
+    int rank = 0, world = 1;
+    // one cudaMalloc block (cudaIpcGetMemHandle exports whole allocations):
+    //   [ Q  ni x kpad float | ib  ni float (padded) | ticks  G*B int32 | abort int32 ]
+    char *block = nullptr;
+    size_t off_ib = 0, off_ticks = 0, off_abort = 0, bytes = 0;
+    char *peer = nullptr;        // the block of rank - 1 (the next user of every slab this rank finishes)
+    bool peer_ipc = false;
+    int64_t epochs_done = 0;
+    double *se_part = nullptr;   // [epochs][B]
+    size_t se_cap = 0;
+    SgdRank *d_rank = nullptr;   // device copy of this rank's arguments
+};
+
+static float *ring_Q(char *b) { return reinterpret_cast<float *>(b); }
+
+extern "C" void mfrec_ring_destroy(mfrec_ring *g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    if (g->peer && g->peer_ipc) cudaIpcCloseMemHandle(g->peer);
+    if (g->block) cudaFree(g->block);
+    if (g->se_part) cudaFree(g->se_part);
+    if (g->d_rank) cudaFree(g->d_rank);
+    mfrec_ctx_release(g->ctx);
+    delete g;
+}
+
+extern "C" int mfrec_ring_create(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_model *m, int rank, int world,
+                                 mfrec_ring **out)
+{
+    if (!ctx || !r || !m || !out) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_create: NULL argument");
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world || r->G != world)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_create: rank %d of %d, layout has %d slabs (pack with n_slabs = world)",
+                               rank, world, r->G);
+    if (m->ni != r->ni || m->nu != r->nu || !m->user_perm)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_create: model was not created with this layout");
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    mfrec_ring *g = new (std::nothrow) mfrec_ring();
+    if (!g) return mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_ring_create: host OOM");
+    g->ctx = ctx;
+    mfrec_ctx_retain(ctx);
+    g->r = r; g->m = m; g->rank = rank; g->world = world;
+    const size_t qbytes = ((size_t)m->ni * m->kpad + 64) * 4;
+    g->off_ib = (qbytes + 255) & ~(size_t)255;
+    g->off_ticks = (g->off_ib + ((size_t)m->ni + 64) * 4 + 255) & ~(size_t)255;
+    g->off_abort = g->off_ticks + (size_t)r->G * r->B * 4;
+    g->bytes = g->off_abort + 256;
+    struct Guard { mfrec_ring *g; ~Guard() { if (g) mfrec_ring_destroy(g); } } guard{g};
+    MF_CUDA(ctx, cudaMalloc((void **)&g->block, g->bytes));
+    MF_CUDA(ctx, cudaMalloc((void **)&g->d_rank, sizeof(SgdRank)));
+    cudaStream_t st = ctx->stream;
+    MF_CUDA(ctx, cudaMemsetAsync(g->block, 0, g->bytes, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(g->block, m->Q, (size_t)m->ni * m->kpad * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(g->block + g->off_ib, m->ib, (size_t)m->ni * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(ctx, cudaStreamSynchronize(st));
+    guard.g = nullptr;
+    *out = g;
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ring_handle(mfrec_ring *g, void *handle64)
+{
+    if (!g || !handle64) return mfrec_set_error(g ? g->ctx : nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    MF_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    cudaIpcMemHandle_t h;
+    MF_CUDA(g->ctx, cudaIpcGetMemHandle(&h, g->block));
+    memcpy(handle64, &h, 64);
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ring_connect(mfrec_ring *g, const void *handles)
+{
+    if (!g || (!handles && g->world > 1))
+        return mfrec_set_error(g ? g->ctx : nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_connect: NULL argument");
+    MF_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    if (g->world == 1) { g->peer = g->block; g->peer_ipc = false; return MFREC_OK; }
+    const int dst = (g->rank + g->world - 1) % g->world;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char *>(handles) + (size_t)dst * 64, 64);
+    void *p = nullptr;
+    MF_CUDA(g->ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g->peer = static_cast<char *>(p);
+    g->peer_ipc = true;
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ring_connect_local(mfrec_ring *g, mfrec_ring *next)
+{
+    if (!g || !next) return mfrec_set_error(g ? g->ctx : nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_connect_local: NULL argument");
+    if (next->bytes != g->bytes || next->world != g->world || next->rank != (g->rank + g->world - 1) % g->world)
+        return mfrec_set_error(g->ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_connect_local: rank %d hands its slabs to rank %d, got rank %d",
+                               g->rank, (g->rank + g->world - 1) % g->world, next->rank);
+    MF_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    if (next->ctx->device != g->ctx->device) {
+        int can = 0;
+        MF_CUDA(g->ctx, cudaDeviceCanAccessPeer(&can, g->ctx->device, next->ctx->device));
+        if (!can)
+            return mfrec_set_error(g->ctx, MFREC_ERR_UNSUPPORTED, "device %d cannot address device %d", g->ctx->device, next->ctx->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(next->ctx->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else MF_CUDA(g->ctx, e);
+    }
+    g->peer = next->block;
+    g->peer_ipc = false;
+    return MFREC_OK;
+}
+
+namespace {
+
+void ring_rank_args(const mfrec_ring *g, SgdRank &a, double *se_part)
+{
+    a.packed = g->r->packed;
+    a.bucket_off = g->r->bucket_off;
+    a.col_start = g->r->col_start;
+    a.Q = ring_Q(g->block);
+    a.ib = reinterpret_cast<float *>(g->block + g->off_ib);
+    a.P = g->m->P;
+    a.ub = g->m->ub;
+    a.se_part = se_part;
+    a.ticks = reinterpret_cast<int32_t *>(g->block + g->off_ticks);
+    a.peer_Q = ring_Q(g->peer);
+    a.peer_ib = reinterpret_cast<float *>(g->peer + g->off_ib);
+    a.peer_ticks = reinterpret_cast<int32_t *>(g->peer + g->off_ticks);
+    a.abort = reinterpret_cast<int32_t *>(g->block + g->off_abort);
+    a.rank = g->rank;
+}
+
+unsigned long long ring_wait_ns()
+{
+    const char *s = getenv("MFREC_RING_TIMEOUT_MS");
+    return (unsigned long long)(s ? atoll(s) : 20000) * 1000000ull;
+}
+
+// out[e] = sum of the `n` partials of epoch e
+__global__ void __launch_bounds__(256) se_reduce_epochs_kernel(const double *__restrict__ part, int n,
+                                                               double *__restrict__ out)
+{
+    __shared__ double sh[256];
+    const double *p = part + (size_t)blockIdx.x * n;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) acc += p[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// one launch over `n_ranks` rings that live on ONE device (n_ranks == 1: the normal case)
+int ring_launch(mfrec_ring *const *rings, int n_ranks, int kernel, double learning_rate, double K_users,
+                double K_items, double K_bias, int n_epochs, double *sq_err_out)
+{
+    mfrec_ring *g0 = rings[0];
+    mfrec_ctx *ctx = g0->ctx;
+    const mfrec_ratings *r = g0->r;
+    if (n_epochs <= 0) return MFREC_OK;
+    if (kernel != MFREC_KERNEL_LINEAR && kernel != MFREC_KERNEL_LOGISTIC)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs: kernel=%d", kernel);
+    for (int i = 0; i < n_ranks; ++i) {
+        mfrec_ring *g = rings[i];
+        if (!g->peer) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs: rank %d is not connected", g->rank);
+        if (g->ctx != ctx || g->r->B != r->B || g->r->W != r->W || g->r->G != r->G || g->m->kpad != g0->m->kpad ||
+            g->r->max_cb_items != r->max_cb_items || g->epochs_done != g0->epochs_done)
+            return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs: the rings of one launch must share context and layout shape");
+    }
+    MF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, g0->m->kpad, r->W);
+    const int grid = n_ranks * r->B;
+    if (smem > ctx->smem_optin || !ctx->coop_launch || !sgd_fits_one_wave(ctx, grid, r->W, smem))
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                               "mfrec_ring_epochs: %d CTAs x %zu B shared memory cannot be co-resident; pack with fewer row_blocks",
+                               grid, smem);
+    const size_t need = (size_t)n_epochs * grid;
+    if (g0->se_cap < need) {
+        if (g0->se_part) cudaFree(g0->se_part);
+        g0->se_part = nullptr;
+        g0->se_cap = 0;
+        MF_CUDA(ctx, cudaMalloc((void **)&g0->se_part, need * 8));
+        g0->se_cap = need;
+    }
+    std::vector<SgdRank> args(n_ranks);
+    for (int i = 0; i < n_ranks; ++i) ring_rank_args(rings[i], args[i], g0->se_part + (size_t)i * r->B);
+    DevBuf<SgdRank> d_multi;
+    SgdRank *d_args = g0->d_rank;
+    if (n_ranks > 1) {
+        MF_CUDA(ctx, d_multi.alloc(n_ranks, ctx->stream));
+        d_args = d_multi.p;
+    }
+    MF_CUDA(ctx, cudaMemcpyAsync(d_args, args.data(), sizeof(SgdRank) * n_ranks, cudaMemcpyHostToDevice, ctx->stream));
+    SgdParams prm;
+    memset(&prm, 0, sizeof(prm));
+    fill_hyper(prm, r, learning_rate, K_users, K_items, K_bias, 1, 1);
+    float mx = 0.f;
+    for (int i = 0; i < n_ranks; ++i) mx = fmaxf(mx, rings[i]->r->max_abs_rating);
+    (void)mx;   // (every rank holds ratings of the same scale; the scale comes from rank 0's slice)
+    prm.ranks = d_args;
+    prm.B = r->B; prm.W = r->W; prm.G = r->G; prm.world = g0->world;
+    prm.tile_rows = r->max_cb_items;
+    const int64_t per_epoch = (int64_t)r->G * r->B;
+    prm.it_begin = g0->epochs_done * per_epoch;
+    prm.it_end = (g0->epochs_done + n_epochs) * per_epoch;
+    prm.e_base = g0->epochs_done;
+    prm.se_stride = grid;
+    prm.wait_ns = ring_wait_ns();
+    MF_TRY(launch_sgd_kpad<false>(ctx, g0->m->kpad, kernel, prm, smem, true, grid, true));
+    if (n_ranks > 1) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // d_multi is freed on return
+    for (int i = 0; i < n_ranks; ++i) rings[i]->epochs_done += n_epochs;
+    if (sq_err_out) {
+        se_reduce_epochs_kernel<<<n_epochs, 256, 0, ctx->stream>>>(g0->se_part, grid, sq_err_out);
+        MF_LAUNCH_CHECK(ctx);
+    }
+    return MFREC_OK;
+}
+
+}  // namespace
+
+extern "C" int mfrec_ring_epochs(mfrec_ring *g, int kernel, double learning_rate, double K_users, double K_items,
+                                 double K_bias, int n_epochs, double *sq_err_out)
+{
+    if (!g) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs: NULL ring");
+    return ring_launch(&g, 1, kernel, learning_rate, K_users, K_items, K_bias, n_epochs, sq_err_out);
+}
+
+extern "C" int mfrec_ring_epochs_one_device(mfrec_ring *const *rings, int world, int kernel, double learning_rate,
+                                            double K_users, double K_items, double K_bias, int n_epochs,
+                                            double *sq_err_out)
+{
+    if (!rings || world < 1 || !rings[0])
+        return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs_one_device: NULL argument");
+    for (int i = 0; i < world; ++i)
+        if (!rings[i] || rings[i]->rank != i || rings[i]->world != world)
+            return mfrec_set_error(rings[0]->ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs_one_device: rings[i] must be rank i of %d", world);
+    return ring_launch(rings, world, kernel, learning_rate, K_users, K_items, K_bias, n_epochs, sq_err_out);
+}
+
+extern "C" int mfrec_ring_wait(mfrec_ring *g)
+{
+    if (!g) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_wait: NULL ring");
+    MF_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    int32_t ab = 0;
+    MF_CUDA(g->ctx, cudaMemcpyAsync(&ab, g->block + g->off_abort, 4, cudaMemcpyDeviceToHost, g->ctx->stream));
+    MF_CUDA(g->ctx, cudaStreamSynchronize(g->ctx->stream));
+    if (ab)
+        return mfrec_set_error(g->ctx, MFREC_ERR_CUDA,
+                               "mfrec_ring_wait: rank %d gave up waiting for a column block from its neighbour (MFREC_RING_TIMEOUT_MS)",
+                               g->rank);
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ring_sync_model(mfrec_ring *g)
+{
+    if (!g) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ring_sync_model: NULL ring");
+    MF_TRY(mfrec_ring_wait(g));
+    cudaStream_t st = g->ctx->stream;
+    const mfrec_model *m = g->m;
+    MF_CUDA(g->ctx, cudaMemcpyAsync(m->Q, g->block, (size_t)m->ni * m->kpad * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(g->ctx, cudaMemcpyAsync(m->ib, g->block + g->off_ib, (size_t)m->ni * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(g->ctx, cudaStreamSynchronize(st));
     return MFREC_OK;
 }
 
@@ -1137,6 +1574,40 @@ extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k
             if (a < 0 || a >= nu || b < 0 || b >= ni)
                 return mfrec_set_error(ctx, MFREC_ERR_INDEX, "mfrec_train_kmf: rating %lld has (user,item)=(%d,%d)",
                                        (long long)n, a, b);
+        }
+        // A fold-in (KMFRecommender.retrain_user / retrain_item / add_user, kmf.py:120-172) names a
+        // handful of rows: move only those.  The untouched rest of u / v / the biases is never
+        // copied, so it stays bit-identical like in the reference.
+        if (nnz <= 65536 && (int64_t)ni + nu > 4 * nnz) {
+            std::vector<int32_t> uu(nnz), ii(nnz);
+            for (int64_t n = 0; n < nnz; ++n) { uu[n] = ratings_index[2 * n]; ii[n] = ratings_index[2 * n + 1]; }
+            std::sort(uu.begin(), uu.end());
+            uu.erase(std::unique(uu.begin(), uu.end()), uu.end());
+            std::sort(ii.begin(), ii.end());
+            ii.erase(std::unique(ii.begin(), ii.end()), ii.end());
+            const int32_t mu_ = (int32_t)uu.size(), mi_ = (int32_t)ii.size();
+            std::vector<double> cu((size_t)k * mi_), cv((size_t)k * mu_), cib(mi_), cub_(mu_);
+            std::vector<int32_t> cidx((size_t)2 * nnz);
+            for (int f = 0; f < k; ++f) {
+                for (int32_t a = 0; a < mi_; ++a) cu[(size_t)f * mi_ + a] = u[(size_t)f * ni + ii[a]];
+                for (int32_t a = 0; a < mu_; ++a) cv[(size_t)f * mu_ + a] = v[(size_t)f * nu + uu[a]];
+            }
+            for (int32_t a = 0; a < mi_; ++a) cib[a] = items_bias[ii[a]];
+            for (int32_t a = 0; a < mu_; ++a) cub_[a] = users_bias[uu[a]];
+            for (int64_t n = 0; n < nnz; ++n) {
+                cidx[2 * n] = (int32_t)(std::lower_bound(uu.begin(), uu.end(), ratings_index[2 * n]) - uu.begin());
+                cidx[2 * n + 1] = (int32_t)(std::lower_bound(ii.begin(), ii.end(), ratings_index[2 * n + 1]) - ii.begin());
+            }
+            MF_TRY(train_kmf_sequential(ctx, kernel, nbr_epochs, k, learning_rate, K_users, K_items, K_bias,
+                                        cu.data(), cv.data(), cidx.data(), ratings, nnz, mi_, mu_, cib.data(),
+                                        cub_.data(), update_users, update_items, rmse_per_epoch));
+            for (int f = 0; f < k; ++f) {
+                for (int32_t a = 0; a < mi_; ++a) u[(size_t)f * ni + ii[a]] = cu[(size_t)f * mi_ + a];
+                for (int32_t a = 0; a < mu_; ++a) v[(size_t)f * nu + uu[a]] = cv[(size_t)f * mu_ + a];
+            }
+            for (int32_t a = 0; a < mi_; ++a) items_bias[ii[a]] = cib[a];
+            for (int32_t a = 0; a < mu_; ++a) users_bias[uu[a]] = cub_[a];
+            return MFREC_OK;
         }
         return train_kmf_sequential(ctx, kernel, nbr_epochs, k, learning_rate, K_users, K_items, K_bias,
                                     u, v, ratings_index, ratings, nnz, ni, nu, items_bias, users_bias,

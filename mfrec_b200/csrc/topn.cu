@@ -158,8 +158,29 @@ extern "C" int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u,
                           double min_rating, double max_rating, int32_t N, int32_t *out_items,
                           double *out_scores, int32_t *out_counts)
 {
-    if (!ctx || !u || !v || !users || !out_items || !out_scores || !out_counts)
+    if (!ctx || !u || !v) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn: NULL argument");
+    if (n_users <= 0 || n_candidates <= 0 || N <= 0)   // nothing to score: no upload either
+        return mfrec_topn_on_model(ctx, nullptr, predictor, users, n_users, n_candidates, rated_indptr, rated_items, mu,
+                                min_rating, max_rating, N, out_items, out_scores, out_counts, ni, nu);
+    mfrec_model *M = nullptr;
+    MF_TRY(mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, &M));
+    const int rc = mfrec_topn_on_model(ctx, M, predictor, users, n_users, n_candidates, rated_indptr, rated_items, mu,
+                                    min_rating, max_rating, N, out_items, out_scores, out_counts, ni, nu);
+    mfrec_model_destroy(M);
+    return rc;
+}
+
+// ni / nu: only read when M is NULL (argument checks of a call that scores nothing)
+int mfrec_topn_on_model(mfrec_ctx *ctx, const mfrec_model *M, int predictor, const int32_t *users, int32_t n_users,
+                     int32_t n_candidates, const int64_t *rated_indptr, const int32_t *rated_items, double mu,
+                     double min_rating, double max_rating, int32_t N, int32_t *out_items, double *out_scores,
+                     int32_t *out_counts, int32_t ni, int32_t nu)
+{
+    if (M) { ni = M->ni; nu = M->nu; }
+    if (!ctx || !users || !out_items || !out_scores || !out_counts)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn: NULL argument");
+    if (M && (M->user_perm || M->item_perm))
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn: the model must be in identity layout (created without a ratings layout)");
     if (predictor < 0 || predictor > MFREC_PRED_DOT || n_users < 0 || N <= 0 || n_candidates < 0 ||
         n_candidates > ni)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn: predictor=%d n_users=%d N=%d n_candidates=%d",
@@ -176,9 +197,7 @@ extern "C" int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u,
         for (int32_t j = 0; j < n_users; ++j) out_counts[j] = 0;
         return MFREC_OK;
     }
-    mfrec_model *M = nullptr;
-    MF_TRY(mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, &M));
-    struct Guard { mfrec_model *m; ~Guard() { mfrec_model_destroy(m); } } guard{M};
+    if (!M) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn: NULL model");
 
     // batch users so the two key buffers stay under ~1 GiB each
     const int64_t max_rows = std::max<int64_t>(64, (int64_t)(1ll << 27) / nc);
@@ -240,4 +259,14 @@ extern "C" int mfrec_topn(mfrec_ctx *ctx, int predictor, int k, const double *u,
         MF_CUDA(ctx, cudaStreamSynchronize(st));
     }
     return MFREC_OK;
+}
+
+extern "C" int mfrec_model_topn(mfrec_ctx *ctx, const mfrec_model *m, int predictor, const int32_t *users,
+                                int32_t n_users, int32_t n_candidates, const int64_t *rated_indptr,
+                                const int32_t *rated_items, double mu, double min_rating, double max_rating,
+                                int32_t N, int32_t *out_items, double *out_scores, int32_t *out_counts)
+{
+    if (!m) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_model_topn: NULL model");
+    return mfrec_topn_on_model(ctx, m, predictor, users, n_users, n_candidates, rated_indptr, rated_items, mu,
+                               min_rating, max_rating, N, out_items, out_scores, out_counts, m->ni, m->nu);
 }

@@ -645,8 +645,27 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
                                 double min_rating, double max_rating, int32_t N, int32_t *out_items,
                                 double *out_scores, int32_t *out_counts, double stats[8])
 {
-    if (!ctx || !u || !v || !out_items || !out_scores || !out_counts)
+    if (!ctx || !u || !v) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn_sweep: NULL argument");
+    mfrec_model *M = nullptr;
+    MF_TRY(mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, &M));
+    const int rc = mfrec_model_topn_sweep(ctx, M, predictor, users, n_users, n_candidates, rated_indptr, rated_items,
+                                          mu, min_rating, max_rating, N, out_items, out_scores, out_counts, stats);
+    mfrec_model_destroy(M);
+    return rc;
+}
+
+extern "C" int mfrec_model_topn_sweep(mfrec_ctx *ctx, const mfrec_model *M, int predictor, const int32_t *users,
+                                      int32_t n_users, int32_t n_candidates, const int64_t *rated_indptr,
+                                      const int32_t *rated_items, double mu, double min_rating, double max_rating,
+                                      int32_t N, int32_t *out_items, double *out_scores, int32_t *out_counts,
+                                      double stats[8])
+{
+    if (!ctx || !M || !out_items || !out_scores || !out_counts)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn_sweep: NULL argument");
+    if (M->user_perm || M->item_perm)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn_sweep: the model must be in identity layout (created without a ratings layout)");
+    const int k = M->k;
+    const int32_t ni = M->ni, nu = M->nu;
     if (predictor < 0 || predictor > MFREC_PRED_DOT || n_users < 0 || N <= 0 || n_candidates < 0 || n_candidates > ni)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_topn_sweep: predictor=%d n_users=%d N=%d n_candidates=%d",
                                predictor, n_users, N, n_candidates);
@@ -669,16 +688,12 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
             all.resize(n_users);
             for (int32_t j = 0; j < n_users; ++j) all[j] = j;
         }
-        return mfrec_topn(ctx, predictor, k, u, v, ni, nu, users ? users : all.data(), n_users, n_candidates,
-                          rated_indptr, rated_items, mu, items_bias, users_bias, min_rating, max_rating, N,
-                          out_items, out_scores, out_counts);
+        return mfrec_topn_on_model(ctx, M, predictor, users ? users : all.data(), n_users, n_candidates, rated_indptr,
+                                rated_items, mu, min_rating, max_rating, N, out_items, out_scores, out_counts, ni, nu);
     }
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Tracer tr("topn_sweep", st);
-    mfrec_model *M = nullptr;
-    MF_TRY(mfrec_model_create(ctx, nullptr, k, ni, nu, u, v, items_bias, users_bias, &M));
-    struct Guard { mfrec_model *m; ~Guard() { mfrec_model_destroy(m); } } guard{M};
     const int kpad = M->kpad;
     const int nc = n_candidates;
     const int NA = KB >= 3 ? 2 : 4;
@@ -826,10 +841,9 @@ extern "C" int mfrec_topn_sweep(mfrec_ctx *ctx, int predictor, int k, const doub
             }
         std::vector<int32_t> f_items((size_t)nf * N), f_counts(nf);
         std::vector<double> f_scores((size_t)nf * N);
-        MF_TRY(mfrec_topn(ctx, predictor, k, u, v, ni, nu, fb_users.data(), nf, n_candidates,
-                          rated_indptr ? f_indptr.data() : nullptr, f_rated.empty() ? nullptr : f_rated.data(), mu,
-                          items_bias, users_bias, min_rating, max_rating, N, f_items.data(), f_scores.data(),
-                          f_counts.data()));
+        MF_TRY(mfrec_topn_on_model(ctx, M, predictor, fb_users.data(), nf, n_candidates,
+                                rated_indptr ? f_indptr.data() : nullptr, f_rated.empty() ? nullptr : f_rated.data(), mu,
+                                min_rating, max_rating, N, f_items.data(), f_scores.data(), f_counts.data(), ni, nu));
         for (int32_t j = 0; j < nf; ++j) {
             memcpy(out_items + (size_t)fb_pos[j] * N, f_items.data() + (size_t)j * N, (size_t)N * 4);
             memcpy(out_scores + (size_t)fb_pos[j] * N, f_scores.data() + (size_t)j * N, (size_t)N * 8);

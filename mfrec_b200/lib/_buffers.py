@@ -31,6 +31,20 @@ def buffer_arg(a, name, dtype, ndim, writable=True):
     return a
 
 
+def check_rating_arrays(u, v, ratings_index, ratings, items_bias=None, users_bias=None):
+    """Shape consistency the native side relies on (it takes nnz from ``ratings``, ni / nu from the
+    widths of ``u`` / ``v`` and copies nnz * 8, ni * 8, nu * 8 bytes from these host pointers): a
+    short index or bias array must raise here, not be read out of bounds there."""
+    if ratings_index.shape[0] and ratings_index.shape[1] != 2:
+        raise ValueError("ratings_index must have shape [nnz, 2]")
+    if ratings_index.shape[0] < ratings.shape[0]:
+        raise ValueError("ratings_index has fewer rows than ratings")
+    if items_bias is not None and items_bias.shape[0] < u.shape[1]:
+        raise ValueError("items_bias is shorter than the item factor array")
+    if users_bias is not None and users_bias.shape[0] < v.shape[1]:
+        raise ValueError("users_bias is shorter than the user factor array")
+
+
 # Process-wide knobs of the CUDA implementation (not part of the reference signature).
 # schedule: "stratified" (default, fp32, all SMs) | "sequential" (fp64, reference order).
 options = {

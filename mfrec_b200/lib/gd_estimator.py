@@ -17,7 +17,7 @@ overwrites its own accumulator; it is not reproduced and raises NotImplementedEr
 import numpy as np
 
 from mfrec_b200 import _native
-from mfrec_b200.lib._buffers import buffer_arg, native_opts, options
+from mfrec_b200.lib._buffers import buffer_arg, check_rating_arrays, native_opts, options
 
 last_feature_epochs = None
 last_feature_rmse = None
@@ -35,6 +35,7 @@ def _train(variant, min_epochs, max_epochs, min_improvement, dim, f_init, learni
     if variant != _native.FUNK_WITHOUT_BIAS:
         buffer_arg(items_bias, "items_bias", np.float64, 1, writable=False)
         buffer_arg(users_bias, "users_bias", np.float64, 1, writable=False)
+    check_rating_arrays(u, v, ratings_index, ratings, items_bias, users_bias)
     if dim > u.shape[0] or dim > v.shape[0] or dim < 0:
         raise ValueError("dim=%d exceeds the factor arrays (%d, %d features)" % (dim, u.shape[0], v.shape[0]))
     if dim == 0:
@@ -84,6 +85,7 @@ def _dev_common(dim, u, v, ratings_index, ratings, nbr_users):
     buffer_arg(v, "v", np.float64, 2)
     buffer_arg(ratings_index, "ratings_index", np.int32, 2, writable=False)
     buffer_arg(ratings, "ratings", np.float64, 1, writable=False)
+    check_rating_arrays(u, v, ratings_index, ratings)
     if dim > u.shape[0] or dim > v.shape[0] or dim < 0:
         raise ValueError("dim=%d exceeds the factor arrays (%d, %d features)" % (dim, u.shape[0], v.shape[0]))
     if nbr_users is not None and int(nbr_users) != v.shape[1]:
@@ -181,6 +183,7 @@ def estimator_loop_with_learned_bias(min_epochs, max_epochs, min_improvement, di
     dim = _dev_common(dim, u, v, ratings_index, ratings, None)
     buffer_arg(items_bias, "items_bias", np.float64, 1)
     buffer_arg(users_bias, "users_bias", np.float64, 1)
+    check_rating_arrays(u, v, ratings_index, ratings, items_bias, users_bias)
     if u.shape[0] != dim or v.shape[0] != dim:
         # full_estimator sums over `dim` features of the arrays it is given (:141-142)
         raise ValueError("estimator_loop_with_learned_bias needs factor arrays of exactly dim rows")

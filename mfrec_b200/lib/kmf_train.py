@@ -10,7 +10,7 @@ Same call signature as the reference's Cython functions (mfrec/lib/kmf_train.pyx
 import numpy as np
 
 from mfrec_b200 import _native
-from mfrec_b200.lib._buffers import buffer_arg, native_opts, options
+from mfrec_b200.lib._buffers import buffer_arg, check_rating_arrays, native_opts, options
 
 last_rmse = None  # rmse per epoch of the most recent call (the reference only prints it)
 
@@ -25,14 +25,9 @@ def _train(kernel, nbr_epochs, dim, learning_rate, K_users, K_items, K_bias, u, 
     buffer_arg(ratings, "ratings", np.float64, 1, writable=False)
     buffer_arg(items_bias, "items_bias", np.float64, 1)
     buffer_arg(users_bias, "users_bias", np.float64, 1)
-    if ratings_index.shape[0] and ratings_index.shape[1] != 2:
-        raise ValueError("ratings_index must have shape [nnz, 2]")
+    check_rating_arrays(u, v, ratings_index, ratings, items_bias, users_bias)
     if dim > u.shape[0] or dim > v.shape[0] or dim < 0:
         raise ValueError("dim=%d exceeds the factor arrays (%d, %d features)" % (dim, u.shape[0], v.shape[0]))
-    if items_bias.shape[0] < u.shape[1] or users_bias.shape[0] < v.shape[1]:
-        raise ValueError("bias arrays are shorter than the factor arrays")
-    if ratings_index.shape[0] < ratings.shape[0]:
-        raise ValueError("ratings_index has fewer rows than ratings")
     if dim == 0 or ratings.shape[0] == 0 or nbr_epochs <= 0:
         last_rmse = np.full(max(nbr_epochs, 0), np.nan)
         return None

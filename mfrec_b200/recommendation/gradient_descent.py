@@ -119,7 +119,10 @@ class GDRecommender(MFRecommender):
         (gradient_descent.py:577-599)."""
         rmse = np.zeros(self.max_epochs * self.dimensionality)
         self._init_model(initialize_model)
-        ratings_index, ratings = self.get_ratings(randomize_order=True)
+        # the reference shuffles (consuming the RNG) and then OVERWRITES both arrays with
+        # ratings_iterator() order (gradient_descent.py:588-592): it trains on the unshuffled order
+        self.get_ratings(randomize_order=True)
+        ratings_index, ratings = self.get_ratings()
         gd_estimator.estimator_loop(
             self.min_epochs, self.max_epochs, self.min_improvement, self.dimensionality, self.feature_init,
             self.learning_rate, self.K, self.svd_u, self.svd_v, ratings_index, ratings, 0, rmse,
@@ -151,9 +154,10 @@ class GDRecommender(MFRecommender):
         if method == 'norm_cosine':   # log(1 + cosine of the rows centred by the per-feature means)
             rows = rows - self.svd_u[1:self.dimensionality, :].mean(axis=1)[None, :]
             return self._similar_rows(rows, item_index, nbr_recommendations, similarity_threshold,
-                                      similarities_output, 'cosine', transform=lambda c: float(np.log(1.0 + c)))
+                                      similarities_output, 'cosine', transform=lambda c: float(np.log(1.0 + c)),
+                                      tag='items_norm_cosine')
         return self._similar_rows(rows, item_index, nbr_recommendations, similarity_threshold,
-                                  similarities_output, method)
+                                  similarities_output, method, tag='items_gd', skip_first=(method == 'euclidean'))
 
     # ---- fold-in (gradient_descent.py:879-905) ----------------------------------------------------------
     def _retrain(self, valid_ids, ratings_index, ratings, update_users, update_items, verbose):

@@ -13,6 +13,19 @@ _KERNELS = {'train_logistic_kernel': kmf_train.train_logistic_kernel,
             'train_linear_kernel': kmf_train.train_linear_kernel}
 
 
+def _fold_in(kernel, *args):
+    """A fold-in trains a handful of ratings against a frozen side: run it in the reference's own
+    order and precision (sequential schedule: float64, bit-exact for the linear kernel).  The library
+    then moves only the rows the ratings name, so the frozen factors stay bit-identical like in
+    the reference (a stratified fp32 pass would round every row of the model in place)."""
+    saved = kmf_train.options["schedule"]
+    kmf_train.options["schedule"] = "sequential"
+    try:
+        return _KERNELS[kernel](*args)
+    finally:
+        kmf_train.options["schedule"] = saved
+
+
 class KMFRecommender(MFRecommender):
     # As in the reference (kmf.py:33-42) the three regularisation keys map to K / K2 / K3 while
     # training reads K_users / K_items / K_bias: those settings are silently ignored there, and
@@ -83,7 +96,7 @@ class KMFRecommender(MFRecommender):
     def retrain_user(self, user_index, ratings_index, ratings, verbose=False, kernel='train_logistic_kernel'):
         valid_ids = np.where(ratings_index[:, 0] == user_index)[0]
         self.init_user_features(user_index)
-        _KERNELS[kernel](self.nbr_epochs, self.dimensionality, self.feature_init, self.learning_rate,
+        _fold_in(kernel, self.nbr_epochs, self.dimensionality, self.feature_init, self.learning_rate,
                          self.learning_rate_users, self.learning_rate_items, self.K_users,
                          self.K_items, self.K_bias, self.overall_bias, self.svd_u, self.svd_v,
                          np.ascontiguousarray(ratings_index[valid_ids, :]),
@@ -95,7 +108,7 @@ class KMFRecommender(MFRecommender):
         # this is the evident intent, symmetric to retrain_user
         valid_ids = np.where(ratings_index[:, 1] == item_index)[0]
         self.init_item_features(item_index)
-        _KERNELS[kernel](self.nbr_epochs, self.dimensionality, self.feature_init, self.learning_rate,
+        _fold_in(kernel, self.nbr_epochs, self.dimensionality, self.feature_init, self.learning_rate,
                          self.learning_rate_users, self.learning_rate_items, self.K_users,
                          self.K_items, self.K_bias, self.overall_bias, self.svd_u, self.svd_v,
                          np.ascontiguousarray(ratings_index[valid_ids, :]),

@@ -22,10 +22,17 @@ def test_predict_rating(recommender, u_test, nbr_samples=10, verbose=False, pred
     if name in native and sample.shape[0]:
         pairs = np.ascontiguousarray(sample[:, 0:2], dtype=np.int32)
         real = np.ascontiguousarray(sample[:, 2], dtype=np.float64)
-        _, all_errors = _native.rmse_pairs(native[name], recommender.svd_u, recommender.svd_v, pairs,
-                                           real, recommender.overall_bias or 0.0,
-                                           recommender.items_bias, recommender.users_bias,
-                                           recommender.min_rating, recommender.max_rating)
+        if hasattr(recommender, '_resident_model'):
+            # the recommender keeps its factors in HBM: only the pairs and the predictions move
+            pred, _ = recommender._resident_model().predict(
+                native[name], pairs, None, recommender.overall_bias or 0.0, recommender.min_rating,
+                recommender.max_rating)
+            all_errors = real - pred
+        else:
+            _, all_errors = _native.rmse_pairs(native[name], recommender.svd_u, recommender.svd_v, pairs,
+                                               real, recommender.overall_bias or 0.0,
+                                               recommender.items_bias, recommender.users_bias,
+                                               recommender.min_rating, recommender.max_rating)
         if verbose:
             for i, (e, r) in enumerate(zip(all_errors, real)):
                 print('Prediction %d: Predicted = %s, Real = %s' % (i, r - e, r))
@@ -56,14 +63,26 @@ def precision_recall(recommender, u_test, nbr_recommendations=5, predictor='pred
         test_sample_dict.setdefault(int(rating[0]), []).append(int(rating[1]))
     precision = recall = 0.0
     users_count = 0
-    for user_index, held_out in test_sample_dict.items():
-        try:
-            recommended_set = set(recommender.find_recommended_items(
-                user_index=user_index, nbr_recommendations=nbr_recommendations, output_label=False,
-                predictor=predictor)[0])
-            users_count += 1
-        except KeyError:
+    users = list(test_sample_dict.keys())
+    if hasattr(recommender, 'find_recommended_items_batch') and len(users) > 1:
+        # one device call for all test users instead of one find_recommended_items call each
+        items, _scores, counts = recommender.find_recommended_items_batch(users, nbr_recommendations, predictor)
+        recommended = [set(int(i) for i in items[j, :counts[j]]) for j in range(len(users))]
+    else:
+        recommended = []
+        for user_index in users:
+            try:
+                recommended.append(set(recommender.find_recommended_items(
+                    user_index=user_index, nbr_recommendations=nbr_recommendations, output_label=False,
+                    predictor=predictor)[0]))
+            except KeyError:
+                recommended.append(None)
+    for user_index, recommended_set in zip(users, recommended):
+        held_out = test_sample_dict[user_index]
+        if recommended_set is None:
             recommended_set = set()
+        else:
+            users_count += 1
         intersection = float(len(recommended_set.intersection(held_out)))
         precision += intersection / nbr_recommendations
         recall += intersection / len(held_out)

@@ -72,16 +72,65 @@ class MFRecommender(BaseRecommender):
         col = self.relationship_matrix_csc[:, user_index].tocoo()
         return np.sort(col.row[col.data != 0]).astype(np.int32)
 
+    # ---- resident model: the factors stay in HBM between calls ------------------------------------
+    def invalidate_model(self):
+        """Forget the device copy of the factors (call after editing svd_u / svd_v / the bias arrays
+        element-wise; retraining and re-assignment are noticed without it)."""
+        self._model_cache = None
+
+    def _resident_model(self):
+        """``mfrec_model`` of the current factors in identity layout, uploaded once and reused by
+        predict / RMSE / top-N calls until the arrays change (their address, shape or sampled
+        contents): ``test_predict_rating(nbr_samples=10)`` or one ``find_recommended_items`` call no
+        longer moves 0.5 GB of factors at Netflix shape."""
+        key = tuple(_native.array_fingerprint(a) for a in (self.svd_u, self.svd_v, self.items_bias, self.users_bias))
+        cached = getattr(self, '_model_cache', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        k, ni = self.svd_u.shape
+        model = _native.Model(k, ni, self.svd_v.shape[1], self.svd_u, self.svd_v, self.items_bias, self.users_bias)
+        self._model_cache = (key, model)
+        return model
+
+    def _rated_csr(self, users):
+        """(indptr, items) of the rows ``relationship_matrix_csc[:, user]`` for a list of users."""
+        m = self.relationship_matrix_csc
+        indptr = np.zeros(len(users) + 1, dtype=np.int64)
+        chunks = []
+        for j, user in enumerate(users):
+            a, b = m.indptr[user], m.indptr[user + 1]
+            rows = m.indices[a:b][m.data[a:b] != 0]
+            chunks.append(np.sort(rows))
+            indptr[j + 1] = indptr[j] + rows.shape[0]
+        flat = np.concatenate(chunks).astype(np.int32) if chunks else np.zeros(0, dtype=np.int32)
+        return indptr, flat
+
     def _topn(self, user_index, n_candidates, nbr_recommendations, predictor):
         rated = self._rated_items(user_index)
         indptr = np.array([0, rated.shape[0]], dtype=np.int64)
-        items, scores, counts = _native.topn(
-            self.NATIVE_PREDICTORS[predictor], self.svd_u, self.svd_v,
-            np.array([user_index], dtype=np.int32), n_candidates, indptr, rated,
-            nbr_recommendations, self.overall_bias or 0.0, self.items_bias, self.users_bias,
-            self.min_rating, self.max_rating)
+        items, scores, counts = self._resident_model().topn(
+            self.NATIVE_PREDICTORS[predictor], np.array([user_index], dtype=np.int32), n_candidates, indptr,
+            rated, nbr_recommendations, self.overall_bias or 0.0, self.min_rating, self.max_rating)
         c = int(counts[0])
         return [int(i) for i in items[0, :c]], [float(s) for s in scores[0, :c]]
+
+    def find_recommended_items_batch(self, user_indices, nbr_recommendations=5, predictor='predict'):
+        """``find_recommended_items`` for MANY users in one device call (the all-users sweep on the
+        tensor cores, ``mfrec_model_topn_sweep``): what ``metrics.precision_recall`` needs -- the
+        reference calls ``find_recommended_items`` once per test user (metrics.py:104-107).  Same
+        per-user results and the same RNG consumption as that loop.  Returns (items int32 [n, N]
+        padded with -1, scores float64 [n, N], counts int32 [n])."""
+        user_indices = np.asarray(user_indices, dtype=np.int32).reshape(-1)
+        self.neighborhood = min([self.neighborhood, self.nbr_items])
+        for _ in range(user_indices.shape[0]):
+            self.get_items_subset(count=self.neighborhood)   # the reference draws (and ignores) a sample per call
+        name = predictor if predictor in self.NATIVE_PREDICTORS else self._predict_alias(predictor)
+        indptr, rated = self._rated_csr(user_indices)
+        items, scores, counts, stats = self._resident_model().topn(
+            self.NATIVE_PREDICTORS[name], user_indices, self.neighborhood, indptr, rated, nbr_recommendations,
+            self.overall_bias or 0.0, self.min_rating, self.max_rating, sweep=True)
+        self.last_topn_stats = stats
+        return items, scores, counts
 
     def find_recommended_items(self, user_index=None, user_label=None, nbr_recommendations=5,
                                output_label=False, predictor='predict'):
@@ -99,25 +148,58 @@ class MFRecommender(BaseRecommender):
             items = [self.items_label[i] for i in items]
         return items, scores
 
-    # ---- item-item similarity in factor space (base.py:1420-1466) ----------------------------------
-    def _similar_rows(self, rows, query, nbr_recommendations, similarity_threshold, similarities_output,
-                      method, transform=None):
-        """Top neighbours of row ``query`` of ``rows`` ([n, d]) by cosine / Pearson similarity.
-        Both are dot products of normalised rows, i.e. one row of a Gram matrix: scored and ranked
-        on the device by the top-N kernel (the query itself is excluded there -- the reference
-        drops the first entry of the sorted list, which is the item itself)."""
-        if method not in ('cosine', 'pearson'):
-            raise NotImplementedError("similarity method %r: only 'cosine' and 'pearson' run on the device" % method)
+    # ---- similarity in factor space (base.py:1294-1348 users, 1420-1466 items) ----------------------
+    def _similarity_model(self, rows, method, tag):
+        """Resident model whose "item" and "user" factors are both the prepared rows, so that one
+        row of the similarity matrix is one top-N query.  cosine / Pearson: rows (centred for Pearson)
+        scaled to unit length, score = dot.  euclidean: item side -2 x_i with bias |x_i|^2, user side
+        x_q with bias |x_q|^2, so the linear predictor gives |x_i - x_q|^2.  Cached per (rows,
+        method): repeated queries upload nothing."""
+        key = (tag, method, _native.array_fingerprint(rows))
+        cache = getattr(self, '_sim_cache', None)
+        if cache is not None and cache[0] == key:
+            return cache[1]
         x = np.array(rows, dtype=np.float64)
-        if method == 'pearson':
-            x = x - x.mean(axis=1, keepdims=True)
-        norm = np.sqrt((x * x).sum(axis=1, keepdims=True))
-        x = np.divide(x, norm, out=np.zeros_like(x), where=norm > 0)
-        xt = np.ascontiguousarray(x.T)                      # [d, n]: "item factors" and "user factors"
-        n = x.shape[0]
+        if method == 'euclidean':
+            sq = (x * x).sum(axis=1)
+            model = _native.Model(x.shape[1], x.shape[0], x.shape[0], np.ascontiguousarray(-2.0 * x.T),
+                                  np.ascontiguousarray(x.T), sq, sq)
+        else:
+            if method == 'pearson':
+                x = x - x.mean(axis=1, keepdims=True)
+            norm = np.sqrt((x * x).sum(axis=1, keepdims=True))
+            x = np.divide(x, norm, out=np.zeros_like(x), where=norm > 0)
+            xt = np.ascontiguousarray(x.T)                  # [d, n]: "item factors" and "user factors"
+            model = _native.Model(x.shape[1], x.shape[0], x.shape[0], xt, xt, None, None)
+        self._sim_cache = (key, model)
+        return model
+
+    def _similar_rows_batch(self, rows, queries, nbr_recommendations, method, tag, skip_first=False):
+        """Neighbours of every row in ``queries``: (ids [n, N], similarities [n, N], counts [n]), most
+        similar first (euclidean: the reference sorts DISTANCES in descending order, i.e. farthest
+        first -- kept).  The query row itself is excluded on the device.  skip_first: drop the head
+        of each list (what the reference's ``similar_items`` does to a euclidean ranking, where the
+        head is not the item itself)."""
+        if method not in ('cosine', 'pearson', 'euclidean'):
+            raise NotImplementedError("similarity method %r: 'cosine', 'pearson' and 'euclidean' run on the device" % method)
+        n = rows.shape[0]
         N = n - 1 if nbr_recommendations == 'All' else int(nbr_recommendations)
-        items, scores, counts = _native.topn('predict_dot', xt, xt, np.array([query], dtype=np.int32), n,
-                                             None, None, max(N, 1))
+        ask = max(min(N + (1 if skip_first else 0), n), 1)
+        model = self._similarity_model(rows, method, tag)
+        q = np.asarray(queries, dtype=np.int32).reshape(-1)
+        predictor = 'predict_linear' if method == 'euclidean' else 'predict_dot'
+        items, scores, counts = model.topn(predictor, q, n, None, None, ask, sweep=q.shape[0] >= 128)[:3]
+        if method == 'euclidean':
+            scores = np.sqrt(np.maximum(scores, 0.0))
+        if skip_first:
+            items, scores, counts = items[:, 1:], scores[:, 1:], np.maximum(counts - 1, 0)
+        return items[:, :N], scores[:, :N], np.minimum(counts, N)
+
+    def _similar_rows(self, rows, query, nbr_recommendations, similarity_threshold, similarities_output,
+                      method, transform=None, tag='rows', skip_first=False):
+        """Top neighbours of row ``query`` of ``rows`` ([n, d]), scored and ranked on the device by the
+        top-N kernel (one row of a Gram matrix)."""
+        items, scores, counts = self._similar_rows_batch(rows, [query], nbr_recommendations, method, tag, skip_first)
         c = int(counts[0])
         ids = [int(i) for i in items[0, :c]]
         sims = [float(v) for v in scores[0, :c]]
@@ -126,13 +208,24 @@ class MFRecommender(BaseRecommender):
         if similarity_threshold:
             keep = [j for j, v in enumerate(sims) if v > similarity_threshold]
             ids, sims = [ids[j] for j in keep], [sims[j] for j in keep]
-        ids, sims = ids[:N], sims[:N]
         return (ids, sims) if similarities_output else ids
 
     def similar_items(self, item_index, nbr_recommendations=2, similarity_threshold=False,
                       similarities_output=False, method='cosine'):
         return self._similar_rows(self.svd_u.T, item_index, nbr_recommendations, similarity_threshold,
-                                  similarities_output, method)
+                                  similarities_output, method, tag='items', skip_first=(method == 'euclidean'))
+
+    def similar_items_batch(self, item_indices, nbr_recommendations=2, method='cosine'):
+        """``similar_items`` for many items in one device call: (ids, similarities, counts)."""
+        return self._similar_rows_batch(self.svd_u.T, item_indices, nbr_recommendations, method, 'items',
+                                        skip_first=(method == 'euclidean'))
+
+    def similar_users(self, user_index, nbr_recommendations=2, similarity_threshold=False,
+                      similarities_output=False, method='pearson'):
+        """User-user neighbours in factor space (base.py:1294-1348; the user itself is removed
+        explicitly there, so no entry is skipped)."""
+        return self._similar_rows(self.svd_v.T[:, 0:self.dimensionality], user_index, nbr_recommendations,
+                                  similarity_threshold, similarities_output, method, tag='users')
 
     def similar_items_by_label(self, item_label, nbr_recommendations=2, similarity_threshold=False,
                                similarities_output=False, method='cosine'):
