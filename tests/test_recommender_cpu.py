@@ -154,13 +154,25 @@ def test_gd_development_trainers_drive_the_native_loops_like_the_reference(monke
 
     def fake_loop(mn, mx, mi, dim, fi, lr, K, u, v, ri, ra, batch, hist, nbu, nbi, verbose=0):
         seen.update(batch=batch, hist_len=hist.shape[0], nbu=nbu, nbi=nbi)
+        seen_order["ri"], seen_order["ra"] = ri.copy(), ra.copy()
         cpu.funk_loop_dev(mn, mx, mi, dim, fi, lr, K, u, v, ri, ra, batch, hist)
 
     monkeypatch.setattr(gd_estimator, "estimator_loop", fake_loop)
+    seen_order = {}
     np.random.seed(5)
     rec = make()
     hist = rec.feature_training_dev()
     assert seen == {"batch": 0, "hist_len": 5 * 3, "nbu": nu, "nbi": ni}
+    # the reference shuffles (RNG consumed) and then overwrites the arrays with ratings_iterator()
+    # order (gradient_descent.py:588-592): the loop trains on the UNSHUFFLED lil -> coo order
+    ri0, ra0 = rec.get_ratings()
+    assert np.array_equal(seen_order["ri"], ri0) and np.array_equal(seen_order["ra"], ra0)
+    np.random.seed(5)
+    np.random.shuffle(np.arange(n))
+    state_after_one_shuffle = np.random.get_state()[1][:4].copy()
+    np.random.seed(5)
+    make().feature_training_dev()
+    assert np.array_equal(np.random.get_state()[1][:4], state_after_one_shuffle)   # exactly one shuffle drawn
     assert hist.shape == (15,) and (hist.reshape(3, 5)[:, :2] > 0).all()
 
     # feature_training_bias: bias statistics first, then the learned-bias loop with K -> K_feature, K2 -> K_bias

@@ -181,4 +181,165 @@ def test_similar_items_match_the_reference_loops():
     assert ids == wi
     np.testing.assert_allclose(sims, ws, rtol=1e-5, atol=1e-6)
     with pytest.raises(NotImplementedError):
-        rec.similar_items(1, method='euclidean')
+        rec.similar_items(1, method='manhattan')
+
+    # euclidean: the reference sorts DISTANCES in descending order and drops the head of the list
+    # (base.py:1434-1466), i.e. it returns the farthest items but one; similar_users removes the
+    # user itself explicitly and keeps the head (base.py:1335)
+    def reference_euclid(rows, q, n, drop_first):
+        d = [float(np.linalg.norm(c - rows[q])) for c in rows]
+        order = sorted(range(len(d)), key=lambda i: d[i], reverse=True)
+        if not drop_first:
+            order = [i for i in order if i != q]
+        order = order[1:n + 1] if drop_first else order[:n]
+        return order, [d[i] for i in order]
+
+    ids, dist = rec.similar_items(17, nbr_recommendations=5, similarities_output=True, method='euclidean')
+    wi, wd = reference_euclid(rec.svd_u.T, 17, 5, True)
+    assert ids == wi
+    np.testing.assert_allclose(dist, wd, rtol=1e-4)
+    ids, dist = rec.similar_users(4, nbr_recommendations=5, similarities_output=True, method='euclidean')
+    wi, wd = reference_euclid(rec.svd_v.T, 4, 5, False)
+    assert ids == wi
+    np.testing.assert_allclose(dist, wd, rtol=1e-4)
+    ids, sims = rec.similar_users(9, nbr_recommendations=4, similarities_output=True)     # Pearson by default
+    wi, ws = reference(rec.svd_v.T, 9, 4, 'pearson')
+    assert ids == wi
+    np.testing.assert_allclose(sims, ws, rtol=1e-5, atol=1e-6)
+    # many queries in one call == one query at a time; the prepared rows are uploaded once
+    bi, bs, bc = rec.similar_items_batch(np.arange(ni), nbr_recommendations=6)
+    for q in (0, 17, 89):
+        assert [int(i) for i in bi[q, :bc[q]]] == rec.similar_items(q, nbr_recommendations=6)
+
+
+def test_resident_model_is_reused_until_the_factors_change():
+    """predict / RMSE / top-N through the reference's entry points keep the factors in HBM
+    (the model is uploaded once, not per call) and notice retraining."""
+    from mfrec_b200 import _native
+    from mfrec_b200.recommendation import KMFRecommender, metrics
+    nu, ni, nnz = 300, 200, 6000
+    rec = KMFRecommender(nu, ni, {'nbr_epochs': 3, 'nbr_features': 16})
+    d = _fill(rec, nu, ni, nnz)
+    np.random.seed(1)
+    rec.train(kernel='train_linear_kernel')
+    u_test = np.c_[d["idx"][:50], d["r"][:50]]
+    m1 = rec._resident_model()
+    metrics.test_predict_rating(rec, u_test, nbr_samples=10, predictor='predict_linear')
+    rec.find_recommended_items(user_index=3, nbr_recommendations=5)
+    assert rec._resident_model() is m1                       # same device copy, nothing re-uploaded
+    np.random.seed(2)
+    rec.train(kernel='train_linear_kernel')                 # new factors (new arrays)
+    m2 = rec._resident_model()
+    assert m2 is not m1
+    rmse, errors = metrics.test_predict_rating(rec, u_test, nbr_samples=10, predictor='predict_linear')
+    want = np.array([row[2] - rec.predict_linear(int(row[1]), int(row[0])) for row in u_test[:10]])
+    np.testing.assert_allclose(errors, want, rtol=1e-5, atol=1e-5)
+    rec.svd_u[:, 7] += 1.0                                    # an element-wise edit: tell the cache
+    rec.invalidate_model()
+    assert rec._resident_model() is not m2
+
+
+def test_precision_recall_is_one_sweep_for_all_users():
+    """metrics.precision_recall (metrics.py:85-130) over >= 10k test users: ONE batched top-N call
+    (launch count independent of the number of users), same numbers as the per-user loop."""
+    from mfrec_b200 import _native
+    from mfrec_b200.recommendation import KMFRecommender, metrics
+    rng = np.random.default_rng(3)
+    nu, ni, k = 12000, 2500, 32
+    d = synth.make_ratings(nu, ni, 200000, seed=4, shuffle_seed=None)
+    rec = KMFRecommender(nu, ni, {'nbr_features': k})
+    rec.set_ratings(d["idx"], d["r"])
+    rec.svd_u = rng.normal(0, 0.3, (k, ni))
+    rec.svd_v = rng.normal(0, 0.3, (k, nu))
+    rec.items_bias, rec.users_bias = rng.normal(0, 0.1, ni), rng.normal(0, 0.1, nu)
+    rec.overall_bias = 3.5
+    rec.relationship_matrix_csc = rec.relationship_matrix.T.tocsc()
+    rec.neighborhood = ni
+    held = np.c_[rng.integers(0, nu, 40000), rng.integers(0, ni, 40000), np.ones(40000)]
+    n_users = np.unique(held[:, 0]).shape[0]
+    assert n_users >= 10000
+    ctx = _native.default_context()
+    rec._resident_model()
+    l0 = ctx.launch_count
+    p, r, f = metrics.precision_recall(rec, held, nbr_recommendations=10)
+    launches = ctx.launch_count - l0
+    assert launches < 200, launches                          # one sweep launch set, not one per user
+    # the same numbers from the reference's per-user loop on a subset of the users
+    some = held[np.isin(held[:, 0], np.unique(held[:, 0])[:40])]
+    items, _s, counts = rec.find_recommended_items_batch(np.unique(some[:, 0]).astype(np.int32), 10)
+    for j, user in enumerate(np.unique(some[:, 0]).astype(int)):
+        one, _ = rec.find_recommended_items(user_index=user, nbr_recommendations=10)
+        assert set(one) == set(int(i) for i in items[j, :counts[j]])   # (fp32 summation order may swap near-ties)
+    assert 0.0 <= p <= 1.0 and 0.0 <= r <= 1.0
+
+
+def test_few_pairs_do_not_upload_the_model():
+    """test_predict_rating's default is 10 samples: with Netflix-sized factors the call must stay
+    under a millisecond-scale budget (resident model), and the one-shot C entry points gather only
+    the rows the pairs name."""
+    import time
+    from mfrec_b200 import _native
+    from mfrec_b200.recommendation import KMFRecommender, metrics
+    from oracle import cpu
+    rng = np.random.default_rng(5)
+    nu, ni, k = synth.SHAPES["netflix"][0], synth.SHAPES["netflix"][1], 128
+    rec = KMFRecommender(4, 6, {'nbr_features': k})
+    rec.svd_u = rng.normal(0, 0.1, (k, ni))
+    rec.svd_v = rng.standard_normal((k, nu)) * 0.1
+    rec.items_bias, rec.users_bias = np.zeros(ni), np.zeros(nu)
+    rec.overall_bias = 0.0
+    pairs = np.c_[rng.integers(0, nu, 10), rng.integers(0, ni, 10)].astype(np.int32)
+    real = rng.integers(1, 6, 10).astype(np.float64)
+    u_test = np.c_[pairs, real]
+    # one-shot C ABI: compact model
+    t0 = time.perf_counter()
+    stats, errs = _native.rmse_pairs("predict_linear", rec.svd_u, rec.svd_v, pairs, real, 0.0, rec.items_bias, rec.users_bias)
+    dt_oneshot = time.perf_counter() - t0
+    want, werr = cpu.rmse_pairs("predict_linear", rec.svd_u, rec.svd_v, pairs, real, 0.0, rec.items_bias, rec.users_bias)
+    np.testing.assert_allclose(errs, werr, rtol=1e-5, atol=1e-6)
+    assert abs(stats[0] - want[0]) <= 1e-5 * want[0]
+    assert dt_oneshot < 0.05, dt_oneshot                     # was a 0.5 GB upload (~40 ms of PCIe alone + conversion)
+    # recommender entry point: resident model, first call uploads, later calls do not
+    metrics.test_predict_rating(rec, u_test, nbr_samples=10, predictor='predict_linear')
+    best = 1e9
+    for _ in range(20):
+        t0 = time.perf_counter()
+        _native_model = rec._resident_model()
+        pred, _ = _native_model.predict("predict_linear", pairs, None, 0.0, 1.0, 5.0)
+        best = min(best, time.perf_counter() - t0)
+    np.testing.assert_allclose(real - pred, werr, rtol=1e-5, atol=1e-6)
+    print("10 pairs on resident Netflix-shaped factors: %.3f ms per call" % (best * 1e3))
+    assert best < 1e-3, best
+
+
+def test_fold_in_leaves_the_frozen_side_bit_identical():
+    """retrain_user (kmf.py:120-131, update_items = 0): svd_u, items... stay exactly as they were,
+    and every other user's row too (a stratified fp32 pass rounded them in place)."""
+    from mfrec_b200.recommendation import KMFRecommender
+    from oracle import cpu
+    nu, ni, nnz = 60, 40, 1500
+    rec = KMFRecommender(nu, ni, {'nbr_epochs': 8, 'nbr_features': 8})
+    d = _fill(rec, nu, ni, nnz)
+    np.random.seed(4)
+    rec.train(kernel='train_linear_kernel')
+    # give the model non-fp32-representable values: any fp32 round trip would change them
+    rec.svd_u += 1e-12
+    rec.svd_v += 1e-12
+    u0, v0, ib0, ub0 = rec.svd_u.copy(), rec.svd_v.copy(), rec.items_bias.copy(), rec.users_bias.copy()
+    idx, r = d["idx"], d["r"]
+    np.random.seed(6)
+    rec.retrain_user(7, idx, r, kernel='train_linear_kernel')
+    assert np.array_equal(rec.svd_u, u0)
+    others = np.arange(nu) != 7
+    assert np.array_equal(rec.svd_v[:, others], v0[:, others])
+    assert np.array_equal(rec.users_bias[others], ub0[others])
+    # and the retrained row is the reference's own result (sequential order, float64)
+    np.random.seed(6)
+    v_ref, ib_ref, ub_ref = v0.copy(), ib0.copy(), ub0.copy()
+    v_ref[:, 7] = np.random.normal(0.0, 0.1, 8)
+    m = idx[:, 0] == 7
+    u_ref = u0.copy()
+    cpu.kmf_train("linear", 8, 8, rec.learning_rate, rec.K_users, rec.K_items, rec.K_bias, u_ref, v_ref,
+                  np.ascontiguousarray(idx[m]), np.ascontiguousarray(r[m]), ib_ref, ub_ref, 1, 0)
+    assert np.array_equal(rec.svd_v[:, 7], v_ref[:, 7])
+    assert np.array_equal(rec.items_bias, ib_ref)
