@@ -10,7 +10,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfrec_b200.so")
+# MFREC_B200_LIB: another build of the same library (kernel experiments; see tools/README.md)
+LIB_PATH = os.environ.get("MFREC_B200_LIB") or os.path.join(_HERE, "libmfrec_b200.so")
 
 OK = 0
 ERR_BAD_ARG, ERR_INDEX, ERR_OOM, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3, -4, -5

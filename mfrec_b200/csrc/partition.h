@@ -152,6 +152,88 @@ inline void partition_ids(const std::vector<int32_t> &deg, const std::vector<int
     for (int64_t id = 0; id < n; ++id) perm[id] = cursor[gof[id]]++;
 }
 
+// Item side with hot-item copies (pack.cu): the ids are VIRTUAL items -- item i appears as
+// vbase[i+1] - vbase[i] copies, each trained on a disjoint share of the item's ratings and merged
+// after every epoch -- and the partition has three levels: real items -> n_slabs slabs (so that
+// all copies of an item travel together and are merged by whichever rank holds the slab),
+// a slab's virtual ids -> blocks_per_slab blocks, a block's ids -> W groups; every level balanced
+// by (degree + 1).  `deg` / `sorted` are over virtual ids (heaviest first), `real_deg` over real
+// items.  With n_slabs == 1 and no copies this is partition_ids.
+inline void partition_items(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted,
+                            const std::vector<int32_t> &real_deg, const std::vector<int32_t> &vbase,
+                            int n_slabs, int blocks_per_slab, int W, std::vector<int32_t> &group_of,
+                            std::vector<int32_t> &perm, std::vector<int32_t> &start, Workspace &ws)
+{
+    const int64_t n = (int64_t)deg.size();
+    const int32_t ni = (int32_t)real_deg.size();
+    const int nblocks = n_slabs * blocks_per_slab;
+    // level 0: real items -> slabs (heaviest first, ties by id: every rank of a ring computes the same)
+    std::vector<int32_t> slab_of_item(ni, 0);
+    if (n_slabs > 1) {
+        std::vector<int32_t> order(ni), dsorted(ni), bin(ni);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return real_deg[a] > real_deg[b]; });
+        for (int32_t j = 0; j < ni; ++j) dsorted[j] = real_deg[order[j]];
+        balanced_bins(dsorted.data(), ni, n_slabs, bin.data());
+        for (int32_t j = 0; j < ni; ++j) slab_of_item[order[j]] = bin[j];
+    }
+    std::vector<int32_t> item_of(n);
+    for (int32_t i = 0; i < ni; ++i)
+        for (int32_t v = vbase[i]; v < vbase[i + 1]; ++v) item_of[v] = i;
+    // level 1: per slab, its virtual ids (still heaviest first) -> blocks
+    ws.deg_sorted.resize(n);
+    ws.block_r.resize(n);
+    int32_t *deg_sorted = ws.deg_sorted.data(), *block_r = ws.block_r.data();
+    for (int64_t j = 0; j < n; ++j) deg_sorted[j] = deg[sorted[j]];
+    {
+        std::vector<std::vector<int64_t>> ranks_of_slab(n_slabs);
+        for (int64_t j = 0; j < n; ++j) ranks_of_slab[slab_of_item[item_of[sorted[j]]]].push_back(j);
+        std::vector<int32_t> d, b;
+        for (int g = 0; g < n_slabs; ++g) {
+            const std::vector<int64_t> &rk = ranks_of_slab[g];
+            d.resize(rk.size());
+            b.resize(rk.size());
+            for (size_t t = 0; t < rk.size(); ++t) d[t] = deg_sorted[rk[t]];
+            if (!rk.empty()) balanced_bins(d.data(), (int64_t)rk.size(), blocks_per_slab, b.data());
+            for (size_t t = 0; t < rk.size(); ++t) block_r[rk[t]] = g * blocks_per_slab + b[t];
+        }
+    }
+    // level 2 and the relabelling: as in partition_ids
+    ws.bstart.assign(nblocks + 1, 0);
+    int64_t *bstart = ws.bstart.data();
+    for (int64_t j = 0; j < n; ++j) bstart[block_r[j] + 1] += 1;
+    for (int b = 0; b < nblocks; ++b) bstart[b + 1] += bstart[b];
+    ws.members.resize(n);
+    ws.mdeg.resize(n);
+    ws.sub.resize(n);
+    int32_t *members = ws.members.data(), *mdeg = ws.mdeg.data(), *sub = ws.sub.data();
+    {
+        ws.cur.assign(ws.bstart.begin(), ws.bstart.end() - 1);
+        int64_t *cur = ws.cur.data();
+        for (int64_t j = 0; j < n; ++j) {
+            const int64_t at = cur[block_r[j]]++;
+            members[at] = (int32_t)j;
+            mdeg[at] = deg_sorted[j];
+        }
+    }
+    group_of.resize(n);
+    int32_t *gof = group_of.data();
+    for (int b = 0; b < nblocks; ++b) {
+        const int64_t a = bstart[b], m = bstart[b + 1] - a;
+        if (m > 0) balanced_bins(mdeg + a, m, W, sub + a);
+        for (int64_t t = a; t < a + m; ++t) gof[sorted[members[t]]] = b * W + sub[t];
+    }
+    const int ng = nblocks * W;
+    ws.count.assign(ng + 1, 0);
+    for (int64_t id = 0; id < n; ++id) ws.count[gof[id] + 1] += 1;
+    start.assign(ng + 1, 0);
+    for (int g = 0; g < ng; ++g) start[g + 1] = start[g] + ws.count[g + 1];
+    ws.cursor.assign(start.begin(), start.end() - 1);
+    int32_t *cursor = ws.cursor.data();
+    perm.resize(n);
+    for (int64_t id = 0; id < n; ++id) perm[id] = cursor[gof[id]]++;
+}
+
 inline void partition_ids(const std::vector<int32_t> &deg, const std::vector<int32_t> &sorted, int nblocks,
                           int W, int n_slabs, std::vector<int32_t> &group_of, std::vector<int32_t> &perm,
                           std::vector<int32_t> &start)

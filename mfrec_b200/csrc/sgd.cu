@@ -388,20 +388,30 @@ sgd_block_kernel(const SgdParams prm)
         }
     };
 
+    // it = (epoch * G + slab step t) * B + sub-epoch s; the slab of a step is (rank + t) mod G.
+    // (epoch, t, s) are carried along instead of being decoded from `it`: a 64-bit division per
+    // sub-epoch and warp cost 5 % of the epoch.
+    int s, t_slab, epoch_rel;
+    {
+        const int64_t e0 = prm.it_begin / steps_per_epoch;
+        const int in0 = (int)(prm.it_begin - e0 * steps_per_epoch);
+        epoch_rel = (int)(e0 - prm.e_base);
+        t_slab = in0 / prm.B;
+        s = in0 - t_slab * prm.B;
+    }
     for (int64_t it = prm.it_begin; it < prm.it_end; ++it) {
         const int step = (int)(it - prm.it_begin);
-        // it = (epoch * G + slab step) * B + sub-epoch; the slab of a step is (rank + step) mod G
-        const int64_t epoch = it / steps_per_epoch;
-        const int in_epoch = (int)(it - epoch * steps_per_epoch);
-        const int s = in_epoch % prm.B;
-        const int slab = (R.rank + in_epoch / prm.B) % prm.G;
-        const int cbl = (rb + s) % prm.B;
+        const int in_epoch = t_slab * prm.B + s;
+        int slab = R.rank + t_slab;
+        if (slab >= prm.G) slab -= prm.G;
+        int cbl = rb + s;
+        if (cbl >= prm.B) cbl -= prm.B;
         const int cbg = slab * prm.B + cbl;
         const int cs = R.col_start[cbg * W];
         const int nq = R.col_start[(cbg + 1) * W] - cs;
         // uses of this column block that must be complete before this one: around a ring it is used
         // in every step of every epoch (by one rank after the other), on one device once per epoch
-        const int tick_need = RING ? (int)it : (int)(epoch - prm.e_base) * prm.B + s;
+        const int tick_need = RING ? (int)it : epoch_rel * prm.B + s;
 
         // this CTA's W*W bucket descriptors (worker-major: index w * W + phase) + end sentinel
         const int64_t bucket_base = (((int64_t)slab * prm.B + rb) * prm.B + cbl) * W * W;
@@ -854,11 +864,17 @@ sgd_block_kernel(const SgdParams prm)
         // now, so that they cross while the CTA waits for its last warp, writes the tile back and
         // waits for the next column block (the stream does not depend on any other CTA).
         chunks_issued = false;
+        // (s, t) of the next iteration
+        int ns = s + 1, nt = t_slab;
+        if (ns == prm.B) {
+            ns = 0;
+            nt = t_slab + 1 == prm.G ? 0 : t_slab + 1;
+        }
         if (it + 1 < prm.it_end) {
-            const int64_t nit = it + 1;
-            const int n_in_epoch = (int)(nit % steps_per_epoch);
-            const int nslab = (R.rank + n_in_epoch / prm.B) % prm.G;
-            const int ncbl = (rb + n_in_epoch % prm.B) % prm.B;
+            int nslab = R.rank + nt;
+            if (nslab >= prm.G) nslab -= prm.G;
+            int ncbl = rb + ns;
+            if (ncbl >= prm.B) ncbl -= prm.B;
             const int64_t nbase = ((((int64_t)nslab * prm.B + rb) * prm.B + ncbl) * W + warp) * W;
             const int64_t nS0 = __ldg(R.bucket_off + nbase);
             const uint32_t nslen = (uint32_t)(__ldg(R.bucket_off + nbase + W) - nS0);
@@ -931,8 +947,11 @@ sgd_block_kernel(const SgdParams prm)
         if (epoch_ends && threadIdx.x == 0) {
             double tot = 0.0;
             for (int w = 0; w < W; ++w) tot += se_s[w];
-            R.se_part[(epoch - prm.e_base) * prm.se_stride + rb] = tot;
+            R.se_part[(int64_t)epoch_rel * prm.se_stride + rb] = tot;
         }
+        if (ns == 0 && nt == 0) epoch_rel += 1;
+        s = ns;
+        t_slab = nt;
         lap(6);
     }
     if constexpr (TIMING) {
