@@ -224,7 +224,12 @@ def run_native(args):
     # ---------------- device-resident arm: K epochs, CUDA events on the library stream ------
     R = _native.Ratings(None, None, ni, nu, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
                         nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
-                        workers=args.workers, n_slabs=(G if G > 1 else 0))
+                        workers=args.workers, n_slabs=(G if G > 1 else 0),
+                        split=_native.SPLIT_OFF if args.no_split else _native.SPLIT_AUTO)
+    _vb, item_rows, n_split = R.copies()
+    hot = {"items_split": n_split, "copies": item_rows - ni + n_split,
+           "what": "items heavier than half a column group are trained as several copies merged after every epoch "
+                   "(DESIGN.md 4.1b); --no-split restores exact sequential equivalence"}
     M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
     layout_desc = ("stratified B=%d W=%d sub-epochs/epoch=%d max_bucket=%d widest_column_block=%d items"
                    % (R.B, R.W, R.launches_per_epoch, R.max_bucket, R.max_cb_items))
@@ -388,12 +393,12 @@ def run_native(args):
     configs_index = {"ml100k": 0, "ml20m": 1, "netflix": 2, "yahoo": 3}[args.workload]
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "%s-shaped %dx%d nnz=%d k=%d (BASELINE configs[%d]%s)"
                                   % (args.workload, nu, ni, nnz, k, configs_index,
                                      "" if nnz == synth.SHAPES[args.workload][2] else ", nnz overridden"),
                       "kernel": "train_linear_kernel", "schedule": layout_desc, "balance": balance,
-                      "quad_types": quad_types,
+                      "quad_types": quad_types, "hot_item_copies": hot,
                       "l2": "inputs (%.1f GB ratings + %.0f MB factors) exceed the 126 MB L2"
                             % (nnz * 12 / 1e9, (nu + ni) * k * 4 / 1e6),
                       "hyper": HP},
@@ -667,6 +672,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10, help="timed end-to-end calls (median reported)")
     ap.add_argument("--long-call-epochs", type=int, default=200,
                     help="epochs of the one long end-to-end call (0 = skip)")
+    ap.add_argument("--no-split", action="store_true", help="pack without hot-item copies (exact sequential equivalence)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the predict / top-N / Funk blocks")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = persistent launches + column blocks over peer memory; nccl = slab send/recv")

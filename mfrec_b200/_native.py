@@ -41,7 +41,7 @@ EXPORTS = (
     "mfrec_model_device_ptrs", "mfrec_sgd_epoch", "mfrec_model_predict",
     "mfrec_ring_create", "mfrec_ring_destroy", "mfrec_ring_handle", "mfrec_ring_connect",
     "mfrec_ring_connect_local", "mfrec_ring_epochs", "mfrec_ring_epochs_one_device", "mfrec_ring_wait",
-    "mfrec_ring_sync_model", "mfrec_model_topn", "mfrec_model_topn_sweep",
+    "mfrec_ring_sync_model", "mfrec_model_topn", "mfrec_model_topn_sweep", "mfrec_ratings_copies",
 )
 
 
@@ -53,10 +53,13 @@ class MfrecError(RuntimeError):
         self.code = code
 
 
+SPLIT_AUTO, SPLIT_ON, SPLIT_OFF = 0, 1, 2
+
+
 class Opts(C.Structure):
     _fields_ = [("schedule", C.c_int32), ("row_blocks", C.c_int32), ("workers", C.c_int32),
                 ("n_slabs", C.c_int32), ("keep_order", C.c_int32), ("k_hint", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("split", C.c_int32), ("split_min_copy", C.c_int32)]
 
 
 _lib = None
@@ -109,9 +112,10 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
-def _opts(schedule=0, row_blocks=0, workers=0, n_slabs=0, keep_order=0, k_hint=0, seed=0):
+def _opts(schedule=0, row_blocks=0, workers=0, n_slabs=0, keep_order=0, k_hint=0, seed=0, split=0,
+          split_min_copy=0):
     return Opts(int(schedule), int(row_blocks), int(workers), int(n_slabs), int(keep_order),
-                int(k_hint), int(seed))
+                int(k_hint), int(seed), int(split), int(split_min_copy))
 
 
 class Context(object):
@@ -436,6 +440,14 @@ class Ratings(object):
         _check(lib().mfrec_ratings_quad_types(self._h, out))
         return dict(generic=int(out[0]), chain=int(out[1]), clean=int(out[2]), independent=int(out[3]))
 
+    def copies(self):
+        """(vbase int32 [ni + 1], item rows in HBM, items trained as more than one copy): item i is
+        trained as vbase[i+1] - vbase[i] copies (hot-item splitting, include/mfrec_b200.h)."""
+        vb = np.zeros(self.ni + 1, dtype=np.int32)
+        cnt = (C.c_int64 * 2)()
+        _check(lib().mfrec_ratings_copies(self._h, _ptr(vb), cnt))
+        return vb, int(cnt[0]), int(cnt[1])
+
     def slab_items(self, slab):
         a, b = C.c_int32(), C.c_int32()
         _check(lib().mfrec_ratings_slab_items(self._h, C.c_int32(slab), C.byref(a), C.byref(b)))
@@ -573,6 +585,16 @@ def _model_topn(self, predictor, users, n_candidates, rated_indptr, rated_items,
 
 
 Model.topn = _model_topn
+
+
+def copy_of_user(users, copies):
+    """Which copy of a split item a user's rating trains: pack.cu's copy_of_user, restated for the
+    tests (uint32 arithmetic)."""
+    x = (np.asarray(users).astype(np.uint64) * np.uint64(0x9e3779b1)) & np.uint64(0xffffffff)
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x85ebca77)) & np.uint64(0xffffffff)
+    x ^= x >> np.uint64(13)
+    return (x % np.asarray(copies).astype(np.uint64)).astype(np.int64)
 
 
 def array_fingerprint(a):

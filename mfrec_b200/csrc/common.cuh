@@ -79,8 +79,15 @@ struct mfrec_ratings {
     float max_abs_rating = 0.f;    // sizes the fixed-point scale of the warp reduction
     int64_t quad_types[4] = {0, 0, 0, 0};  // quads by kQuadGeneric / kQuadChain / kQuadClean / kQuadIndep
     // device
+    int32_t ni_v = 0;              // item ROWS = virtual items (hot items are trained as several copies)
+    int32_t n_hot = 0;             // items with more than one copy
     int32_t *user_perm = nullptr;  // [nu] old -> packed id
-    int32_t *item_perm = nullptr;  // [ni]
+    int32_t *item_perm = nullptr;  // [ni_v] virtual item -> packed row
+    int32_t *item_rows = nullptr;  // [ni] item -> packed row of its first copy
+    int32_t *item_vbase = nullptr; // [ni + 1] first virtual id of each item
+    int32_t *vitem_src = nullptr;  // [ni_v] virtual id -> item
+    int32_t *hot_off = nullptr;    // [n_hot + 1] CSR over hot_rows
+    int32_t *hot_rows = nullptr;   // packed rows of the copies of every split item
     int32_t *col_start = nullptr;  // [G*B*W + 1] packed item id where each column group begins
     PackedRating *packed = nullptr;
     int64_t *bucket_off = nullptr; // [n_buckets] first packed position (multiple of 4)
@@ -89,6 +96,7 @@ struct mfrec_ratings {
     // host mirrors
     std::vector<int32_t> h_row_start;  // [B*W + 1]
     std::vector<int32_t> h_col_start;  // [G*B*W + 1]
+    std::vector<int32_t> h_vbase;      // [ni + 1]
 };
 
 struct mfrec_model {
@@ -96,8 +104,11 @@ struct mfrec_model {
     int device = 0;
     int k = 0, kpad = 0;
     int32_t ni = 0, nu = 0;
-    float *Q = nullptr;   // [ni][kpad]  item factors
-    float *ib = nullptr;  // [ni]
+    int32_t ni_rows = 0;  // rows of Q / ib: ni, or the layout's virtual items (copies of hot items)
+    int32_t n_hot = 0;
+    int32_t *hot_off = nullptr, *hot_rows = nullptr;   // own copies of the layout's merge list
+    float *Q = nullptr;   // [ni_rows][kpad]  item factors
+    float *ib = nullptr;  // [ni_rows]
     float *P = nullptr;   // [nu][kpad]  user factors
     float *ub = nullptr;  // [nu]
     int32_t *user_perm = nullptr;  // own copies (nullptr = identity)
@@ -216,11 +227,22 @@ int mfrec_topn_on_model(mfrec_ctx *ctx, const mfrec_model *M, int predictor, con
 // is in `dst_host`.
 int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
 int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st);
+// n_rows / src_of_dev: write n_rows rows, row j taken from source column src_of_dev[j] (item copies);
+// defaults: one row per source column
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
-                        const int32_t *perm_dev, float *dst_nk, const double *staged_dev = nullptr);
+                        const int32_t *perm_dev, float *dst_nk, const double *staged_dev = nullptr,
+                        int32_t n_rows = -1, const int32_t *src_of_dev = nullptr);
 int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,
                           const int32_t *perm_dev, double *host_kn);
 int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
-                     float *dst, const double *staged_dev = nullptr);
+                     float *dst, const double *staged_dev = nullptr, int32_t n_rows = -1,
+                     const int32_t *src_of_dev = nullptr);
+// sgd.cu: average the copies of every split item whose rows lie in [row_lo, row_hi) and write the
+// mean back to all of them.  ticks != null: first wait until counters [tick_lo, tick_hi) have reached
+// tick_need (a ring rank merges the slab it holds once its neighbour has pushed all of it).
+int mfrec_merge_copies(mfrec_ctx *ctx, float *Q, float *ib, int kpad, const int32_t *hot_off,
+                       const int32_t *hot_rows, int32_t n_hot, int32_t row_lo, int32_t row_hi,
+                       const int32_t *ticks, int32_t tick_lo, int32_t tick_hi, int32_t tick_need,
+                       int32_t *abort_flag, unsigned long long wait_ns);
 int mfrec_download_vec(mfrec_ctx *ctx, const float *src, int32_t n, const int32_t *perm_dev,
                        double *host);

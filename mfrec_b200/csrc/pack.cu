@@ -58,16 +58,32 @@ struct KeyLayout {
     int W, B;
 };
 
+// which copy of a split item a user's rating trains (any fixed function of the user will do: the
+// copies only have to see disjoint, similarly sized shares of the item's ratings)
+__host__ __device__ inline uint32_t copy_of_user(uint32_t user, uint32_t copies)
+{
+    uint32_t x = user * 0x9e3779b1u;
+    x ^= x >> 15;
+    x *= 0x85ebca77u;
+    x ^= x >> 13;
+    return x % copies;
+}
+
 __global__ void key_kernel(const int32_t *__restrict__ idx, int64_t nnz,
                            const int32_t *__restrict__ user_perm,
-                           const int32_t *__restrict__ item_perm,
+                           const int32_t *__restrict__ item_perm,   // [ni_v] virtual item -> packed id
                            const int32_t *__restrict__ user_group,  // packed row group  [nu]
-                           const int32_t *__restrict__ item_group,  // packed col group  [ni]
+                           const int32_t *__restrict__ item_group,  // packed col group  [ni_v]
+                           const int32_t *__restrict__ item_vbase,  // [ni + 1] first virtual id of each item
                            KeyLayout kl, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnz; n += stride) {
-        const int2 ui = reinterpret_cast<const int2 *>(idx)[n];
+        int2 ui = reinterpret_cast<const int2 *>(idx)[n];
+        {
+            const int32_t vb = item_vbase[ui.y], copies = item_vbase[ui.y + 1] - vb;
+            ui.y = vb + (copies > 1 ? (int32_t)copy_of_user((uint32_t)ui.x, (uint32_t)copies) : 0);   // virtual item
+        }
         const int rg = user_group[ui.x], cg = item_group[ui.y];
         const int rb = rg / kl.W, wr = rg % kl.W;
         const int cbg = cg / kl.W, wc = cg % kl.W;   // cbg = slab * B + local column block
@@ -233,7 +249,7 @@ __global__ void degree_key_kernel(const int32_t *__restrict__ deg, int32_t n, ui
 }
 
 struct PackHost {
-    std::vector<int32_t> deg_u, deg_i, ug, up, ig, ip, sorted_u, sorted_i;
+    std::vector<int32_t> deg_u, deg_i, deg_v, ug, up, ig, ip, sorted_u, sorted_i;
     mfrec_part::Workspace ws_u, ws_i;
     // pinned staging for the partition tables: the device PULLS them with a kernel instead of a
     // host -> device copy, which would queue on the copy engine behind the caller's rating values
@@ -295,7 +311,8 @@ extern "C" void mfrec_ratings_destroy(mfrec_ratings *r)
     if (!r) return;
     cudaSetDevice(r->device);
     cudaStream_t st = r->ctx->stream;
-    void *ptrs[] = {r->user_perm, r->item_perm, r->col_start, r->packed, r->bucket_off, r->bucket_cnt, r->order};
+    void *ptrs[] = {r->user_perm, r->item_perm, r->col_start, r->packed, r->bucket_off, r->bucket_cnt, r->order,
+                    r->item_vbase, r->item_rows, r->vitem_src, r->hot_off, r->hot_rows};
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
     mfrec_ctx_release(r->ctx);
@@ -417,15 +434,53 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     R->G = G;
     R->W = W;
     std::vector<int32_t> &ug = H.ug, &up = H.up, &ig = H.ig, &ip = H.ip, &sorted_u = H.sorted_u, &sorted_i = H.sorted_i;
-    if (item_degree)   // the device copy drives the sort: replace it by the global degrees
-        MF_CUDA(ctx, cudaMemcpyAsync(deg_i.p, h_deg_i.data(), (size_t)ni * 4, cudaMemcpyHostToDevice, st));
+    // ---- hot-item copies ------------------------------------------------------
+    // The ratings of one item are a serial chain (its row changes with every update): the hottest
+    // item's ~250k ratings at Netflix shape take as long as everything else together.  An item with
+    // more than tau ratings is therefore trained as several COPIES -- virtual items, each fed the
+    // ratings of a fixed share of the users -- which the scheduler treats like any other item
+    // and which are merged (averaged) after every epoch.  tau = half the weight of an average
+    // column group, so no copy dominates its group; a copy keeps at least `split_min_copy` ratings,
+    // enough for its row to have converged to the same stationary estimate as its siblings
+    // (tools/hot_split_sim.py; tests/test_convergence_gpu.py pins the RMSE against the reference).
+    std::vector<int32_t> &h_vbase = R->h_vbase;
+    h_vbase.assign((size_t)ni + 1, 0);
+    {
+        const int split = opts ? opts->split : 0;
+        const int64_t min_copy = (opts && opts->split_min_copy > 0) ? opts->split_min_copy : 1024;
+        double tot = 0.0;
+        for (int32_t i = 0; i < ni; ++i) tot += (double)h_deg_i[i];
+        const double tau = std::max(1.0, 0.5 * tot / ((double)G * B * W));
+        for (int32_t i = 0; i < ni; ++i) {
+            int64_t copies = 1;
+            if (split != MFREC_SPLIT_OFF && (double)h_deg_i[i] > tau) {
+                copies = (int64_t)ceil((double)h_deg_i[i] / tau);
+                copies = std::min<int64_t>(copies, std::max<int64_t>(1, h_deg_i[i] / min_copy));
+                copies = std::min<int64_t>(copies, 64);
+            }
+            h_vbase[i + 1] = h_vbase[i] + (int32_t)copies;
+        }
+    }
+    const int32_t ni_v = h_vbase[ni];
+    if (ni_v > kIdMask)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: more than 2^27 item rows");
+    R->ni_v = ni_v;
+    std::vector<int32_t> &h_deg_v = H.deg_v;   // degree of every virtual item: an even share of its item's
+    h_deg_v.resize(ni_v);
+    for (int32_t i = 0; i < ni; ++i) {
+        const int32_t c = h_vbase[i + 1] - h_vbase[i];
+        for (int32_t j = 0; j < c; ++j) h_deg_v[h_vbase[i] + j] = h_deg_i[i] / c + (j < h_deg_i[i] % c ? 1 : 0);
+    }
+    DevBuf<int32_t> deg_v;
+    MF_CUDA(ctx, deg_v.alloc(ni_v, ctx->stream));
+    MF_CUDA(ctx, cudaMemcpyAsync(deg_v.p, h_deg_v.data(), (size_t)ni_v * 4, cudaMemcpyHostToDevice, st));
     MF_TRY(sorted_by_degree(ctx, deg_u.p, nu, seed, sorted_u));
-    MF_TRY(sorted_by_degree(ctx, deg_i.p, ni, seed ^ 0x5bd1e995u, sorted_i));
+    MF_TRY(sorted_by_degree(ctx, deg_v.p, ni_v, seed ^ 0x5bd1e995u, sorted_i));
     tr.lap("degree sort");
     for (;;) {
         // items on a second host thread while this one does the users (4 threads for their blocks)
         std::thread items([&] {
-            mfrec_part::partition_ids(h_deg_i, sorted_i, G * B, W, G, ig, ip, R->h_col_start, H.ws_i, 1);
+            mfrec_part::partition_items(h_deg_v, sorted_i, h_deg_i, h_vbase, G, B, W, ig, ip, R->h_col_start, H.ws_i);
         });
         mfrec_part::partition_ids(h_deg_u, sorted_u, B, W, 1, ug, up, R->h_row_start, H.ws_u, 4);
         items.join();
@@ -443,7 +498,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     R->B = B;
     R->n_buckets = (int64_t)G * B * B * W * W;
     KeyLayout kl;
-    kl.bits_i = bits_for(ni);
+    kl.bits_i = bits_for(ni_v);
     kl.bits_u = bits_for(nu);
     kl.bits_b = bits_for(R->n_buckets);
     kl.W = W;
@@ -454,20 +509,44 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
 
     DevBuf<int32_t> d_ug, d_ig;
     MF_CUDA(ctx, d_ug.alloc(nu, ctx->stream));
-    MF_CUDA(ctx, d_ig.alloc(ni, ctx->stream));
+    MF_CUDA(ctx, d_ig.alloc(ni_v, ctx->stream));
+    // item-side tables: item_perm [ni_v] virtual item -> packed row; item_rows [ni] item -> packed row
+    // of its FIRST copy (what readers of the model use: all copies are equal between epochs);
+    // vitem_src [ni_v] the item each virtual id is a copy of; hot_off / hot_rows: CSR of the packed
+    // rows of every split item (the merge kernel's work list)
+    std::vector<int32_t> h_item_rows(ni), h_vsrc(ni_v), h_hot_off(1, 0), h_hot_rows;
+    for (int32_t i = 0; i < ni; ++i) {
+        h_item_rows[i] = ip[h_vbase[i]];
+        for (int32_t v = h_vbase[i]; v < h_vbase[i + 1]; ++v) h_vsrc[v] = i;
+        if (h_vbase[i + 1] - h_vbase[i] > 1) {
+            for (int32_t v = h_vbase[i]; v < h_vbase[i + 1]; ++v) h_hot_rows.push_back(ip[v]);
+            h_hot_off.push_back((int32_t)h_hot_rows.size());
+        }
+    }
+    R->n_hot = (int32_t)h_hot_off.size() - 1;
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->user_perm, ((size_t)nu + 1) * 4, st));
-    MF_CUDA(ctx, cudaMallocAsync((void **)&R->item_perm, ((size_t)ni + 1) * 4, st));
+    MF_CUDA(ctx, cudaMallocAsync((void **)&R->item_perm, ((size_t)ni_v + 1) * 4, st));
+    MF_CUDA(ctx, cudaMallocAsync((void **)&R->item_rows, ((size_t)ni + 1) * 4, st));
+    MF_CUDA(ctx, cudaMallocAsync((void **)&R->item_vbase, ((size_t)ni + 2) * 4, st));
+    MF_CUDA(ctx, cudaMallocAsync((void **)&R->vitem_src, ((size_t)ni_v + 1) * 4, st));
+    MF_CUDA(ctx, cudaMallocAsync((void **)&R->hot_off, h_hot_off.size() * 4, st));
+    MF_CUDA(ctx, cudaMallocAsync((void **)&R->hot_rows, (h_hot_rows.size() + 1) * 4, st));
     MF_CUDA(ctx, cudaMallocAsync((void **)&R->col_start, R->h_col_start.size() * 4, st));
     {
         const size_t ncs = R->h_col_start.size();
         // the previous call's pull kernels have finished: every pack ends with a stream sync
-        MF_CUDA(ctx, H.reserve(2 * (size_t)nu + 2 * (size_t)ni + ncs));
-        struct Seg { const int32_t *src; int32_t *dst; size_t n; } segs[5] = {
+        MF_CUDA(ctx, H.reserve(2 * (size_t)nu + 3 * (size_t)ni_v + 2 * (size_t)ni + 2 + ncs + h_hot_off.size() +
+                               h_hot_rows.size()));
+        struct Seg { const int32_t *src; int32_t *dst; size_t n; } segs[10] = {
             {ug.data(), d_ug.p, (size_t)nu}, {up.data(), R->user_perm, (size_t)nu},
-            {ig.data(), d_ig.p, (size_t)ni}, {ip.data(), R->item_perm, (size_t)ni},
+            {ig.data(), d_ig.p, (size_t)ni_v}, {ip.data(), R->item_perm, (size_t)ni_v},
+            {h_item_rows.data(), R->item_rows, (size_t)ni}, {h_vbase.data(), R->item_vbase, (size_t)ni + 1},
+            {h_vsrc.data(), R->vitem_src, (size_t)ni_v}, {h_hot_off.data(), R->hot_off, h_hot_off.size()},
+            {h_hot_rows.data(), R->hot_rows, h_hot_rows.size()},
             {R->h_col_start.data(), R->col_start, ncs}};
         size_t at = 0;
         for (const Seg &sg : segs) {
+            if (sg.n == 0) continue;
             memcpy(H.pinned + at, sg.src, sg.n * 4);
             pull_host_kernel<<<std::max<int>(1, std::min<int>(grid, (int)((sg.n + 255) / 256))), 256, 0, st>>>(
                 H.pinned + at, sg.dst, (int64_t)sg.n);
@@ -486,7 +565,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     cub::DoubleBuffer<uint64_t> dkeys(keys_a.p, keys_b.p);
     cub::DoubleBuffer<uint32_t> dvals(vals_a.p, vals_b.p);
     if (nnz > 0) {
-        key_kernel<<<grid, 256, 0, st>>>(d_idx, nnz, R->user_perm, R->item_perm, d_ug.p, d_ig.p, kl,
+        key_kernel<<<grid, 256, 0, st>>>(d_idx, nnz, R->user_perm, R->item_perm, d_ug.p, d_ig.p, R->item_vbase, kl,
                                          keys_a.p, vals_a.p);
         MF_LAUNCH_CHECK(ctx);
         size_t tmp_bytes = 0;
@@ -615,7 +694,7 @@ extern "C" int mfrec_ratings_perm(mfrec_ctx *ctx, const mfrec_ratings *r, int32_
     if (!ctx || !r) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_perm: NULL argument");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     if (user_perm) MF_CUDA(ctx, cudaMemcpy(user_perm, r->user_perm, (size_t)r->nu * 4, cudaMemcpyDeviceToHost));
-    if (item_perm) MF_CUDA(ctx, cudaMemcpy(item_perm, r->item_perm, (size_t)r->ni * 4, cudaMemcpyDeviceToHost));
+    if (item_perm) MF_CUDA(ctx, cudaMemcpy(item_perm, r->item_rows, (size_t)r->ni * 4, cudaMemcpyDeviceToHost));
     return MFREC_OK;
 }
 
@@ -661,5 +740,16 @@ extern "C" int mfrec_ratings_slab_items(const mfrec_ratings *r, int32_t slab, in
         return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ratings_slab_items: bad argument");
     *begin = r->h_col_start[(size_t)slab * r->B * r->W];
     *end = r->h_col_start[(size_t)(slab + 1) * r->B * r->W];
+    return MFREC_OK;
+}
+
+extern "C" int mfrec_ratings_copies(const mfrec_ratings *r, int32_t *vbase, int64_t counts[2])
+{
+    if (!r) return mfrec_set_error(nullptr, MFREC_ERR_BAD_ARG, "mfrec_ratings_copies: NULL argument");
+    if (vbase) memcpy(vbase, r->h_vbase.data(), ((size_t)r->ni + 1) * 4);
+    if (counts) {
+        counts[0] = r->ni_v;
+        counts[1] = r->n_hot;
+    }
     return MFREC_OK;
 }

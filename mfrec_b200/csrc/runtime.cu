@@ -142,23 +142,28 @@ extern "C" int64_t mfrec_ctx_launch_count(const mfrec_ctx *ctx) { return ctx ? c
 // contiguous axis of the reference's feature-major arrays), writes along k (the contiguous
 // axis of the device rows), through a padded 32x32 shared tile.
 // ---------------------------------------------------------------------------------------
+// n_rows rows are written; row j comes from source column src_of[j] (null: j).  Copies of a hot
+// item (src_of not injective) sit next to each other, so the reads stay nearly coalesced.
 __global__ void __launch_bounds__(256)
-factor_to_rows_kernel(const double *__restrict__ src_kn, int k, int kpad, int32_t n,
-                      const int32_t *__restrict__ perm, float *__restrict__ dst_nk)
+factor_to_rows_kernel(const double *__restrict__ src_kn, int k, int kpad, int32_t n, int32_t n_rows,
+                      const int32_t *__restrict__ src_of, const int32_t *__restrict__ perm,
+                      float *__restrict__ dst_nk)
 {
     __shared__ float tile[32][33];
     const int64_t j0 = (int64_t)blockIdx.x * 32;
     const int f0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t jc = j0 + tx;
+    const int64_t col = jc < n_rows ? (src_of ? src_of[jc] : jc) : 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int f = f0 + ty + r * 8;
-        const int64_t j = j0 + tx;
         float val = 0.f;
-        if (f < k && j < n) val = (float)src_kn[(int64_t)f * n + j];
+        if (f < k && jc < n_rows) val = (float)src_kn[(int64_t)f * n + col];
         tile[ty + r * 8][tx] = val;
     }
     __syncthreads();
+    n = n_rows;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int64_t j = j0 + ty + r * 8;
@@ -198,11 +203,11 @@ rows_to_factor_kernel(const float *__restrict__ src_nk, int k, int kpad, int32_t
     }
 }
 
-__global__ void vec_to_dev_kernel(const double *__restrict__ src, int32_t n,
+__global__ void vec_to_dev_kernel(const double *__restrict__ src, int32_t n_rows, const int32_t *__restrict__ src_of,
                                   const int32_t *__restrict__ perm, float *__restrict__ dst)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) dst[perm ? perm[j] : j] = (float)src[j];
+    if (j < n_rows) dst[perm ? perm[j] : j] = (float)src[src_of ? src_of[j] : j];
 }
 
 __global__ void vec_from_dev_kernel(const float *__restrict__ src, int32_t n,
@@ -357,11 +362,13 @@ int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t b
 }
 
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
-                        const int32_t *perm_dev, float *dst_nk, const double *staged_dev)
+                        const int32_t *perm_dev, float *dst_nk, const double *staged_dev, int32_t n_rows,
+                        const int32_t *src_of_dev)
 {
     if (n == 0) return MFREC_OK;
+    if (n_rows < 0) n_rows = n;
     if (!host_kn) {
-        MF_CUDA(ctx, cudaMemsetAsync(dst_nk, 0, (size_t)n * kpad * sizeof(float), ctx->stream));
+        MF_CUDA(ctx, cudaMemsetAsync(dst_nk, 0, (size_t)n_rows * kpad * sizeof(float), ctx->stream));
         return MFREC_OK;
     }
     DevBuf<double> stage;
@@ -371,8 +378,8 @@ int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, 
         MF_TRY(mfrec_copy_h2d(ctx, stage.p, host_kn, (size_t)k * n * sizeof(double), ctx->stream));
         src = stage.p;
     }
-    dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
-    factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, perm_dev, dst_nk);
+    dim3 grid((unsigned)ceil_div64(n_rows, 32), (unsigned)(kpad / 32));
+    factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, n_rows, src_of_dev, perm_dev, dst_nk);
     MF_LAUNCH_CHECK(ctx);
     if (!staged_dev) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host buffer is borrowed
     return MFREC_OK;
@@ -392,11 +399,12 @@ int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, 
 }
 
 int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
-                     float *dst, const double *staged_dev)
+                     float *dst, const double *staged_dev, int32_t n_rows, const int32_t *src_of_dev)
 {
     if (n == 0) return MFREC_OK;
+    if (n_rows < 0) n_rows = n;
     if (!host) {
-        MF_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)n * sizeof(float), ctx->stream));
+        MF_CUDA(ctx, cudaMemsetAsync(dst, 0, (size_t)n_rows * sizeof(float), ctx->stream));
         return MFREC_OK;
     }
     DevBuf<double> stage;
@@ -407,7 +415,7 @@ int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_
                                      cudaMemcpyHostToDevice, ctx->stream));
         src = stage.p;
     }
-    vec_to_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(src, n, perm_dev, dst);
+    vec_to_dev_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, ctx->stream>>>(src, n_rows, src_of_dev, perm_dev, dst);
     MF_LAUNCH_CHECK(ctx);
     if (!staged_dev) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MFREC_OK;
@@ -435,7 +443,7 @@ extern "C" void mfrec_model_destroy(mfrec_model *m)
     if (!m) return;
     cudaSetDevice(m->device);
     cudaStream_t st = m->ctx->stream;
-    void *ptrs[] = {m->Q, m->ib, m->P, m->ub, m->user_perm, m->item_perm};
+    void *ptrs[] = {m->Q, m->ib, m->P, m->ub, m->user_perm, m->item_perm, m->hot_off, m->hot_rows};
     for (void *q : ptrs)
         if (q) cudaFreeAsync(q, st);
     mfrec_ctx_release(m->ctx);
@@ -468,6 +476,11 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
     m->kpad = kpad;
     m->ni = ni;
     m->nu = nu;
+    // with a layout the item side has one row per VIRTUAL item (hot items are trained as several
+    // copies, pack.cu); readers address an item through the row of its first copy
+    const int32_t ni_rows = layout ? layout->ni_v : ni;
+    m->ni_rows = ni_rows;
+    m->n_hot = layout ? layout->n_hot : 0;
     int rc = MFREC_OK;
     auto fail = [&](int code) {
         mfrec_model_destroy(m);
@@ -481,17 +494,26 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
                                         "%s -> %s", #call, cudaGetErrorString(e__)));     \
     } while (0)
     // +64 floats of slack so vector loads of the last row never leave the allocation
-    MF_M(cudaMallocAsync((void **)&m->Q, ((size_t)ni * kpad + 64) * sizeof(float), ctx->stream));
+    MF_M(cudaMallocAsync((void **)&m->Q, ((size_t)ni_rows * kpad + 64) * sizeof(float), ctx->stream));
     MF_M(cudaMallocAsync((void **)&m->P, ((size_t)nu * kpad + 64) * sizeof(float), ctx->stream));
-    MF_M(cudaMallocAsync((void **)&m->ib, ((size_t)ni + 64) * sizeof(float), ctx->stream));
+    MF_M(cudaMallocAsync((void **)&m->ib, ((size_t)ni_rows + 64) * sizeof(float), ctx->stream));
     MF_M(cudaMallocAsync((void **)&m->ub, ((size_t)nu + 64) * sizeof(float), ctx->stream));
     if (layout) {
         MF_M(cudaMallocAsync((void **)&m->user_perm, ((size_t)nu + 1) * sizeof(int32_t), ctx->stream));
         MF_M(cudaMallocAsync((void **)&m->item_perm, ((size_t)ni + 1) * sizeof(int32_t), ctx->stream));
         MF_M(cudaMemcpyAsync(m->user_perm, layout->user_perm, (size_t)nu * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, ctx->stream));
-        MF_M(cudaMemcpyAsync(m->item_perm, layout->item_perm, (size_t)ni * sizeof(int32_t),
+        MF_M(cudaMemcpyAsync(m->item_perm, layout->item_rows, (size_t)ni * sizeof(int32_t),
                              cudaMemcpyDeviceToDevice, ctx->stream));
+        if (m->n_hot > 0) {
+            std::vector<int32_t> off((size_t)m->n_hot + 1);
+            MF_M(cudaMemcpyAsync(off.data(), layout->hot_off, off.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MF_M(cudaStreamSynchronize(ctx->stream));
+            MF_M(cudaMallocAsync((void **)&m->hot_off, off.size() * 4, ctx->stream));
+            MF_M(cudaMallocAsync((void **)&m->hot_rows, ((size_t)off.back() + 1) * 4, ctx->stream));
+            MF_M(cudaMemcpyAsync(m->hot_off, layout->hot_off, off.size() * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            MF_M(cudaMemcpyAsync(m->hot_rows, layout->hot_rows, (size_t)off.back() * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     }
 #undef MF_M
     // a one-call drop-in may have staged the float64 arrays on the device already (common.cuh)
@@ -501,9 +523,12 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
         cudaError_t we = cudaStreamWaitEvent(ctx->stream, staged.ready, 0);
         if (we != cudaSuccess) return fail(mfrec_set_error(ctx, MFREC_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(we)));
     }
-    if ((rc = mfrec_upload_factor(ctx, u, k, kpad, ni, m->item_perm, m->Q, staged.u)) != MFREC_OK) return fail(rc);
+    // (item rows: every virtual item takes the column of the item it is a copy of)
+    if ((rc = mfrec_upload_factor(ctx, u, k, kpad, ni, layout ? layout->item_perm : nullptr, m->Q, staged.u, ni_rows,
+                                  layout ? layout->vitem_src : nullptr)) != MFREC_OK) return fail(rc);
     if ((rc = mfrec_upload_factor(ctx, v, k, kpad, nu, m->user_perm, m->P, staged.v)) != MFREC_OK) return fail(rc);
-    if ((rc = mfrec_upload_vec(ctx, items_bias, ni, m->item_perm, m->ib, staged.ib)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_vec(ctx, items_bias, ni, layout ? layout->item_perm : nullptr, m->ib, staged.ib, ni_rows,
+                               layout ? layout->vitem_src : nullptr)) != MFREC_OK) return fail(rc);
     if ((rc = mfrec_upload_vec(ctx, users_bias, nu, m->user_perm, m->ub, staged.ub)) != MFREC_OK) return fail(rc);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess)
@@ -532,7 +557,7 @@ extern "C" int mfrec_model_device_ptrs(const mfrec_model *m, void *ptrs[4], int6
     ptrs[1] = m->ib;
     ptrs[2] = m->P;
     ptrs[3] = m->ub;
-    dims[0] = m->ni;
+    dims[0] = m->ni_rows;   // rows of Q / ib (item copies included): what a slab exchange addresses
     dims[1] = m->nu;
     dims[2] = m->kpad;
     return MFREC_OK;

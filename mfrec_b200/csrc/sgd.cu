@@ -983,6 +983,59 @@ __global__ void __launch_bounds__(1024) se_reduce_kernel(const double *__restric
     if (threadIdx.x == 0) *out = sh[0];
 }
 
+// Hot-item copies (pack.cu): after an epoch every split item's copies are replaced by their mean,
+// rows and biases alike.  One warp per item, fixed summation order: deterministic.  Around a ring
+// the rank that holds the slab merges it, after its neighbour's last pushes have arrived
+// (ticks != null: wait until counters [tick_lo, tick_hi) reach tick_need, system scope).
+__global__ void __launch_bounds__(256)
+merge_copies_kernel(float *__restrict__ Q, float *__restrict__ ib, int kpad, const int32_t *__restrict__ hot_off,
+                    const int32_t *__restrict__ hot_rows, int32_t n_hot, int32_t row_lo, int32_t row_hi,
+                    const int32_t *ticks, int32_t tick_lo, int32_t tick_hi, int32_t tick_need,
+                    int32_t *abort_flag, unsigned long long wait_ns)
+{
+    __shared__ int ok;
+    if (ticks) {
+        if (threadIdx.x == 0) {
+            ok = 1;
+            const unsigned long long t0 = global_ns();
+            for (int32_t c = tick_lo; c < tick_hi && ok; ++c) {
+                uint32_t polls = 0;
+                while (ld_acquire_sys(ticks + c) < tick_need) {
+                    __nanosleep(256);
+                    if ((++polls & 255u) == 0 &&
+                        (*(volatile int32_t *)abort_flag || (wait_ns && global_ns() - t0 > wait_ns))) {
+                        *(volatile int32_t *)abort_flag = 1;
+                        ok = 0;
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (!ok) return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < n_hot; h += warps) {
+        const int32_t a = hot_off[h], b = hot_off[h + 1];
+        const int32_t first = hot_rows[a];
+        if (first < row_lo || first >= row_hi) continue;   // (all copies of an item live in one slab)
+        const float inv = 1.f / (float)(b - a);
+        for (int c = lane; c < kpad; c += 32) {
+            float acc = 0.f;
+            for (int32_t j = a; j < b; ++j) acc += __ldcg(Q + (size_t)hot_rows[j] * kpad + c);
+            acc *= inv;
+            for (int32_t j = a; j < b; ++j) Q[(size_t)hot_rows[j] * kpad + c] = acc;
+        }
+        if (lane == 0) {
+            float acc = 0.f;
+            for (int32_t j = a; j < b; ++j) acc += __ldcg(ib + hot_rows[j]);
+            acc *= inv;
+            for (int32_t j = a; j < b; ++j) ib[hot_rows[j]] = acc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Sequential schedule: the reference's loop verbatim (kmf_train.pyx:241-273), one thread,
 // fp64, round-to-nearest multiplies and adds kept separate (the reference build has no FMA).
@@ -1157,6 +1210,19 @@ int ensure_scratch(mfrec_ctx *ctx, size_t se_doubles, size_t ticks)
 
 }  // namespace
 
+int mfrec_merge_copies(mfrec_ctx *ctx, float *Q, float *ib, int kpad, const int32_t *hot_off,
+                       const int32_t *hot_rows, int32_t n_hot, int32_t row_lo, int32_t row_hi,
+                       const int32_t *ticks, int32_t tick_lo, int32_t tick_hi, int32_t tick_need,
+                       int32_t *abort_flag, unsigned long long wait_ns)
+{
+    if (n_hot <= 0) return MFREC_OK;
+    const int blocks = std::max(1, std::min((n_hot + 7) / 8, ctx->sm_count));
+    merge_copies_kernel<<<blocks, 256, 0, ctx->stream>>>(Q, ib, kpad, hot_off, hot_rows, n_hot, row_lo, row_hi, ticks,
+                                                         tick_lo, tick_hi, tick_need, abort_flag, wait_ns);
+    MF_LAUNCH_CHECK(ctx);
+    return MFREC_OK;
+}
+
 extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_model *m, int kernel,
                                double learning_rate, double K_users, double K_items, double K_bias,
                                int update_users, int update_items, int32_t slab, double *sq_err_out)
@@ -1164,9 +1230,13 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
     if (!ctx || !r || !m) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: NULL argument");
     if (kernel != MFREC_KERNEL_LINEAR && kernel != MFREC_KERNEL_LOGISTIC)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: kernel=%d", kernel);
-    if (m->ni != r->ni || m->nu != r->nu || !m->user_perm)
+    if (m->ni != r->ni || m->nu != r->nu || !m->user_perm || m->ni_rows != r->ni_v)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: model was not created with this layout");
     if (slab >= r->G) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_sgd_epoch: slab=%d of %d", slab, r->G);
+    if (slab >= 0 && r->n_hot > 0)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                               "mfrec_sgd_epoch: a layout with hot-item copies is trained a whole epoch at a time (its copies are "
+                               "merged at the end of the epoch); pack with opts.split = MFREC_SPLIT_OFF to drive single slabs");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
     if (smem > ctx->smem_optin)
@@ -1244,6 +1314,9 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
         se_reduce_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->se_scratch, nparts, sq_err_out);
         MF_LAUNCH_CHECK(ctx);
     }
+    // the epoch is complete: merge the copies of the split items
+    MF_TRY(mfrec_merge_copies(ctx, m->Q, m->ib, m->kpad, m->hot_off, m->hot_rows, m->n_hot, 0, m->ni_rows, nullptr, 0, 0, 0,
+                              nullptr, 0));
     return MFREC_OK;
 }
 
@@ -1298,7 +1371,7 @@ extern "C" int mfrec_ring_create(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_m
     if (world < 1 || rank < 0 || rank >= world || r->G != world)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_create: rank %d of %d, layout has %d slabs (pack with n_slabs = world)",
                                rank, world, r->G);
-    if (m->ni != r->ni || m->nu != r->nu || !m->user_perm)
+    if (m->ni != r->ni || m->nu != r->nu || !m->user_perm || m->ni_rows != r->ni_v)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_create: model was not created with this layout");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     mfrec_ring *g = new (std::nothrow) mfrec_ring();
@@ -1306,9 +1379,9 @@ extern "C" int mfrec_ring_create(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_m
     g->ctx = ctx;
     mfrec_ctx_retain(ctx);
     g->r = r; g->m = m; g->rank = rank; g->world = world;
-    const size_t qbytes = ((size_t)m->ni * m->kpad + 64) * 4;
+    const size_t qbytes = ((size_t)m->ni_rows * m->kpad + 64) * 4;
     g->off_ib = (qbytes + 255) & ~(size_t)255;
-    g->off_ticks = (g->off_ib + ((size_t)m->ni + 64) * 4 + 255) & ~(size_t)255;
+    g->off_ticks = (g->off_ib + ((size_t)m->ni_rows + 64) * 4 + 255) & ~(size_t)255;
     g->off_abort = g->off_ticks + (size_t)r->G * r->B * 4;
     g->bytes = g->off_abort + 256;
     struct Guard { mfrec_ring *g; ~Guard() { if (g) mfrec_ring_destroy(g); } } guard{g};
@@ -1316,8 +1389,8 @@ extern "C" int mfrec_ring_create(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_m
     MF_CUDA(ctx, cudaMalloc((void **)&g->d_rank, sizeof(SgdRank)));
     cudaStream_t st = ctx->stream;
     MF_CUDA(ctx, cudaMemsetAsync(g->block, 0, g->bytes, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(g->block, m->Q, (size_t)m->ni * m->kpad * 4, cudaMemcpyDeviceToDevice, st));
-    MF_CUDA(ctx, cudaMemcpyAsync(g->block + g->off_ib, m->ib, (size_t)m->ni * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(g->block, m->Q, (size_t)m->ni_rows * m->kpad * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(ctx, cudaMemcpyAsync(g->block + g->off_ib, m->ib, (size_t)m->ni_rows * 4, cudaMemcpyDeviceToDevice, st));
     MF_CUDA(ctx, cudaStreamSynchronize(st));
     guard.g = nullptr;
     *out = g;
@@ -1447,33 +1520,52 @@ int ring_launch(mfrec_ring *const *rings, int n_ranks, int kernel, double learni
         MF_CUDA(ctx, cudaMalloc((void **)&g0->se_part, need * 8));
         g0->se_cap = need;
     }
-    std::vector<SgdRank> args(n_ranks);
-    for (int i = 0; i < n_ranks; ++i) ring_rank_args(rings[i], args[i], g0->se_part + (size_t)i * r->B);
-    DevBuf<SgdRank> d_multi;
-    SgdRank *d_args = g0->d_rank;
-    if (n_ranks > 1) {
-        MF_CUDA(ctx, d_multi.alloc(n_ranks, ctx->stream));
-        d_args = d_multi.p;
-    }
-    MF_CUDA(ctx, cudaMemcpyAsync(d_args, args.data(), sizeof(SgdRank) * n_ranks, cudaMemcpyHostToDevice, ctx->stream));
-    SgdParams prm;
-    memset(&prm, 0, sizeof(prm));
-    fill_hyper(prm, r, learning_rate, K_users, K_items, K_bias, 1, 1);
-    float mx = 0.f;
-    for (int i = 0; i < n_ranks; ++i) mx = fmaxf(mx, rings[i]->r->max_abs_rating);
-    (void)mx;   // (every rank holds ratings of the same scale; the scale comes from rank 0's slice)
-    prm.ranks = d_args;
-    prm.B = r->B; prm.W = r->W; prm.G = r->G; prm.world = g0->world;
-    prm.tile_rows = r->max_cb_items;
+    bool hot = false;
+    for (int i = 0; i < n_ranks; ++i) hot = hot || rings[i]->m->n_hot > 0;
+    // layouts with hot-item copies merge them after every epoch: one launch per epoch (each rank's
+    // merge waits for its neighbour's last pushes, so the next launch starts from merged rows)
+    const int per_launch = hot ? 1 : n_epochs;
     const int64_t per_epoch = (int64_t)r->G * r->B;
-    prm.it_begin = g0->epochs_done * per_epoch;
-    prm.it_end = (g0->epochs_done + n_epochs) * per_epoch;
-    prm.e_base = g0->epochs_done;
-    prm.se_stride = grid;
-    prm.wait_ns = ring_wait_ns();
-    MF_TRY(launch_sgd_kpad<false>(ctx, g0->m->kpad, kernel, prm, smem, true, grid, true));
+    DevBuf<SgdRank> d_multi;
+    for (int e0 = 0; e0 < n_epochs; e0 += per_launch) {
+        std::vector<SgdRank> args(n_ranks);
+        for (int i = 0; i < n_ranks; ++i)
+            ring_rank_args(rings[i], args[i], g0->se_part + (size_t)e0 * grid + (size_t)i * r->B);
+        SgdRank *d_args = g0->d_rank;
+        if (n_ranks > 1) {
+            if (!d_multi.p) MF_CUDA(ctx, d_multi.alloc(n_ranks, ctx->stream));
+            d_args = d_multi.p;
+        }
+        MF_CUDA(ctx, cudaMemcpyAsync(d_args, args.data(), sizeof(SgdRank) * n_ranks, cudaMemcpyHostToDevice, ctx->stream));
+        SgdParams prm;
+        memset(&prm, 0, sizeof(prm));
+        fill_hyper(prm, r, learning_rate, K_users, K_items, K_bias, 1, 1);
+        prm.ranks = d_args;
+        prm.B = r->B; prm.W = r->W; prm.G = r->G; prm.world = g0->world;
+        prm.tile_rows = r->max_cb_items;
+        prm.it_begin = g0->epochs_done * per_epoch;
+        prm.it_end = (g0->epochs_done + per_launch) * per_epoch;
+        prm.e_base = g0->epochs_done;
+        prm.se_stride = grid;
+        prm.wait_ns = ring_wait_ns();
+        MF_TRY(launch_sgd_kpad<false>(ctx, g0->m->kpad, kernel, prm, smem, true, grid, true));
+        for (int i = 0; i < n_ranks; ++i) rings[i]->epochs_done += per_launch;
+        if (hot) {
+            for (int i = 0; i < n_ranks; ++i) {
+                mfrec_ring *g = rings[i];
+                // after whole epochs rank i holds slab i: rows [a, b), column blocks [i * B, i * B + B)
+                const int32_t a = g->r->h_col_start[(size_t)g->rank * r->B * r->W];
+                const int32_t b = g->r->h_col_start[(size_t)(g->rank + 1) * r->B * r->W];
+                const bool remote = g->world > 1 && n_ranks == 1;   // the pushes come from another device
+                MF_TRY(mfrec_merge_copies(ctx, ring_Q(g->block), reinterpret_cast<float *>(g->block + g->off_ib), g->m->kpad,
+                                          g->m->hot_off, g->m->hot_rows, g->m->n_hot, a, b,
+                                          remote ? reinterpret_cast<const int32_t *>(g->block + g->off_ticks) : nullptr,
+                                          g->rank * r->B, g->rank * r->B + r->B, (int32_t)(g->epochs_done * per_epoch),
+                                          reinterpret_cast<int32_t *>(g->block + g->off_abort), ring_wait_ns()));
+            }
+        }
+    }
     if (n_ranks > 1) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // d_multi is freed on return
-    for (int i = 0; i < n_ranks; ++i) rings[i]->epochs_done += n_epochs;
     if (sq_err_out) {
         se_reduce_epochs_kernel<<<n_epochs, 256, 0, ctx->stream>>>(g0->se_part, grid, sq_err_out);
         MF_LAUNCH_CHECK(ctx);
@@ -1522,8 +1614,8 @@ extern "C" int mfrec_ring_sync_model(mfrec_ring *g)
     MF_TRY(mfrec_ring_wait(g));
     cudaStream_t st = g->ctx->stream;
     const mfrec_model *m = g->m;
-    MF_CUDA(g->ctx, cudaMemcpyAsync(m->Q, g->block, (size_t)m->ni * m->kpad * 4, cudaMemcpyDeviceToDevice, st));
-    MF_CUDA(g->ctx, cudaMemcpyAsync(m->ib, g->block + g->off_ib, (size_t)m->ni * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(g->ctx, cudaMemcpyAsync(m->Q, g->block, (size_t)m->ni_rows * m->kpad * 4, cudaMemcpyDeviceToDevice, st));
+    MF_CUDA(g->ctx, cudaMemcpyAsync(m->ib, g->block + g->off_ib, (size_t)m->ni_rows * 4, cudaMemcpyDeviceToDevice, st));
     MF_CUDA(g->ctx, cudaStreamSynchronize(st));
     return MFREC_OK;
 }

@@ -234,9 +234,11 @@ def _run_ring(torch, dist, native, args, ctx, rank, world, dev, idx_d, r_d, nu_r
     """Pack this rank's slice, run warm-up + timed epochs; returns a dict of measurements plus the
     objects needed for the end-to-end arm."""
     nnz_r = int(idx_d.shape[0])
+    # (the slab-at-a-time NCCL transport cannot merge item copies at the end of an epoch: no splitting)
+    split = native.SPLIT_OFF if (args.exchange == "nccl" or args.no_split) else native.SPLIT_AUTO
     R = native.Ratings(None, None, ni_tot, nu_r, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
                        nnz=nnz_r, ratings_are_f32=True, k_hint=k, n_slabs=world, row_blocks=args.row_blocks,
-                       workers=args.workers, item_degree=deg_np)
+                       workers=args.workers, item_degree=deg_np, split=split)
     M = native.Model(k, ni_tot, nu_r, u0, v0, None, None, layout=R, ctx=ctx)
     n_ep = args.warmup + args.steps
     se = torch.zeros(n_ep, device=dev, dtype=torch.float64)
@@ -322,7 +324,8 @@ def _e2e_ring(torch, dist, native, args, ctx, rank, world, dev, idx_d, r_d, nu_r
         dist.barrier()
         t0 = time.perf_counter()
         R2 = native.Ratings(idx_n, r_n, ni_tot, nu_r, ctx=ctx, k_hint=k, n_slabs=world, row_blocks=args.row_blocks,
-                            workers=args.workers, item_degree=deg_np)
+                            workers=args.workers, item_degree=deg_np,
+                            split=native.SPLIT_OFF if (args.exchange == "nccl" or args.no_split) else native.SPLIT_AUTO)
         M2 = native.Model(k, ni_tot, nu_r, u0, v0, None, None, layout=R2, ctx=ctx)
         if args.exchange == "peer":
             drv = PeerRingDriver(torch, dist, native, ctx, R2, M2, native.KERNEL_LINEAR, hp, rank, world)
@@ -418,7 +421,8 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
                              % (args.workload, nu, ni, nnz, k, nu * world, ni_tot, nnz_total)),
                 "parallelism": "dsgd ring of %d; item slab = %d rows, %d B per step and rank" % (world, b0 - a0, (b0 - a0) * (4 * kpad + 4)),
                 "exchange": m["exchange"],
-                "schedule": "stratified B=%d W=%d slabs=%d sub-epochs/epoch=%d" % (R.B, R.W, R.G, R.G * R.B),
+                "schedule": "stratified B=%d W=%d slabs=%d sub-epochs/epoch=%d; hot-item copies: %d items trained as %d rows"
+                            % (R.B, R.W, R.G, R.G * R.B, R.copies()[2], R.copies()[1] - ni_tot + R.copies()[2]),
                 "roofline_frac_algorithmic_per_gpu": achieved / peak,
                 "rmse_per_epoch": m["rmse"], "gpu_launches": m["launches_timed"],
                 "launches_warmup": m["launches_warmup"], "clocks": m["clocks"]}

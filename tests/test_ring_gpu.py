@@ -35,7 +35,7 @@ def split_users(idx, nu, world):
     return bounds
 
 
-def build_ranks(native, idx, r, nu, ni, k, world, B, W, u0, v0):
+def build_ranks(native, idx, r, nu, ni, k, world, B, W, u0, v0, **pack_opts):
     """Per rank: (row mask, first user, Ratings, Model, PeerRing), rings connected in-process."""
     bounds = split_users(idx, nu, world)
     deg_i = np.bincount(idx[:, 1], minlength=ni).astype(np.int64)
@@ -46,7 +46,7 @@ def build_ranks(native, idx, r, nu, ni, k, world, B, W, u0, v0):
         idx_w = np.ascontiguousarray(idx[mine])
         idx_w[:, 0] -= a
         R = native.Ratings(idx_w, np.ascontiguousarray(r[mine]), ni, b - a, row_blocks=B, workers=W,
-                           n_slabs=world, keep_order=1, k_hint=k, item_degree=deg_i)
+                           n_slabs=world, keep_order=1, k_hint=k, item_degree=deg_i, **pack_opts)
         M = native.Model(k, ni, b - a, u0, np.ascontiguousarray(v0[:, a:b]), None, None, layout=R)
         ranks.append(dict(mine=np.nonzero(mine)[0], first=a, n=b - a, R=R, M=M))
     for w in range(world):
@@ -108,6 +108,60 @@ def test_ring_on_one_device_matches_oracle_replay(world, B, W, k, kernel, small_
         np.testing.assert_allclose(b_, a_, rtol=2e-4, atol=2e-5)
     # the three epochs' error sums add up to the replay's (one pass over 3 x nnz ratings)
     np.testing.assert_allclose(float(se.sum().item()), float(rm[0]) ** 2 * rep.shape[0], rtol=1e-4)
+
+
+def test_ring_with_hot_item_copies_matches_the_oracle():
+    """Hot-item copies around a ring: the copies of an item live in ONE slab and travel with it; the
+    rank that holds the slab at the end of an epoch averages them.  Oracle: the same block order
+    over the same copies with the same per-epoch merge."""
+    from mfrec_b200 import _native as native
+    from oracle import cpu
+    import torch
+    world, B, W, k = 2, 2, 2, 32
+    nu, ni, nnz = 1200, 12, 9000
+    d = synth.make_ratings(nu, ni, nnz, seed=4, shuffle_seed=5)
+    idx, r = d["idx"], d["r"]
+    u0, v0 = synth.init_factors(nu, ni, k, seed=2)
+    ranks = build_ranks(native, idx, r, nu, ni, k, world, B, W, u0, v0, split=native.SPLIT_ON, split_min_copy=16)
+    vbase, rows, n_hot = ranks[0]["R"].copies()
+    assert n_hot > 0
+    for rk in ranks[1:]:
+        assert np.array_equal(rk["R"].copies()[0], vbase)
+    J = np.diff(vbase)
+    item_of = np.repeat(np.arange(ni), J)
+    rings = [rk["ring"] for rk in ranks]
+    se = torch.zeros(2, device="cuda", dtype=torch.float64)
+    native.ring_epochs_one_device(rings, native.KERNEL_LINEAR, LR, KU, KI, KB, n_epochs=2, sq_err_ptr=se.data_ptr())
+    for g in rings:
+        g.sync_model()
+    # oracle
+    vidx = idx.copy()
+    for rk in ranks:
+        m = rk["mine"]
+        vidx[m, 1] = vbase[idx[m, 1]] + native.copy_of_user(idx[m, 0] - rk["first"], J[idx[m, 1]])   # rank-local user ids
+    per = [[rk["mine"][o] for o in rk["R"].replay_order(by_slab=True)] for rk in ranks]
+    u, ib = u0.copy(), np.zeros(ni)
+    ub = np.zeros(nu)
+    for _ in range(2):
+        uv, ibv = np.ascontiguousarray(u[:, item_of]), ib[item_of].copy()
+        for step in range(world):
+            for w in range(world):
+                o = per[w][(w + step) % world]
+                if o.shape[0]:
+                    cpu.kmf_train("linear", 1, k, LR, KU, KI, KB, uv, v0, np.ascontiguousarray(vidx[o]),
+                                  np.ascontiguousarray(r[o]), ibv, ub)
+        for i in range(ni):
+            u[:, i] = uv[:, vbase[i]:vbase[i + 1]].mean(axis=1)
+            ib[i] = ibv[vbase[i]:vbase[i + 1]].mean()
+    ip0 = ranks[0]["R"].perms()[1]
+    for w, rk in enumerate(ranks):
+        uw, vw, ibw, ubw = rk["M"].read()
+        a, b = rk["R"].slab_items(w)
+        held = (ip0 >= a) & (ip0 < b)
+        assert held.any()
+        np.testing.assert_allclose(uw[:, held], u[:, held], rtol=3e-4, atol=3e-5)
+        np.testing.assert_allclose(ibw[held], ib[held], rtol=3e-4, atol=3e-5)
+        np.testing.assert_allclose(vw, v0[:, rk["first"]:rk["first"] + rk["n"]], rtol=3e-4, atol=3e-5)
 
 
 def test_ring_reports_a_missing_neighbour(small_problem, monkeypatch):

@@ -306,3 +306,57 @@ def test_staged_pageable_copies_change_nothing(native, small_problem, monkeypatc
     got = run()
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
+
+
+def _train_with_copies(cpu, kernel, epochs, k, idx, r, vbase, u0, v0, ib0, ub0):
+    """The oracle under the hot-item-copy semantics: every item trains as its copies (a rating goes
+    to copy hash(user) mod copies), the copies are averaged after each epoch."""
+    from mfrec_b200 import _native
+    ni = u0.shape[1]
+    J = np.diff(vbase)
+    item_of = np.repeat(np.arange(ni), J)
+    vidx = idx.copy()
+    vidx[:, 1] = vbase[idx[:, 1]] + _native.copy_of_user(idx[:, 0], J[idx[:, 1]])
+    u, ib = u0.copy(), ib0.copy()
+    for _ in range(epochs):
+        uv, ibv = np.ascontiguousarray(u[:, item_of]), ib[item_of].copy()
+        cpu.kmf_train(kernel, 1, k, LR, KU, KI, KB, uv, v0, vidx, r, ibv, ub0)
+        for i in range(ni):
+            u[:, i] = uv[:, vbase[i]:vbase[i + 1]].astype(np.float32).mean(axis=1, dtype=np.float32) if J[i] > 1 else uv[:, vbase[i]]
+            ib[i] = ibv[vbase[i]:vbase[i + 1]].mean()
+    return u, v0, ib, ub0
+
+
+@pytest.mark.parametrize("kernel", ["linear", "logistic"])
+@pytest.mark.parametrize("k,nu,ni,nnz,B,W,G", [(128, 500, 8, 3000, 1, 8, 1), (32, 1500, 40, 12000, 2, 4, 1),
+                                                (64, 1200, 30, 9000, 2, 2, 3)])
+def test_hot_item_copies_match_the_oracle_with_the_same_semantics(native, kernel, k, nu, ni, nnz, B, W, G):
+    """Hot-item splitting (pack.cu): items heavier than half a column group train as
+    several copies merged after every epoch.  The GPU result must equal the oracle replaying the
+    same block order over the same copies with the same per-epoch averaging."""
+    from oracle import cpu
+    d = synth.make_ratings(nu, ni, nnz, seed=4, shuffle_seed=5)
+    idx, r = d["idx"], d["r"]
+    R = native.Ratings(idx, r, ni, nu, row_blocks=B, workers=W, n_slabs=G, keep_order=1, k_hint=k,
+                       split=native.SPLIT_ON, split_min_copy=16)
+    vbase, rows, n_hot = R.copies()
+    assert n_hot > 0 and rows == vbase[-1] > ni             # something was split
+    R0 = native.Ratings(idx, r, ni, nu, row_blocks=B, workers=W, n_slabs=G, k_hint=k, split=native.SPLIT_OFF)
+    assert R0.copies()[2] == 0
+    rep = R.replay_order()
+    assert np.array_equal(np.sort(rep), np.arange(nnz))
+    u0, v0, ib0, ub0 = _fresh(nu, ni, k)
+    M = native.Model(k, ni, nu, u0, v0, ib0, ub0, layout=R)
+    kid = {"linear": native.KERNEL_LINEAR, "logistic": native.KERNEL_LOGISTIC}[kernel]
+    for _ in range(3):
+        M.sgd_epoch(R, kid, LR, KU, KI, KB)
+    M.ctx.sync()
+    u1, v1, ib1, ub1 = M.read()
+    ur, vr, ibr, ubr = _train_with_copies(cpu, kernel, 3, k, np.ascontiguousarray(idx[rep]),
+                                          np.ascontiguousarray(r[rep]), vbase, u0, v0, ib0, ub0)
+    for a, b in ((ur, u1), (vr, v1), (ibr, ib1), (ubr, ub1)):
+        np.testing.assert_allclose(b, a, rtol=3e-4, atol=3e-5)
+    # predictions on the model read its merged rows (first copy) through the layout
+    out, _ = M.predict("predict_linear", idx[:500])
+    want = np.einsum("kn,kn->n", ur[:, idx[:500, 1]], vr[:, idx[:500, 0]]) + ibr[idx[:500, 1]] + ubr[idx[:500, 0]]
+    np.testing.assert_allclose(out, want, rtol=1e-3, atol=1e-3)
