@@ -450,7 +450,9 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         const int64_t min_copy = (opts && opts->split_min_copy > 0) ? opts->split_min_copy : 1024;
         double tot = 0.0;
         for (int32_t i = 0; i < ni; ++i) tot += (double)h_deg_i[i];
-        const double tau = std::max(1.0, 0.5 * tot / ((double)G * B * W));
+        static double tau_frac = -1.0;   // MFREC_SPLIT_TAU: experiments with the threshold (fraction of a column group)
+        if (tau_frac < 0) tau_frac = getenv("MFREC_SPLIT_TAU") ? atof(getenv("MFREC_SPLIT_TAU")) : 0.5;
+        const double tau = std::max(1.0, tau_frac * tot / ((double)G * B * W));
         for (int32_t i = 0; i < ni; ++i) {
             int64_t copies = 1;
             if (split != MFREC_SPLIT_OFF && (double)h_deg_i[i] > tau) {

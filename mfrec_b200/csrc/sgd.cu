@@ -1110,8 +1110,12 @@ int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool coo
     // (update_users / update_items = 0) the gated one
     const bool gated = !(prm.update_users && prm.update_items);
     void (*fn)(const SgdParams) = nullptr;
+    // 9..12 warps: 384 threads leave 170 registers per thread (the kernel needs ~165: no spills);
+    // 13..16 warps run the 512-thread build (128 registers, spills)
+    const bool mid = prm.W > 8 && prm.W <= 12 && !gated && !TIMING;
 #define MF_PICK(K)                                                                                     \
-    fn = wide ? (gated ? sgd_block_kernel<E, K, TIMING, 512, true, false> : sgd_block_kernel<E, K, TIMING, 512, false, false>) \
+    fn = mid ? sgd_block_kernel<E, K, false, 384, false, false>                                         \
+       : wide ? (gated ? sgd_block_kernel<E, K, TIMING, 512, true, false> : sgd_block_kernel<E, K, TIMING, 512, false, false>) \
               : (gated ? sgd_block_kernel<E, K, TIMING, 256, true, false> : sgd_block_kernel<E, K, TIMING, 256, false, false>)
 #define MF_PICK_RING(K) \
     fn = wide ? sgd_block_kernel<E, K, false, 512, false, true> : sgd_block_kernel<E, K, false, 256, false, true>

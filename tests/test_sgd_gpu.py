@@ -328,8 +328,8 @@ def _train_with_copies(cpu, kernel, epochs, k, idx, r, vbase, u0, v0, ib0, ub0):
 
 
 @pytest.mark.parametrize("kernel", ["linear", "logistic"])
-@pytest.mark.parametrize("k,nu,ni,nnz,B,W,G", [(128, 500, 8, 3000, 1, 8, 1), (32, 1500, 40, 12000, 2, 4, 1),
-                                                (64, 1200, 30, 9000, 2, 2, 3)])
+@pytest.mark.parametrize("k,nu,ni,nnz,B,W,G", [(128, 500, 8, 3000, 1, 8, 1), (32, 1500, 10, 12000, 2, 4, 1),
+                                                (64, 1200, 12, 9000, 2, 2, 3)])
 def test_hot_item_copies_match_the_oracle_with_the_same_semantics(native, kernel, k, nu, ni, nnz, B, W, G):
     """Hot-item splitting (pack.cu): items heavier than half a column group train as
     several copies merged after every epoch.  The GPU result must equal the oracle replaying the
