@@ -357,7 +357,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     const double want_p = sqrt(nnz_plan / G / 40.0);
     if (W == 0) {
         W = B > 0 ? (int)lround(want_p / B) : (int)lround(want_p / ctx->sm_count);
-        W = std::max(4, std::min(W, 8));
+        W = std::max(4, std::min(W, 10));   // (10 warps: measured best at Netflix shape once hot items are split; 12 is slower)
     }
     if (W > 16) W = 16;  // the SGD kernel is built for at most 16 warps per CTA
     if (B == 0) B = std::max(1, std::min((int)(want_p / W), ctx->sm_count));

@@ -1118,7 +1118,8 @@ int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool coo
        : wide ? (gated ? sgd_block_kernel<E, K, TIMING, 512, true, false> : sgd_block_kernel<E, K, TIMING, 512, false, false>) \
               : (gated ? sgd_block_kernel<E, K, TIMING, 256, true, false> : sgd_block_kernel<E, K, TIMING, 256, false, false>)
 #define MF_PICK_RING(K) \
-    fn = wide ? sgd_block_kernel<E, K, false, 512, false, true> : sgd_block_kernel<E, K, false, 256, false, true>
+    fn = mid ? sgd_block_kernel<E, K, false, 384, false, true>                                           \
+       : wide ? sgd_block_kernel<E, K, false, 512, false, true> : sgd_block_kernel<E, K, false, 256, false, true>
     if (ring) {
         if (gated || TIMING)
             return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "ring launches train both sides and have no timing build");
@@ -1530,17 +1531,22 @@ int ring_launch(mfrec_ring *const *rings, int n_ranks, int kernel, double learni
     // merge waits for its neighbour's last pushes, so the next launch starts from merged rows)
     const int per_launch = hot ? 1 : n_epochs;
     const int64_t per_epoch = (int64_t)r->G * r->B;
+    // Per-rank arguments: uploaded ONCE per call, before the first launch.  (A host -> device copy
+    // between launches would be ordered behind the running kernel, and a process that drives several
+    // devices would block in it before it has launched the neighbours that kernel is waiting for.)
     DevBuf<SgdRank> d_multi;
-    for (int e0 = 0; e0 < n_epochs; e0 += per_launch) {
+    SgdRank *d_args = g0->d_rank;
+    {
         std::vector<SgdRank> args(n_ranks);
-        for (int i = 0; i < n_ranks; ++i)
-            ring_rank_args(rings[i], args[i], g0->se_part + (size_t)e0 * grid + (size_t)i * r->B);
-        SgdRank *d_args = g0->d_rank;
+        for (int i = 0; i < n_ranks; ++i) ring_rank_args(rings[i], args[i], g0->se_part + (size_t)i * r->B);
         if (n_ranks > 1) {
-            if (!d_multi.p) MF_CUDA(ctx, d_multi.alloc(n_ranks, ctx->stream));
+            MF_CUDA(ctx, d_multi.alloc(n_ranks, ctx->stream));
             d_args = d_multi.p;
         }
         MF_CUDA(ctx, cudaMemcpyAsync(d_args, args.data(), sizeof(SgdRank) * n_ranks, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int64_t e_first = g0->epochs_done;
+    for (int e0 = 0; e0 < n_epochs; e0 += per_launch) {
         SgdParams prm;
         memset(&prm, 0, sizeof(prm));
         fill_hyper(prm, r, learning_rate, K_users, K_items, K_bias, 1, 1);
@@ -1549,7 +1555,7 @@ int ring_launch(mfrec_ring *const *rings, int n_ranks, int kernel, double learni
         prm.tile_rows = r->max_cb_items;
         prm.it_begin = g0->epochs_done * per_epoch;
         prm.it_end = (g0->epochs_done + per_launch) * per_epoch;
-        prm.e_base = g0->epochs_done;
+        prm.e_base = e_first;          // sums of epoch e go to se_part[(e - e_first) * grid ...]
         prm.se_stride = grid;
         prm.wait_ns = ring_wait_ns();
         MF_TRY(launch_sgd_kpad<false>(ctx, g0->m->kpad, kernel, prm, smem, true, grid, true));
