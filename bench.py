@@ -685,6 +685,11 @@ def main():
     ap.add_argument("--emulate-slabs", type=int, default=1,
                     help="debug: run one rank's share of a G-GPU ring on one GPU (no exchange)")
     args = ap.parse_args()
+    # exactly ONE line on stdout: libraries print banners there (e.g. "NCCL version ..." at the
+    # first communicator), so everything but the final JSON line is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "native":
         print("bench.py: warmup < 3 breaks the timing rules; using 3", file=sys.stderr)
         args.warmup = 3
@@ -693,7 +698,8 @@ def main():
     else:
         out = run_reference(args) if args.impl == "reference" else run_native(args)
     if out is not None:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -123,6 +123,18 @@ int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k, double le
                     int update_users, int update_items, const mfrec_opts *opts,
                     double *rmse_per_epoch);
 
+/* mfrec_train_kmf over SEVERAL GPUs driven by this process (devices: n_dev distinct CUDA device
+ * ids): the users are cut into n_dev slices of equal rating count, every device packs and trains
+ * its slice, item slabs travel around the DSGD ring below through directly addressed peer
+ * memory; same arrays in and out as mfrec_train_kmf (both sides are trained: update_users =
+ * update_items = 1).  No context argument: it creates one per device for the duration of the
+ * call; errors are reported through mfrec_last_error(NULL).  n_dev == 1 is mfrec_train_kmf. */
+int mfrec_train_kmf_multi(const int32_t *devices, int n_dev, int kernel, int nbr_epochs, int k,
+                          double learning_rate, double K_users, double K_items, double K_bias,
+                          double *u, double *v, const int32_t *ratings_index, const double *ratings,
+                          int64_t nnz, int32_t ni, int32_t nu, double *items_bias,
+                          double *users_bias, const mfrec_opts *opts, double *rmse_per_epoch);
+
 /* Replaces estimator_loop_without_bias / _with_bias / _with_bias_dev
  * (gd_estimator.pyx:691-779, 489-582, 588-685) as called by GDRecommender.feature_training
  * and retrain_user / retrain_item (gradient_descent.py:506-545, 879-905).

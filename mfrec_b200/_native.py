@@ -42,6 +42,7 @@ EXPORTS = (
     "mfrec_ring_create", "mfrec_ring_destroy", "mfrec_ring_handle", "mfrec_ring_connect",
     "mfrec_ring_connect_local", "mfrec_ring_epochs", "mfrec_ring_epochs_one_device", "mfrec_ring_wait",
     "mfrec_ring_sync_model", "mfrec_model_topn", "mfrec_model_topn_sweep", "mfrec_ratings_copies",
+    "mfrec_train_kmf_multi",
 )
 
 
@@ -175,6 +176,21 @@ def train_kmf(kernel, nbr_epochs, k, lr, K_users, K_items, K_bias, u, v, ratings
         _ptr(ratings_index), _ptr(ratings), C.c_int64(ratings.shape[0]), C.c_int32(u.shape[1]),
         C.c_int32(v.shape[1]), _ptr(items_bias), _ptr(users_bias), C.c_int(update_users),
         C.c_int(update_items), C.byref(o), _ptr(rm)), ctx.handle)
+    return rm[:max(int(nbr_epochs), 0)]
+
+
+def train_kmf_multi(devices, kernel, nbr_epochs, k, lr, K_users, K_items, K_bias, u, v, ratings_index, ratings,
+                    items_bias, users_bias, **opts):
+    """train_kmf on several GPUs of this process (DSGD ring over peer memory); in place, returns
+    rmse per epoch."""
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    rm = np.zeros(max(int(nbr_epochs), 1), dtype=np.float64)
+    o = _opts(**opts)
+    _check(lib().mfrec_train_kmf_multi(
+        _ptr(dev), C.c_int(dev.shape[0]), C.c_int(kernel), C.c_int(nbr_epochs), C.c_int(k), C.c_double(lr),
+        C.c_double(K_users), C.c_double(K_items), C.c_double(K_bias), _ptr(u), _ptr(v), _ptr(ratings_index),
+        _ptr(ratings), C.c_int64(ratings.shape[0]), C.c_int32(u.shape[1]), C.c_int32(v.shape[1]),
+        _ptr(items_bias), _ptr(users_bias), C.byref(o), _ptr(rm)), None)
     return rm[:max(int(nbr_epochs), 0)]
 
 

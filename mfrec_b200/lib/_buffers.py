@@ -53,6 +53,9 @@ options = {
     "workers": int(os.environ.get("MFREC_B200_WORKERS", "0")),
     "seed": int(os.environ.get("MFREC_B200_SEED", "0")),
     "device": int(os.environ.get("MFREC_B200_DEVICE", "-1")),
+    # several CUDA devices, e.g. [0, 1, 2, 3] (MFREC_B200_DEVICES=0,1,2,3): train_linear_kernel /
+    # train_logistic_kernel calls that train both sides run as a DSGD ring over them
+    "devices": [int(x) for x in os.environ.get("MFREC_B200_DEVICES", "").split(",") if x.strip()],
 }
 
 

@@ -31,17 +31,29 @@ def _train(kernel, nbr_epochs, dim, learning_rate, K_users, K_items, K_bias, u, 
     if dim == 0 or ratings.shape[0] == 0 or nbr_epochs <= 0:
         last_rmse = np.full(max(nbr_epochs, 0), np.nan)
         return None
+    if len(options["devices"]) > 1 and update_users and update_items and options["schedule"] == "stratified":
+        opts = native_opts()
+        opts.pop("schedule")
+        last_rmse = _native.train_kmf_multi(
+            options["devices"], kernel, nbr_epochs, dim, float(learning_rate), float(K_users), float(K_items),
+            float(K_bias), u[:dim], v[:dim], ratings_index, ratings, items_bias, users_bias, **opts)
+        _print_rmse(kernel, verbose)
+        return None
     ctx = _native.default_context(options["device"])
     last_rmse = _native.train_kmf(
         kernel, nbr_epochs, dim, float(learning_rate), float(K_users), float(K_items),
         float(K_bias), u[:dim], v[:dim], ratings_index, ratings, items_bias, users_bias,
         1 if update_users else 0, 1 if update_items else 0, ctx=ctx, **native_opts())
+    _print_rmse(kernel, verbose)
+    return None
+
+
+def _print_rmse(kernel, verbose):
     if verbose:
         for epoch, rmse in enumerate(last_rmse):
             if kernel == _native.KERNEL_LOGISTIC:
                 print("EPOCHS: " + str(epoch + 1))
             print("RMSE: " + str(rmse) + "\n")
-    return None
 
 
 def train_linear_kernel(nbr_epochs, dim, f_init, learning_rate, learning_rate_users,

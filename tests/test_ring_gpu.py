@@ -201,3 +201,39 @@ def test_ring_over_nvlink(world, tmp_path):
     assert res["ranks_agree_on_layout"]
     assert abs(res["rmse_ring"] - res["rmse_single"]) / res["rmse_single"] <= 0.005
     assert abs(res["probe_ring"] - res["probe_single"]) / res["probe_single"] <= 0.005
+
+
+def test_kmf_recommender_trains_on_all_gpus_of_the_process():
+    """`mfrec.lib.kmf_train.options["devices"] = [0, 1, ...]`: KMFRecommender.train (kmf.py:197-220)
+    runs as a DSGD ring over the GPUs of THIS process (mfrec_train_kmf_multi, peer memory
+    addressed directly).  Same data on one GPU: end-of-training RMSE within 0.5 %; two runs
+    bit-identical."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs 2 GPUs")
+    from mfrec_b200 import _native as native
+    from mfrec.lib import kmf_train
+    nu, ni, nnz, k, epochs = 30000, 2500, 2_000_000, 64, 8
+    d = synth.make_ratings(nu, ni, nnz, seed=0, shuffle_seed=3, probe_frac=0.1)
+    idx, r = d["idx"], d["r"]
+    hp = (0.005, 0.05, 0.05, 0.007)
+
+    def run(devices):
+        u, v = synth.init_factors(nu, ni, k, seed=2)
+        ib, ub = np.zeros(ni), np.zeros(nu)
+        kmf_train.options["devices"] = devices
+        try:
+            kmf_train.train_linear_kernel(epochs, k, 0.1, hp[0], 0.0, 0.0, hp[1], hp[2], hp[3], 0.0, u, v, idx, r, ib, ub)
+        finally:
+            kmf_train.options["devices"] = []
+        probe, _ = native.rmse_pairs("predict_linear", u, v, d["probe_idx"], d["probe_r"], 0.0, ib, ub)
+        return u, v, ib, ub, float(kmf_train.last_rmse[-1]), float(probe[0])
+
+    single = run([])
+    for world in sorted({2, min(n_dev, 4)}):
+        a = run(list(range(world)))
+        b = run(list(range(world)))
+        assert all(np.array_equal(x, y) for x, y in zip(a[:4], b[:4]))
+        assert abs(a[4] - single[4]) / single[4] <= 0.005 and abs(a[5] - single[5]) / single[5] <= 0.005, (a[4:], single[4:])
+        assert np.isfinite(a[0]).all() and np.isfinite(a[1]).all()
