@@ -388,6 +388,7 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
         mfrec_opts o;
         if (opts) o = *opts; else memset(&o, 0, sizeof(o));
         o.n_slabs = 1;
+        o.split = MFREC_SPLIT_OFF;   // bit-exact with the reference order: no item copies here
         o.k_hint = 4;   // the tile holds 16 B per item here, far below any factor-row tile
         mfrec_ratings *R = nullptr;
         MF_TRY(mfrec_ratings_pack(ctx, ratings_index, ratings, 0, 0, nnz, ni, nu, nullptr, &o, &R));

@@ -8,8 +8,10 @@
 //   users  -> B row blocks      x W row groups      (balanced by degree, LPT)
 //   items  -> G slabs x B column blocks x W column groups
 //   bucket(slab g, row block rb, column block cb, phase p, worker w) holds the ratings of
-//   row group (rb, w) x column group (cb, (w + p) mod W), sorted by (user, item) so that
-//   ratings of one user are adjacent (sgd.cu keeps that user's row in registers).
+//   row group (rb, w) x column group (cb, (w + p) mod W).  A bucket is one warp's serial work,
+//   so any order inside it is a legal SGD order: its (item, user)-sorted ratings are dealt
+//   round-robin over its quads (dealt_position), which makes most aligned groups of four
+//   ratings share neither a user nor an item -- sgd.cu applies those side by side.
 //   Buckets are stored in (g, rb, cb, w, p) order -- worker-major, so the W buckets one warp
 //   walks through are one contiguous stream -- each starting on a 16-byte boundary so the
 //   warp can pull the stream through shared memory with cp.async.bulk.
@@ -92,8 +94,8 @@ __global__ void key_kernel(const int32_t *__restrict__ idx, int64_t nnz,
         const uint64_t bucket =
             ((((uint64_t)slab * kl.B + rb) * kl.B + cbl) * kl.W + wr) * kl.W + p;
         keys[n] = (bucket << (kl.bits_u + kl.bits_i)) |
-                  ((uint64_t)(uint32_t)user_perm[ui.x] << kl.bits_i) |
-                  (uint64_t)(uint32_t)item_perm[ui.y];   // bucket, then user, then item
+                  ((uint64_t)(uint32_t)item_perm[ui.y] << kl.bits_u) |
+                  (uint64_t)(uint32_t)user_perm[ui.x];   // bucket, then item, then user
         vals[n] = (uint32_t)n;
     }
 }
@@ -121,6 +123,21 @@ __global__ void pad_counts_kernel(const int32_t *__restrict__ cnt, int64_t nb,
     if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(widest, c);
 }
 
+// Position of the rating with sorted rank l (by item, then user) inside its bucket of n ratings.
+// The bucket is one warp's serial work, so ANY order of its ratings is a legal SGD order; the
+// order that lets the kernel overlap the most is the one where neighbouring ratings share neither
+// user nor item (sgd.cu applies such an aligned group of four side by side).  The item-sorted
+// ratings are therefore dealt round-robin over the bucket's s = n / 4 full quads: rank l goes to
+// quad l mod s, so an item with up to s ratings in the bucket appears at most once per quad
+// (and its users are distinct anyway).  The n mod 4 leftovers close the bucket.
+__device__ __forceinline__ int64_t dealt_position(int64_t l, int64_t n)
+{
+    const int64_t s = n >> 2;
+    return l < 4 * s ? (l % s) * 4 + l / s : l;
+}
+
+constexpr int32_t kTmpFirst = 1 << 30;   // .u, only between gather_kernel and hint_kernel: first rating of its bucket
+
 template <typename RT>
 __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                               int64_t nnz, const RT *__restrict__ ratings, KeyLayout kl,
@@ -134,38 +151,61 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
         const uint64_t key = keys[s];
         const uint32_t src = vals[s];
         const uint64_t b = key >> (kl.bits_u + kl.bits_i);
-        const int64_t dst = pad_off[b] + (s - raw_off[b]);
+        const int64_t first = raw_off[b], n = raw_off[b + 1] - first;
+        const int64_t at = dealt_position(s - first, n);
+        const int64_t dst = pad_off[b] + at;
         PackedRating pr;
-        pr.u = (int32_t)((key >> kl.bits_i) & mask_u);
-        pr.i = (int32_t)(key & mask_i);
+        pr.u = (int32_t)(key & mask_u) | (at == 0 ? kTmpFirst : 0);
+        pr.i = (int32_t)((key >> kl.bits_u) & mask_i);
         pr.r = (float)ratings[src];
-        // hints for the SGD kernel (common.cuh).  The ratings that precede this one in its warp's
-        // stream are its predecessors in sorted order down to the first bucket of the worker
-        // (bucket index rounded down to a multiple of W); looking at 32 RATINGS back covers at
-        // least 32 stream POSITIONS back (padding only adds distance).  Inside a bucket equal
-        // users are adjacent; in the earlier buckets of the window the user is found by bisection
-        // (every bucket is sorted by user).
-        const uint64_t first_b = b - b % (uint64_t)kl.W;
-        const int64_t local = s - raw_off[b];
-        const bool adjacent = local > 0 && (int32_t)((__ldg(keys + s - 1) >> kl.bits_i) & mask_u) == pr.u;
-        bool stale = false;
-        int64_t remaining = 32 - local;
-        for (uint64_t bb = b; !adjacent && !stale && remaining > 0 && bb > first_b;) {
-            --bb;
-            const int64_t end = raw_off[bb + 1], take = min(remaining, end - raw_off[bb]);
-            int64_t lo = end - take, hi = end;
-            while (lo < hi) {   // first rating of the window whose user is >= pr.u
-                const int64_t mid = (lo + hi) >> 1;
-                if ((int32_t)((__ldg(keys + mid) >> kl.bits_i) & mask_u) < pr.u) lo = mid + 1; else hi = mid;
-            }
-            stale = lo < end && (int32_t)((__ldg(keys + lo) >> kl.bits_i) & mask_u) == pr.u;
-            remaining -= take;
-        }
-        if (adjacent) pr.i |= kFlagAdjUser;   // the predecessor's registers hold the latest row
-        if (stale) pr.i |= kFlagStale;
-        if (s > raw_off[b] && (int32_t)(__ldg(keys + s - 1) & mask_i) == (pr.i & kIdMask)) pr.i |= kFlagSameItem;
         packed[dst] = pr;
         if (order) order[dst] = (int64_t)src;
+    }
+}
+
+// Hints for the SGD kernel (common.cuh), from the FINAL order of the packed array.  The prefetch
+// window of a warp reaches back at most 32 stream positions; the entries before a position in
+// memory are its predecessors in its warp's stream, or -- at the head of a stream -- the tail of
+// another worker's stream, whose users (another row group) never match.
+__global__ void hint_kernel(PackedRating *__restrict__ packed, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int32_t u_raw = packed[j].u, i_raw = packed[j].i;
+        if (i_raw & kFlagPad) continue;
+        const int32_t u = u_raw & kIdMask, it = i_raw & kIdMask;
+        const bool first = (u_raw & kTmpFirst) != 0;
+        bool adjacent = false, same_item = false, stale = false;
+        if (!first) {   // (a bucket's ratings are contiguous: j - 1 is its previous rating)
+            adjacent = (packed[j - 1].u & kIdMask) == u;
+            same_item = (packed[j - 1].i & kIdMask) == it;
+        }
+        const int64_t lo = j >= 32 ? j - 32 : 0;
+        for (int64_t q = j - 1; q >= lo && !stale; --q) {
+            if (adjacent && q == j - 1) continue;
+            const int32_t qi = packed[q].i;
+            if (qi & kFlagPad) continue;
+            stale = (packed[q].u & kIdMask) == u;
+        }
+        if (adjacent && stale) {
+            // the user occurs both right before and further back: the registers hold the latest row
+            stale = false;
+        }
+        int32_t flags = 0;
+        if (adjacent) flags |= kFlagAdjUser;
+        if (stale) flags |= kFlagStale;
+        if (same_item) flags |= kFlagSameItem;
+        packed[j].i = i_raw | flags;
+    }
+}
+
+// (second pass: the temporary marker must not reach the kernel)
+__global__ void clear_tmp_kernel(PackedRating *__restrict__ packed, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int32_t u = packed[j].u;
+        if (u & kTmpFirst) packed[j].u = u & ~kTmpFirst;
     }
 }
 
@@ -647,6 +687,10 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         MF_LAUNCH_CHECK(ctx);
     }
     if (packed_len > 0) {
+        hint_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len);
+        MF_LAUNCH_CHECK(ctx);
+        clear_tmp_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len);
+        MF_LAUNCH_CHECK(ctx);
         quad_type_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len / 4, d_stats.p);
         MF_LAUNCH_CHECK(ctx);
         // largest |rating| (sizes the fixed-point reduction scale of the SGD kernel)
