@@ -255,9 +255,7 @@ int mfrec_train_als_wrmf(mfrec_ctx *ctx, int nbr_epochs, int k, double *u, doubl
 /* Ratings layout: COO -> block-bucketed, user-sorted COO in HBM (the GPU counterpart of
  * BaseRecommender.get_ratings, base.py:1115-1131).  Users and items are relabelled so every
  * row group / column group is a contiguous id range; ratings are bucketed by
- * (slab, row block, column block, worker, phase); inside a bucket (one warp's serial work) the
- * (item, user)-sorted ratings are dealt round-robin over aligned groups of four, so that most
- * groups hold four different users and four different items (applied side by side).
+ * (slab, row block, column block, worker, phase) and sorted by (user, item) inside a bucket.
  * Either pointer pair may be device memory (is_device != 0) or host memory.
  * item_degree: nullable int64 [ni], global item degrees when this process holds only a
  * user-slice of the matrix (multi-GPU); NULL = count from the given ratings. */

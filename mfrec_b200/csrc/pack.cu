@@ -8,10 +8,10 @@
 //   users  -> B row blocks      x W row groups      (balanced by degree, LPT)
 //   items  -> G slabs x B column blocks x W column groups
 //   bucket(slab g, row block rb, column block cb, phase p, worker w) holds the ratings of
-//   row group (rb, w) x column group (cb, (w + p) mod W).  A bucket is one warp's serial work,
-//   so any order inside it is a legal SGD order: its (item, user)-sorted ratings are dealt
-//   round-robin over its quads (dealt_position), which makes most aligned groups of four
-//   ratings share neither a user nor an item -- sgd.cu applies those side by side.
+//   row group (rb, w) x column group (cb, (w + p) mod W), sorted by (user, item) so that
+//   ratings of one user are adjacent (sgd.cu keeps that user's row in registers).  (A bucket is
+//   one warp's serial work, so any order inside it is legal; MFREC_PACK_ORDER=dealt is the
+//   experiment that deals item-sorted ratings over the quads instead, see below.)
 //   Buckets are stored in (g, rb, cb, w, p) order -- worker-major, so the W buckets one warp
 //   walks through are one contiguous stream -- each starting on a 16-byte boundary so the
 //   warp can pull the stream through shared memory with cp.async.bulk.
@@ -58,6 +58,7 @@ __global__ void degree_kernel(const int32_t *__restrict__ idx, int64_t nnz, int3
 struct KeyLayout {
     int bits_i, bits_u, bits_b;
     int W, B;
+    int dealt;   // 1: bucket order = (item, user)-sorted ratings dealt over the quads; 0: sorted by (user, item)
 };
 
 // which copy of a split item a user's rating trains (any fixed function of the user will do: the
@@ -93,9 +94,10 @@ __global__ void key_kernel(const int32_t *__restrict__ idx, int64_t nnz,
         const int p = (wc - wr + kl.W) % kl.W;
         const uint64_t bucket =
             ((((uint64_t)slab * kl.B + rb) * kl.B + cbl) * kl.W + wr) * kl.W + p;
+        const uint64_t pu = (uint32_t)user_perm[ui.x], pi = (uint32_t)item_perm[ui.y];
         keys[n] = (bucket << (kl.bits_u + kl.bits_i)) |
-                  ((uint64_t)(uint32_t)item_perm[ui.y] << kl.bits_u) |
-                  (uint64_t)(uint32_t)user_perm[ui.x];   // bucket, then item, then user
+                  (kl.dealt ? (pi << kl.bits_u) | pu     // bucket, then item, then user
+                            : (pu << kl.bits_i) | pi);   // bucket, then user, then item
         vals[n] = (uint32_t)n;
     }
 }
@@ -152,11 +154,11 @@ __global__ void gather_kernel(const uint64_t *__restrict__ keys, const uint32_t 
         const uint32_t src = vals[s];
         const uint64_t b = key >> (kl.bits_u + kl.bits_i);
         const int64_t first = raw_off[b], n = raw_off[b + 1] - first;
-        const int64_t at = dealt_position(s - first, n);
+        const int64_t at = kl.dealt ? dealt_position(s - first, n) : s - first;
         const int64_t dst = pad_off[b] + at;
         PackedRating pr;
-        pr.u = (int32_t)(key & mask_u) | (at == 0 ? kTmpFirst : 0);
-        pr.i = (int32_t)((key >> kl.bits_u) & mask_i);
+        pr.u = (int32_t)(kl.dealt ? key & mask_u : (key >> kl.bits_i) & mask_u) | (at == 0 ? kTmpFirst : 0);
+        pr.i = (int32_t)(kl.dealt ? (key >> kl.bits_u) & mask_i : key & mask_i);
         pr.r = (float)ratings[src];
         packed[dst] = pr;
         if (order) order[dst] = (int64_t)src;
@@ -545,6 +547,16 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     kl.bits_b = bits_for(R->n_buckets);
     kl.W = W;
     kl.B = B;
+    {
+        // Order inside a bucket.  Sorted by (user, item): a user's ratings are adjacent and its row
+        // stays in registers.  "Dealt" (MFREC_PACK_ORDER=dealt): item-sorted ratings dealt round-robin
+        // over the quads -- more independent quads, but a user with several ratings in the bucket
+        // then recurs inside the prefetch window and takes the slow (re-read) path; measured slower
+        // on skewed data (21.4 vs 15.7 ms per epoch at Netflix shape).
+        static int dealt_env = -1;
+        if (dealt_env < 0) dealt_env = (getenv("MFREC_PACK_ORDER") && !strcmp(getenv("MFREC_PACK_ORDER"), "dealt")) ? 1 : 0;
+        kl.dealt = dealt_env;
+    }
     if (kl.bits_i + kl.bits_u + kl.bits_b > 64)
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
                                "mfrec_ratings_pack: sort key needs %d bits", kl.bits_i + kl.bits_u + kl.bits_b);
