@@ -32,7 +32,7 @@ constexpr int32_t kFlagPad = 1 << 30;       // .i : alignment padding, not a rat
 constexpr int kQuadShift = 28;              // .u of the first entry of an aligned quad, 2 bits:
 constexpr int kQuadGeneric = 0;             //      anything (padding, repeated users, ...)
 constexpr int kQuadChain = 1;               //      4 ratings of ONE item, 4 distinct fresh users
-constexpr int kQuadClean = 2;               //      1-4 ratings (then padding), users fresh or equal to their predecessor, any items
+constexpr int kQuadClean = 2;               //      4 ratings, users fresh or equal to their predecessor, any items
 constexpr int kQuadIndep = 3;               //      4 ratings, 4 distinct fresh users, 4 distinct items
 
 struct mfrec_ctx {

@@ -244,11 +244,7 @@ __global__ void quad_type_kernel(PackedRating *__restrict__ packed, int64_t n_qu
         const int i0 = a.y, i1 = b.x, i2 = b.w, i3 = c.z;
         const int any = i0 | i1 | i2 | i3;
         int type = kQuadGeneric;
-        if (!(any & kFlagStale) && (any & kFlagPad) && !(i0 & kFlagPad)) {
-            // the tail of a bucket: 1-3 ratings, then alignment padding.  With small buckets (many
-            // slabs) this is every fourth or fifth quad: it takes the clean path, which skips pads.
-            type = kQuadClean;
-        } else if (!(any & (kFlagPad | kFlagStale))) {
+        if (!(any & (kFlagPad | kFlagStale))) {
             const int m0 = i0 & kIdMask;
             const bool one_item = (i1 & kIdMask) == m0 && (i2 & kIdMask) == m0 && (i3 & kIdMask) == m0;
             type = (one_item && !(any & kFlagAdjUser)) ? kQuadChain : kQuadClean;

@@ -727,10 +727,6 @@ sgd_block_kernel(const SgdParams prm)
             load_quad_p(slot0, p4, b4);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                if (t > 0 && (f4[t] & kFlagPad)) {   // alignment padding closes a bucket (never its first entry)
-                    hook(t);
-                    continue;
-                }
                 if (f4[t] & kFlagAdjUser) {   // same user as the previous rating: its registers, not the ring
 #pragma unroll
                     for (int e = 0; e < E; ++e) p4[t].x[e] = t ? p4[t ? t - 1 : 0].x[e] : cp.x[e];
@@ -748,19 +744,16 @@ sgd_block_kernel(const SgdParams prm)
                 store_p_row(u4[t], p4[t]);
             }
             {
-                uint32_t keep = (f4[3] & kFlagPad) ? 0u : 0x8u;
+                uint32_t keep = 0x8u;
 #pragma unroll
-                for (int t = 0; t < 3; ++t)
-                    keep |= ((f4[t + 1] & kFlagAdjUser) || (t > 0 && (f4[t] & kFlagPad))) ? 0u : (1u << t);
+                for (int t = 0; t < 3; ++t) keep |= (f4[t + 1] & kFlagAdjUser) ? 0u : (1u << t);
                 store_bias_quad(u4, b4, keep);
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) cp.x[e] = p4[3].x[e];
             cbu = b4[3];
-            // (a padded quad ends its bucket: the next rating starts a new one and is never flagged
-            // as a continuation, so the forwarded row is not used)
-            prev_u = (f4[3] & kFlagPad) ? -1 : u4[3];
-            prev_i = (f4[3] & kFlagPad) ? -1 : i4[3];
+            prev_u = u4[3];
+            prev_i = i4[3];
         };
 
         const int32_t done_base = step * W;
