@@ -62,39 +62,90 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region.
+    """SM clocks / throttle reasons sampled DURING the timed region.
 
-    nvidia-smi needs a few hundred ms to produce its first row, so the sampler is started BEFORE the
-    warm-up steps (`with ClockSampler(i) as c:` around warm-up + timed region) and the timed region
-    is marked with c.begin() / c.end(); summary() uses the rows that fall inside the marks.  When
-    the timed region is shorter than the sampling period (multi-GPU runs: a few epochs of ~50 ms)
-    it falls back to the rows of the second before c.end() -- warm-up steps of the same kernel on
-    the same data, i.e. the same load -- and says so in "window"."""
+    Primary source: NVML polled every 5 ms from a thread of this process (`pynvml`: the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints, without
+    the few hundred ms nvidia-smi needs to produce its first row -- the timed region of a default
+    run is ~80 ms).  Fallback: the nvidia-smi recipe of B200_PROFILING.md at 20 ms.  The sampler is
+    started before the warm-up; c.begin() / c.end() mark the timed region and summary() uses the
+    rows inside the marks (if none fell inside: the rows of the second before c.end(), i.e. warm-up
+    steps of the same kernel on the same data, and it says so in "window")."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"))
 
     def __init__(self, device_index):
         self.device_index = device_index
-        self.rows = []
+        self.rows = []          # (t, sm_mhz, max_mhz, [reason names])
         self.proc = None
+        self.t = None
+        self.stop = threading.Event()
         self.t0 = self.t1 = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber: resolve through the PCI bus id of the CUDA device
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(self.device_index).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.device_index).pci_domain_id
+            dev = torch.cuda.get_device_properties(self.device_index).pci_device_id
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (dom, bus, dev)).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
 
     def __enter__(self):
+        try:
+            nv, h = self._nvml_handle()
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+
+            def poll():
+                while not self.stop.is_set():
+                    try:
+                        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        try:
+                            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.monotonic(), sm, mx, [n for b, n in self.REASONS if mask & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.source = "nvml, 5 ms"
+            return self
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + q,
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            self.source = "nvidia-smi -lms 20"
+            time.sleep(0.5)       # its first row takes a few hundred ms
         except OSError:
             self.proc = None
         return self
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.monotonic(), float(r[0]), float(r[1]),
+                                  [n for n, v in zip(names, r[2:6]) if v.lower().startswith("active")]))
+            except (ValueError, IndexError):
+                continue
 
     def begin(self):
         self.t0 = time.monotonic()
@@ -105,32 +156,28 @@ class ClockSampler(object):
     def __exit__(self, *a):
         if self.t1 is None:
             self.t1 = time.monotonic()
+        self.stop.set()
         if self.proc:
             time.sleep(0.1)
             self.proc.terminate()
+        if self.t:
             self.t.join(timeout=2)
 
     def summary(self):
         t0 = self.t0 if self.t0 is not None else -1.0
         t1 = self.t1 if self.t1 is not None else float("inf")
-        inside = [r for (t, r) in self.rows if t0 <= t <= t1]
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
         window = "timed region"
         if not inside:
-            inside = [r for (t, r) in self.rows if t1 - 1.0 <= t <= t1 + 0.05]
+            inside = [r for r in self.rows if t1 - 1.0 <= r[0] <= t1 + 0.05]
             window = "last second before the end of the timed region (warm-up steps of the same load; the timed region is shorter than the sampling period)"
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = [r[1] for r in inside]
+        mx = max([r[2] for r in inside] or [0.0])
+        reasons = set()
         for r in inside:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            reasons.update(r[3])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------

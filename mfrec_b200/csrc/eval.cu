@@ -31,74 +31,110 @@ struct PredParams {
     int32_t *bad;
 };
 
+// A warp scores FOUR pairs per iteration: eight row requests (4 x 512 B at k = 128 for P and Q
+// each) are in flight before the first is consumed -- with one pair at a time the kernel waited
+// out two dependent L2 round trips per pair (ncu r02m: 3.9 G pairs/s, 1.2 TB/s of DRAM) -- and
+// lanes 0..3 finish one pair each (bias lookup, predictor map, error) instead of lane 0 doing all.
 template <int E>
 __global__ void __launch_bounds__(256) predict_kernel(const PredParams p)
 {
     constexpr int KPAD = E * 32;
     constexpr int V = E >= 4 ? 4 : E, NV = E / V;
+    constexpr int G4 = 4;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     double s2 = 0.0, s1 = 0.0, cnt = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; j < p.n; j += warps) {
-        const int2 ui = reinterpret_cast<const int2 *>(p.pairs)[j];
-        if (ui.x < 0 || ui.x >= p.nu || ui.y < 0 || ui.y >= p.ni) {
-            if (lane == 0) atomicOr(p.bad, 1);
-            continue;
+    for (int64_t j0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * G4; j0 < p.n; j0 += warps * G4) {
+        int64_t ur[G4], ir[G4];
+        bool ok[G4];
+#pragma unroll
+        for (int t = 0; t < G4; ++t) {
+            const int64_t j = j0 + t;
+            int2 ui = make_int2(0, 0);
+            ok[t] = j < p.n;
+            if (ok[t]) ui = reinterpret_cast<const int2 *>(p.pairs)[j];
+            if (ok[t] && (ui.x < 0 || ui.x >= p.nu || ui.y < 0 || ui.y >= p.ni)) {
+                if (lane == 0) atomicOr(p.bad, 1);
+                ok[t] = false;
+            }
+            ur[t] = ok[t] ? (p.user_perm ? p.user_perm[ui.x] : ui.x) : 0;
+            ir[t] = ok[t] ? (p.item_perm ? p.item_perm[ui.y] : ui.y) : 0;
         }
-        const int64_t ur = p.user_perm ? p.user_perm[ui.x] : ui.x;
-        const int64_t ir = p.item_perm ? p.item_perm[ui.y] : ui.y;
-        const float *pu = p.P + ur * KPAD, *qi = p.Q + ir * KPAD;
-        float part = 0.f;
+        float part[G4];
+#pragma unroll
+        for (int t = 0; t < G4; ++t) part[t] = 0.f;
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
             const int off = (c * 32 + lane) * V;
             if constexpr (V == 4) {
-                const float4 a = *reinterpret_cast<const float4 *>(pu + off);
-                const float4 b = *reinterpret_cast<const float4 *>(qi + off);
-                part = fmaf(a.x, b.x, part); part = fmaf(a.y, b.y, part);
-                part = fmaf(a.z, b.z, part); part = fmaf(a.w, b.w, part);
+                float4 a[G4], b[G4];
+#pragma unroll
+                for (int t = 0; t < G4; ++t) {
+                    a[t] = *reinterpret_cast<const float4 *>(p.P + ur[t] * KPAD + off);
+                    b[t] = *reinterpret_cast<const float4 *>(p.Q + ir[t] * KPAD + off);
+                }
+#pragma unroll
+                for (int t = 0; t < G4; ++t) {
+                    part[t] = fmaf(a[t].x, b[t].x, part[t]); part[t] = fmaf(a[t].y, b[t].y, part[t]);
+                    part[t] = fmaf(a[t].z, b[t].z, part[t]); part[t] = fmaf(a[t].w, b[t].w, part[t]);
+                }
             } else if constexpr (V == 2) {
-                const float2 a = *reinterpret_cast<const float2 *>(pu + off);
-                const float2 b = *reinterpret_cast<const float2 *>(qi + off);
-                part = fmaf(a.x, b.x, part); part = fmaf(a.y, b.y, part);
+#pragma unroll
+                for (int t = 0; t < G4; ++t) {
+                    const float2 a = *reinterpret_cast<const float2 *>(p.P + ur[t] * KPAD + off);
+                    const float2 b = *reinterpret_cast<const float2 *>(p.Q + ir[t] * KPAD + off);
+                    part[t] = fmaf(a.x, b.x, part[t]); part[t] = fmaf(a.y, b.y, part[t]);
+                }
             } else {
-                part = fmaf(pu[off], qi[off], part);
+#pragma unroll
+                for (int t = 0; t < G4; ++t) part[t] = fmaf(p.P[ur[t] * KPAD + off], p.Q[ir[t] * KPAD + off], part[t]);
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) {
-            const float dot = part;
-            const float bsum = p.ib[ir] + p.ub[ur];
-            float pred;
-            switch (p.predictor) {
-            case MFREC_PRED_GD_RATING: pred = dot + 1.0f; break;
-            case MFREC_PRED_GD_RATING_BIAS: pred = dot + (p.mu + bsum); break;
-            case MFREC_PRED_KMF_LINEAR: pred = dot + bsum; break;
-            case MFREC_PRED_KMF_LOGISTIC:
-                pred = p.min_rating + (1.f / (1.f + expf(-(dot + bsum)))) * (p.max_rating - p.min_rating);
-                break;
-            case MFREC_PRED_KMF_LINEAR_NEG:
-                pred = p.min_rating + (dot + bsum) * (p.max_rating - p.min_rating);
-                break;
-            default: pred = dot; break;
-            }
-            if (p.out) p.out[j] = (double)pred;
-            if (p.real) {
-                const double real = p.real_is_f32 ? (double)((const float *)p.real)[j]
-                                                  : ((const double *)p.real)[j];
-                const double e = real - (double)pred;
-                if (e == e) { s2 += e * e; s1 += fabs(e); cnt += 1.0; }
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int t = 0; t < G4; ++t) part[t] += __shfl_xor_sync(0xffffffffu, part[t], o);
+        if (lane < G4) {
+            // lane t finishes pair t (every lane holds all four sums after the butterfly)
+            const float dot = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+            const bool mine_ok = lane == 0 ? ok[0] : lane == 1 ? ok[1] : lane == 2 ? ok[2] : ok[3];
+            const int64_t u_ = lane == 0 ? ur[0] : lane == 1 ? ur[1] : lane == 2 ? ur[2] : ur[3];
+            const int64_t i_ = lane == 0 ? ir[0] : lane == 1 ? ir[1] : lane == 2 ? ir[2] : ir[3];
+            const int64_t j = j0 + lane;
+            if (mine_ok) {
+                const float bsum = p.ib[i_] + p.ub[u_];
+                float pred;
+                switch (p.predictor) {
+                case MFREC_PRED_GD_RATING: pred = dot + 1.0f; break;
+                case MFREC_PRED_GD_RATING_BIAS: pred = dot + (p.mu + bsum); break;
+                case MFREC_PRED_KMF_LINEAR: pred = dot + bsum; break;
+                case MFREC_PRED_KMF_LOGISTIC:
+                    pred = p.min_rating + (1.f / (1.f + expf(-(dot + bsum)))) * (p.max_rating - p.min_rating);
+                    break;
+                case MFREC_PRED_KMF_LINEAR_NEG:
+                    pred = p.min_rating + (dot + bsum) * (p.max_rating - p.min_rating);
+                    break;
+                default: pred = dot; break;
+                }
+                if (p.out) p.out[j] = (double)pred;
+                if (p.real) {
+                    const double real = p.real_is_f32 ? (double)((const float *)p.real)[j]
+                                                      : ((const double *)p.real)[j];
+                    const double e = real - (double)pred;
+                    if (e == e) { s2 += e * e; s1 += fabs(e); cnt += 1.0; }
+                }
             }
         }
     }
     if (p.part) {
-        __shared__ double sh[8][3];
-        if (lane == 0) { sh[wib][0] = s2; sh[wib][1] = s1; sh[wib][2] = cnt; }
+        // lanes 0..3 of every warp hold partial sums: fixed-order reduction (deterministic)
+        __shared__ double sh[8][4][3];
+        if (lane < G4) { sh[wib][lane][0] = s2; sh[wib][lane][1] = s1; sh[wib][lane][2] = cnt; }
         __syncthreads();
         if (threadIdx.x == 0) {
             double a = 0, b = 0, c = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[w][0]; b += sh[w][1]; c += sh[w][2]; }
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+                for (int l = 0; l < G4; ++l) { a += sh[w][l][0]; b += sh[w][l][1]; c += sh[w][l][2]; }
             p.part[blockIdx.x * 3 + 0] = a;
             p.part[blockIdx.x * 3 + 1] = b;
             p.part[blockIdx.x * 3 + 2] = c;
@@ -270,7 +306,7 @@ extern "C" int mfrec_model_predict(mfrec_ctx *ctx, const mfrec_model *m, int pre
     MF_CUDA(ctx, d_bad.alloc(1, ctx->stream));
     MF_CUDA(ctx, cudaMemsetAsync(d_bad.p, 0, 4, st));
     const int warps_per_block = 8;
-    int grid = (int)std::min<int64_t>(ceil_div64(n, warps_per_block), (int64_t)ctx->sm_count * 16);
+    int grid = (int)std::min<int64_t>(ceil_div64(n, warps_per_block * 4), (int64_t)ctx->sm_count * 16);
     if (stats_out) {
         MF_CUDA(ctx, d_part.alloc((size_t)grid * 3, ctx->stream));
         MF_CUDA(ctx, d_stats.alloc(4, ctx->stream));

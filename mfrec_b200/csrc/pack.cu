@@ -198,16 +198,7 @@ __global__ void hint_kernel(PackedRating *__restrict__ packed, int64_t n)
         if (stale) flags |= kFlagStale;
         if (same_item) flags |= kFlagSameItem;
         packed[j].i = i_raw | flags;
-    }
-}
-
-// (second pass: the temporary marker must not reach the kernel)
-__global__ void clear_tmp_kernel(PackedRating *__restrict__ packed, int64_t n)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const int32_t u = packed[j].u;
-        if (u & kTmpFirst) packed[j].u = u & ~kTmpFirst;
+        if (first) packed[j].u = u;   // the temporary marker must not reach the kernel (readers above mask it off)
     }
 }
 
@@ -517,7 +508,13 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     }
     DevBuf<int32_t> deg_v;
     MF_CUDA(ctx, deg_v.alloc(ni_v, ctx->stream));
-    MF_CUDA(ctx, cudaMemcpyAsync(deg_v.p, h_deg_v.data(), (size_t)ni_v * 4, cudaMemcpyHostToDevice, st));
+    // (pulled from pinned memory by a kernel, like the partition tables below: a host -> device copy
+    // would queue on the copy engine behind the caller's rating values and stall the sort)
+    MF_CUDA(ctx, H.reserve(2 * (size_t)nu + 3 * (size_t)ni_v + 2 * (size_t)ni + 2 + (size_t)G * 148 * 16 + 65536));
+    memcpy(H.pinned, h_deg_v.data(), (size_t)ni_v * 4);
+    pull_host_kernel<<<std::max<int>(1, std::min<int>(ctx->sm_count * 8, (ni_v + 255) / 256)), 256, 0, st>>>(
+        H.pinned, deg_v.p, (int64_t)ni_v);
+    MF_LAUNCH_CHECK(ctx);
     MF_TRY(sorted_by_degree(ctx, deg_u.p, nu, seed, sorted_u));
     MF_TRY(sorted_by_degree(ctx, deg_v.p, ni_v, seed ^ 0x5bd1e995u, sorted_i));
     tr.lap("degree sort");
@@ -700,8 +697,6 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     }
     if (packed_len > 0) {
         hint_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len);
-        MF_LAUNCH_CHECK(ctx);
-        clear_tmp_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len);
         MF_LAUNCH_CHECK(ctx);
         quad_type_kernel<<<grid, 256, 0, st>>>(R->packed, packed_len / 4, d_stats.p);
         MF_LAUNCH_CHECK(ctx);

@@ -26,3 +26,26 @@ def test_traffic_json_points_at_committed_captures():
     for kernel, rec in t.items():
         assert os.path.exists(os.path.join(ROOT, rec["source"])), (kernel, rec["source"])
         assert rec["dram_bytes_per_launch"] > 0
+
+
+def _lookup(d, dotted):
+    for part in dotted.split("."):
+        d = d[int(part)] if isinstance(d, list) else d[part]
+    return d
+
+
+def test_quoted_numbers_match_the_committed_bench_lines():
+    """profiles/README.md carries a table `| file | key | quoted |`: every number DESIGN.md / README.md
+    quote from a bench line is listed there and must equal the committed JSON within the rounding
+    shown (a cited file once held a different experiment than the text claimed)."""
+    with open(os.path.join(ROOT, "profiles", "README.md")) as f:
+        text = f.read()
+    rows = re.findall(r"^\| `(r\d\d[a-z]_[A-Za-z0-9_]+\.json)` \| `([A-Za-z0-9_.]+)` \| ([0-9.eE+-]+) \|", text, re.M)
+    assert len(rows) >= 8, "the quoted-numbers table is missing"
+    for name, key, quoted in rows:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            lines = [ln for ln in f if ln.startswith("{")]
+        got = float(_lookup(json.loads(lines[-1]), key))
+        want = float(quoted)
+        digits = len(quoted.split(".")[1]) if "." in quoted else 0
+        assert abs(got - want) <= 0.6 * 10 ** (-digits) * max(1.0, 0.0) or abs(got - want) <= 0.006 * abs(want), (name, key, got, quoted)
