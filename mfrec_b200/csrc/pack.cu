@@ -369,7 +369,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Tracer tr("pack", st);
-    const int G = (opts && opts->n_slabs > 0) ? opts->n_slabs : 1;
+    int G = (opts && opts->n_slabs > 0) ? opts->n_slabs : 1;
     // Concurrency P = B * W warps needs P^2 buckets per slab.  Measured on the Netflix shape
     // (DESIGN.md section 5): ~40 ratings per bucket is the sweet spot -- a sub-epoch costs a fixed
     // hand-over (ticket, tile load, write-back) plus the spread of its blocks' work, so with G
@@ -477,8 +477,13 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     // enough for its row to have converged to the same stationary estimate as its siblings
     // (tools/hot_split_sim.py; tests/test_convergence_gpu.py pins the RMSE against the reference).
     std::vector<int32_t> &h_vbase = R->h_vbase;
-    h_vbase.assign((size_t)ni + 1, 0);
-    {
+    std::vector<int32_t> &h_deg_v = H.deg_v;   // degree of every virtual item: an even share of its item's
+    DevBuf<int32_t> deg_v;
+    int32_t ni_v = 0;
+    MF_TRY(sorted_by_degree(ctx, deg_u.p, nu, seed, sorted_u));
+    // copies for the current (G, B, W), their degrees, and the virtual items sorted by degree
+    auto plan_copies = [&]() -> int {
+        h_vbase.assign((size_t)ni + 1, 0);
         const int split = opts ? opts->split : 0;
         const int64_t min_copy = (opts && opts->split_min_copy > 0) ? opts->split_min_copy : 1024;
         double tot = 0.0;
@@ -495,29 +500,28 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
             }
             h_vbase[i + 1] = h_vbase[i] + (int32_t)copies;
         }
-    }
-    const int32_t ni_v = h_vbase[ni];
-    if (ni_v > kIdMask)
-        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: more than 2^27 item rows");
-    R->ni_v = ni_v;
-    std::vector<int32_t> &h_deg_v = H.deg_v;   // degree of every virtual item: an even share of its item's
-    h_deg_v.resize(ni_v);
-    for (int32_t i = 0; i < ni; ++i) {
-        const int32_t c = h_vbase[i + 1] - h_vbase[i];
-        for (int32_t j = 0; j < c; ++j) h_deg_v[h_vbase[i] + j] = h_deg_i[i] / c + (j < h_deg_i[i] % c ? 1 : 0);
-    }
-    DevBuf<int32_t> deg_v;
-    MF_CUDA(ctx, deg_v.alloc(ni_v, ctx->stream));
-    // (pulled from pinned memory by a kernel, like the partition tables below: a host -> device copy
-    // would queue on the copy engine behind the caller's rating values and stall the sort)
-    MF_CUDA(ctx, H.reserve(2 * (size_t)nu + 3 * (size_t)ni_v + 2 * (size_t)ni + 2 + (size_t)G * 148 * 16 + 65536));
-    memcpy(H.pinned, h_deg_v.data(), (size_t)ni_v * 4);
-    pull_host_kernel<<<std::max<int>(1, std::min<int>(ctx->sm_count * 8, (ni_v + 255) / 256)), 256, 0, st>>>(
-        H.pinned, deg_v.p, (int64_t)ni_v);
-    MF_LAUNCH_CHECK(ctx);
-    MF_TRY(sorted_by_degree(ctx, deg_u.p, nu, seed, sorted_u));
-    MF_TRY(sorted_by_degree(ctx, deg_v.p, ni_v, seed ^ 0x5bd1e995u, sorted_i));
+        ni_v = h_vbase[ni];
+        if (ni_v > kIdMask)
+            return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ratings_pack: more than 2^27 item rows");
+        h_deg_v.resize(ni_v);
+        for (int32_t i = 0; i < ni; ++i) {
+            const int32_t c = h_vbase[i + 1] - h_vbase[i];
+            for (int32_t j = 0; j < c; ++j) h_deg_v[h_vbase[i] + j] = h_deg_i[i] / c + (j < h_deg_i[i] % c ? 1 : 0);
+        }
+        MF_CUDA(ctx, deg_v.alloc(ni_v, ctx->stream));
+        // (pulled from pinned memory by a kernel, like the partition tables below: a host -> device copy
+        // would queue on the copy engine behind the caller's rating values and stall the sort)
+        MF_CUDA(ctx, H.reserve(2 * (size_t)nu + 3 * (size_t)ni_v + 2 * (size_t)ni + 2 + (size_t)G * 148 * 16 + 65536));
+        memcpy(H.pinned, h_deg_v.data(), (size_t)ni_v * 4);
+        pull_host_kernel<<<std::max<int>(1, std::min<int>(ctx->sm_count * 8, (ni_v + 255) / 256)), 256, 0, st>>>(
+            H.pinned, deg_v.p, (int64_t)ni_v);
+        MF_LAUNCH_CHECK(ctx);
+        return sorted_by_degree(ctx, deg_v.p, ni_v, seed ^ 0x5bd1e995u, sorted_i);
+    };
+    MF_TRY(plan_copies());
     tr.lap("degree sort");
+    // May this call choose the number of slabs?  (A DSGD rank may not: the ring fixes it.)
+    const bool free_slabs = !(opts && opts->n_slabs > 0) && !item_degree;
     for (;;) {
         // items on a second host thread while this one does the users (4 threads for their blocks)
         std::thread items([&] {
@@ -529,12 +533,22 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         for (int cb = 0; cb < G * B; ++cb)
             widest = std::max(widest, R->h_col_start[(cb + 1) * W] - R->h_col_start[cb * W]);
         R->max_cb_items = widest;
-        // the SGD kernel keeps one column block of Q (kpad floats per row) in shared memory;
-        // grow B until the widest block fits
+        // the SGD kernel keeps one column block of Q (kpad floats per row) in shared memory
         const size_t need = mfrec_sgd_smem_bytes(widest, kpad_hint, W);
         if (need <= ctx->smem_optin || widest <= 1 || (opts && opts->row_blocks > 0)) break;
-        B += std::max(1, B / 8);
+        if (free_slabs && B + std::max(1, B / 8) > ctx->sm_count && G < 64) {
+            // A catalogue too large for one tile per SM (Yahoo shape: 136k items): cut the items into
+            // more LOCAL slabs, processed one after the other inside the same persistent launch, rather
+            // than into more column blocks than there are SMs (which would mean one launch per sub-epoch).
+            G += 1;
+            B = std::min(B, ctx->sm_count);
+            MF_TRY(plan_copies());
+            continue;
+        }
+        B += std::max(1, B / 8);   // grow B until the widest block fits
     }
+    R->G = G;
+    R->ni_v = ni_v;
     tr.lap("host LPT partition");
     R->B = B;
     R->n_buckets = (int64_t)G * B * B * W * W;
