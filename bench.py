@@ -359,6 +359,11 @@ def run_native(args):
             secondary["predict_rmse"] = secondary_predict(torch, dev, _native, ctx, M, idx_d, r_d, k, peak)
         except Exception as exc:   # a secondary number never takes the headline down
             secondary["predict_rmse"] = {"error": repr(exc)}
+        try:
+            secondary["storage_16bit"] = secondary_storage(torch, dev, _native, ctx, idx_d, r_d, nu, ni, nnz, k, u0, v0,
+                                                           args, rmse_curve, ms_per_step, peak)
+        except Exception as exc:
+            secondary["storage_16bit"] = {"error": repr(exc)}
 
     # ---------------- end-to-end arm: the public drop-in call with host buffers -----------------
     e2e = None
@@ -491,6 +496,47 @@ def secondary_predict(torch, dev, _native, ctx, M, idx_d, r_d, k, peak):
                     "each call includes its result read-back and stream sync",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_pair": bpp, "kernel": "predict_kernel"}}
+
+
+def secondary_storage(torch, dev, _native, ctx, idx_d, r_d, nu, ni, nnz, k, u0, v0, args, f32_curve, f32_ms, peak):
+    """The headline workload again with the user-factor rows kept as fp16 / bf16 in HBM
+    (mfrec_opts.storage; float32 arithmetic): the same warm-up + timed epochs, the running RMSE
+    of the last epoch beside the float32 run's.  Beside, never instead of, the float32 line."""
+    out = {"what": "same ratings, seeds, epochs and hyper-parameters as the headline; only the storage type of "
+                   "the user-factor rows P (96 %% of the model bytes) changes; arithmetic is float32",
+           "f32": {"ms_per_epoch": f32_ms, "rmse_last_epoch": f32_curve[-1],
+                   "model_bytes": (nu + ni) * (k * 4 + 4)}}
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    for name, code in (("f16", _native.STORAGE_F16), ("bf16", _native.STORAGE_BF16)):
+        R = _native.Ratings(None, None, ni, nu, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
+                            nnz=nnz, ratings_are_f32=True, k_hint=k, row_blocks=args.row_blocks,
+                            workers=args.workers, storage=code,
+                            split=_native.SPLIT_OFF if args.no_split else _native.SPLIT_AUTO)
+        M = _native.Model(k, ni, nu, u0, v0, None, None, layout=R, ctx=ctx)
+        se = torch.zeros(args.steps + args.warmup, device=dev, dtype=torch.float64)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for e in range(args.warmup):
+            M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
+                        sq_err_ptr=se.data_ptr() + 8 * e)
+        ctx.sync()
+        ev0.record(stream)
+        for e in range(args.steps):
+            M.sgd_epoch(R, _native.KERNEL_LINEAR, HP["lr"], HP["K_users"], HP["K_items"], HP["K_bias"],
+                        sq_err_ptr=se.data_ptr() + 8 * (args.warmup + e))
+        ev1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / args.steps
+        curve = torch.sqrt(se / nnz).cpu().numpy().tolist()
+        bpu = algorithmic_bytes_per_update(k, 4) - 2 * k * 2   # P row read + written at 2 bytes per element
+        out[name] = {"dtype": name, "ms_per_epoch": ms, "value": nnz / (ms * 1e-3), "unit": "updates/s",
+                     "layout": "B=%d W=%d" % (R.B, R.W),
+                     "rmse_last_epoch": curve[-1], "rel_to_f32": abs(curve[-1] - f32_curve[-1]) / f32_curve[-1],
+                     "model_bytes": ni * (k * 4 + 4) + nu * (k * 2 + 4),
+                     "algorithmic_bytes_per_update": bpu,
+                     "frac_algorithmic": nnz / (ms * 1e-3) * bpu / 1e9 / peak}
+        del M, R
+    return out
 
 
 def secondary_topn(torch, dev, _native, ctx, local):

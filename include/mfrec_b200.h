@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MFREC_B200_ABI_VERSION 2
+#define MFREC_B200_ABI_VERSION 3
 
 typedef enum mfrec_status {
     MFREC_OK = 0,
@@ -84,7 +84,20 @@ typedef struct mfrec_opts {
                              group as several copies merged after every epoch;
                              0 = on                                                          */
     int32_t split_min_copy; /* fewest ratings a copy may hold; 0 = 1024                      */
+    int32_t storage;      /* MFREC_STORAGE_*: how models created with this layout keep the USER
+                             factor rows in HBM (96 % of the model bytes at Netflix shape; the
+                             item rows are trained in shared memory in float32 either way)     */
 } mfrec_opts;
+
+/* User-factor storage.  Arithmetic and accumulation are float32 in every mode (rows are widened
+ * on load, narrowed on store); F16 narrows with round-to-nearest, BF16 with stochastic rounding
+ * (an SGD step is below half a bf16 ulp: round-to-nearest would discard most updates).  Halves
+ * the HBM footprint / traffic of P; does NOT make the kernel faster (it is bound by instruction
+ * issue, not by HBM: DESIGN.md section 3).  Stated tolerance of the end-of-training RMSE against
+ * the reference: 1 % (F16), 2 % (BF16) (tests/test_storage_gpu.py); predictions on fixed factors
+ * carry the format's rounding (2^-11 / 2^-8 relative per factor).  Needs k > 32, a single device
+ * and both sides trained. */
+enum { MFREC_STORAGE_F32 = 0, MFREC_STORAGE_F16 = 1, MFREC_STORAGE_BF16 = 2 };
 
 /* Hot-item copies.  The updates of one item are a serial chain, so the most popular item bounds
  * an epoch (250k dependent updates at Netflix shape = the time of everything else together).

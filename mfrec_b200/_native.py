@@ -55,12 +55,14 @@ class MfrecError(RuntimeError):
 
 
 SPLIT_AUTO, SPLIT_ON, SPLIT_OFF = 0, 1, 2
+STORAGE_F32, STORAGE_F16, STORAGE_BF16 = 0, 1, 2
 
 
 class Opts(C.Structure):
     _fields_ = [("schedule", C.c_int32), ("row_blocks", C.c_int32), ("workers", C.c_int32),
                 ("n_slabs", C.c_int32), ("keep_order", C.c_int32), ("k_hint", C.c_int32),
-                ("seed", C.c_uint64), ("split", C.c_int32), ("split_min_copy", C.c_int32)]
+                ("seed", C.c_uint64), ("split", C.c_int32), ("split_min_copy", C.c_int32),
+                ("storage", C.c_int32)]
 
 
 _lib = None
@@ -114,9 +116,9 @@ def _ptr(a):
 
 
 def _opts(schedule=0, row_blocks=0, workers=0, n_slabs=0, keep_order=0, k_hint=0, seed=0, split=0,
-          split_min_copy=0):
+          split_min_copy=0, storage=0):
     return Opts(int(schedule), int(row_blocks), int(workers), int(n_slabs), int(keep_order),
-                int(k_hint), int(seed), int(split), int(split_min_copy))
+                int(k_hint), int(seed), int(split), int(split_min_copy), int(storage))
 
 
 class Context(object):

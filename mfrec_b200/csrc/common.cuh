@@ -1,6 +1,8 @@
 // Internal declarations shared by the translation units of libmfrec_b200.so.
 #pragma once
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -72,6 +74,7 @@ struct mfrec_ratings {
     int64_t nnz = 0;
     int32_t ni = 0, nu = 0;
     int B = 1, W = 1, G = 1;
+    int storage = 0;               // MFREC_STORAGE_* of the user-factor rows of models created with this layout
     int64_t n_buckets = 0;
     int64_t packed_len = 0;        // nnz + alignment padding
     int32_t max_cb_items = 0;      // widest column block (items) -> shared-memory tile size
@@ -104,12 +107,13 @@ struct mfrec_model {
     int device = 0;
     int k = 0, kpad = 0;
     int32_t ni = 0, nu = 0;
+    int p_kind = 0;       // MFREC_STORAGE_*: P is float32 [nu][kpad], or __half / __nv_bfloat16 [nu][kpad]
     int32_t ni_rows = 0;  // rows of Q / ib: ni, or the layout's virtual items (copies of hot items)
     int32_t n_hot = 0;
     int32_t *hot_off = nullptr, *hot_rows = nullptr;   // own copies of the layout's merge list
     float *Q = nullptr;   // [ni_rows][kpad]  item factors
     float *ib = nullptr;  // [ni_rows]
-    float *P = nullptr;   // [nu][kpad]  user factors
+    float *P = nullptr;   // [nu][kpad]  user factors (elements of 4 or 2 bytes, see p_kind)
     float *ub = nullptr;  // [nu]
     int32_t *user_perm = nullptr;  // own copies (nullptr = identity)
     int32_t *item_perm = nullptr;
@@ -210,7 +214,7 @@ static inline int mfrec_kpad(int k)
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // sgd.cu
-size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W);
+size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W, int p_elem_bytes = 4);
 
 // topn.cu: the exact top-N on a resident model (M may be NULL only when nothing is scored; ni / nu are
 // read only then)
@@ -231,9 +235,10 @@ int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t b
 // defaults: one row per source column
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
                         const int32_t *perm_dev, float *dst_nk, const double *staged_dev = nullptr,
-                        int32_t n_rows = -1, const int32_t *src_of_dev = nullptr);
+                        int32_t n_rows = -1, const int32_t *src_of_dev = nullptr,
+                        int row_kind = MFREC_STORAGE_F32);   // row_kind: element type of dst_nk
 int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,
-                          const int32_t *perm_dev, double *host_kn);
+                          const int32_t *perm_dev, double *host_kn, int row_kind = MFREC_STORAGE_F32);
 int mfrec_upload_vec(mfrec_ctx *ctx, const double *host, int32_t n, const int32_t *perm_dev,
                      float *dst, const double *staged_dev = nullptr, int32_t n_rows = -1,
                      const int32_t *src_of_dev = nullptr);

@@ -9,6 +9,7 @@
 //   compute_overall_avg base.py:504-508, compute_{items,users}_bias_bk mf.py:78-121
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -17,7 +18,8 @@
 namespace {
 
 struct PredParams {
-    const float *Q, *ib, *P, *ub;
+    const float *Q, *ib, *ub;
+    const void *P;   // user-factor rows: float, __half or __nv_bfloat16 (mfrec_model::p_kind)
     const int32_t *user_perm, *item_perm;
     const int32_t *pairs;
     const void *real;
@@ -35,7 +37,31 @@ struct PredParams {
 // each) are in flight before the first is consumed -- with one pair at a time the kernel waited
 // out two dependent L2 round trips per pair (ncu r02m: 3.9 G pairs/s, 1.2 TB/s of DRAM) -- and
 // lanes 0..3 finish one pair each (bias lookup, predictor map, error) instead of lane 0 doing all.
-template <int E>
+// PT: storage type of the user-factor rows (float; __half / __nv_bfloat16 for a model trained with
+// mfrec_opts.storage): 16-bit rows are widened in registers, the arithmetic is float32.
+template <int V, typename PT>
+__device__ __forceinline__ void load_p(float (&x)[V], const void *P, int64_t elem)
+{
+    const PT *p = static_cast<const PT *>(P) + elem;
+    if constexpr (sizeof(PT) == 4) {
+        if constexpr (V == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
+        else if constexpr (V == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); x[0] = t.x; x[1] = t.y; }
+        else x[0] = *reinterpret_cast<const float *>(p);
+    } else {
+        uint32_t w[(V + 1) / 2];
+        if constexpr (V == 4) { const uint2 t = *reinterpret_cast<const uint2 *>(p); w[0] = t.x; w[1] = t.y; }
+        else if constexpr (V == 2) w[0] = *reinterpret_cast<const uint32_t *>(p);
+        else w[0] = *reinterpret_cast<const uint16_t *>(p);
+#pragma unroll
+        for (int h = 0; h < V; ++h) {
+            const uint32_t bits = (h & 1) ? (w[h / 2] >> 16) : (w[h / 2] & 0xffffu);
+            if constexpr (std::is_same<PT, __half>::value) x[h] = __half2float(__ushort_as_half((unsigned short)bits));
+            else x[h] = __uint_as_float(bits << 16);
+        }
+    }
+}
+
+template <int E, typename PT>
 __global__ void __launch_bounds__(256) predict_kernel(const PredParams p)
 {
     constexpr int KPAD = E * 32;
@@ -66,29 +92,16 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredParams p)
 #pragma unroll
         for (int c = 0; c < NV; ++c) {
             const int off = (c * 32 + lane) * V;
-            if constexpr (V == 4) {
-                float4 a[G4], b[G4];
+            float a[G4][V], b[G4][V];
 #pragma unroll
-                for (int t = 0; t < G4; ++t) {
-                    a[t] = *reinterpret_cast<const float4 *>(p.P + ur[t] * KPAD + off);
-                    b[t] = *reinterpret_cast<const float4 *>(p.Q + ir[t] * KPAD + off);
-                }
-#pragma unroll
-                for (int t = 0; t < G4; ++t) {
-                    part[t] = fmaf(a[t].x, b[t].x, part[t]); part[t] = fmaf(a[t].y, b[t].y, part[t]);
-                    part[t] = fmaf(a[t].z, b[t].z, part[t]); part[t] = fmaf(a[t].w, b[t].w, part[t]);
-                }
-            } else if constexpr (V == 2) {
-#pragma unroll
-                for (int t = 0; t < G4; ++t) {
-                    const float2 a = *reinterpret_cast<const float2 *>(p.P + ur[t] * KPAD + off);
-                    const float2 b = *reinterpret_cast<const float2 *>(p.Q + ir[t] * KPAD + off);
-                    part[t] = fmaf(a.x, b.x, part[t]); part[t] = fmaf(a.y, b.y, part[t]);
-                }
-            } else {
-#pragma unroll
-                for (int t = 0; t < G4; ++t) part[t] = fmaf(p.P[ur[t] * KPAD + off], p.Q[ir[t] * KPAD + off], part[t]);
+            for (int t = 0; t < G4; ++t) {
+                load_p<V, PT>(a[t], p.P, ur[t] * KPAD + off);
+                load_p<V, float>(b[t], p.Q, ir[t] * KPAD + off);
             }
+#pragma unroll
+            for (int t = 0; t < G4; ++t)
+#pragma unroll
+                for (int h = 0; h < V; ++h) part[t] = fmaf(a[t][h], b[t][h], part[t]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
@@ -320,13 +333,20 @@ extern "C" int mfrec_model_predict(mfrec_ctx *ctx, const mfrec_model *m, int pre
     p.part = stats_out ? d_part.p : nullptr;
     p.ni = m->ni; p.nu = m->nu;
     p.bad = d_bad.p;
+#define MF_PREDICT(E)                                                                                  \
+    do {                                                                                               \
+        if (m->p_kind == MFREC_STORAGE_F16) predict_kernel<E, __half><<<grid, 256, 0, st>>>(p);        \
+        else if (m->p_kind == MFREC_STORAGE_BF16) predict_kernel<E, __nv_bfloat16><<<grid, 256, 0, st>>>(p); \
+        else predict_kernel<E, float><<<grid, 256, 0, st>>>(p);                                        \
+    } while (0)
     switch (m->kpad) {
-    case 32: predict_kernel<1><<<grid, 256, 0, st>>>(p); break;
-    case 64: predict_kernel<2><<<grid, 256, 0, st>>>(p); break;
-    case 128: predict_kernel<4><<<grid, 256, 0, st>>>(p); break;
-    case 256: predict_kernel<8><<<grid, 256, 0, st>>>(p); break;
+    case 32: MF_PREDICT(1); break;
+    case 64: MF_PREDICT(2); break;
+    case 128: MF_PREDICT(4); break;
+    case 256: MF_PREDICT(8); break;
     default: return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", m->kpad);
     }
+#undef MF_PREDICT
     MF_LAUNCH_CHECK(ctx);
     if (stats_out) {
         stats_reduce_kernel<<<1, 256, 0, st>>>(d_part.p, grid, d_stats.p);

@@ -400,6 +400,9 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     const bool keep_order = opts && opts->keep_order;
     int kpad_hint = (opts && opts->k_hint > 0) ? mfrec_kpad(opts->k_hint) : 256;
     if (kpad_hint < 0) kpad_hint = 256;
+    const int storage = opts ? opts->storage : MFREC_STORAGE_F32;
+    if (storage < MFREC_STORAGE_F32 || storage > MFREC_STORAGE_BF16)
+        return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ratings_pack: opts.storage=%d", storage);
 
     // ---- stage inputs on the device -------------------------------------------------
     DevBuf<int32_t> idx_stage;
@@ -466,6 +469,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
     R->nu = nu;
     R->G = G;
     R->W = W;
+    R->storage = storage;
     std::vector<int32_t> &ug = H.ug, &up = H.up, &ig = H.ig, &ip = H.ip, &sorted_u = H.sorted_u, &sorted_i = H.sorted_i;
     // ---- hot-item copies ------------------------------------------------------
     // The ratings of one item are a serial chain (its row changes with every update): the hottest
@@ -534,7 +538,7 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
             widest = std::max(widest, R->h_col_start[(cb + 1) * W] - R->h_col_start[cb * W]);
         R->max_cb_items = widest;
         // the SGD kernel keeps one column block of Q (kpad floats per row) in shared memory
-        const size_t need = mfrec_sgd_smem_bytes(widest, kpad_hint, W);
+        const size_t need = mfrec_sgd_smem_bytes(widest, kpad_hint, W, storage == MFREC_STORAGE_F32 ? 4 : 2);
         if (need <= ctx->smem_optin || widest <= 1 || (opts && opts->row_blocks > 0)) break;
         if (free_slabs && B + std::max(1, B / 8) > ctx->sm_count && G < 64) {
             // A catalogue too large for one tile per SM (Yahoo shape: 136k items): cut the items into

@@ -144,10 +144,21 @@ extern "C" int64_t mfrec_ctx_launch_count(const mfrec_ctx *ctx) { return ctx ? c
 // ---------------------------------------------------------------------------------------
 // n_rows rows are written; row j comes from source column src_of[j] (null: j).  Copies of a hot
 // item (src_of not injective) sit next to each other, so the reads stay nearly coalesced.
+// (T = the rows' storage type: float, or __half / __nv_bfloat16 for 16-bit user-factor rows,
+// narrowed with round-to-nearest)
+template <typename T> __device__ __forceinline__ T row_narrow(float x);
+template <> __device__ __forceinline__ float row_narrow<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half row_narrow<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 row_narrow<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float row_widen(float x) { return x; }
+__device__ __forceinline__ float row_widen(__half x) { return __half2float(x); }
+__device__ __forceinline__ float row_widen(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T>
 __global__ void __launch_bounds__(256)
 factor_to_rows_kernel(const double *__restrict__ src_kn, int k, int kpad, int32_t n, int32_t n_rows,
                       const int32_t *__restrict__ src_of, const int32_t *__restrict__ perm,
-                      float *__restrict__ dst_nk)
+                      T *__restrict__ dst_nk)
 {
     __shared__ float tile[32][33];
     const int64_t j0 = (int64_t)blockIdx.x * 32;
@@ -170,13 +181,14 @@ factor_to_rows_kernel(const double *__restrict__ src_kn, int k, int kpad, int32_
         const int f = f0 + tx;
         if (j < n && f < kpad) {
             const int64_t row = perm ? perm[j] : j;
-            dst_nk[row * kpad + f] = tile[tx][ty + r * 8];
+            dst_nk[row * kpad + f] = row_narrow<T>(tile[tx][ty + r * 8]);
         }
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-rows_to_factor_kernel(const float *__restrict__ src_nk, int k, int kpad, int32_t n,
+rows_to_factor_kernel(const T *__restrict__ src_nk, int k, int kpad, int32_t n,
                       const int32_t *__restrict__ perm, double *__restrict__ dst_kn)
 {
     __shared__ float tile[32][33];
@@ -190,7 +202,7 @@ rows_to_factor_kernel(const float *__restrict__ src_nk, int k, int kpad, int32_t
         float val = 0.f;
         if (j < n && f < kpad) {
             const int64_t row = perm ? perm[j] : j;
-            val = src_nk[row * kpad + f];
+            val = row_widen(src_nk[row * kpad + f]);
         }
         tile[ty + r * 8][tx] = val;
     }
@@ -363,12 +375,12 @@ int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t b
 
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,
                         const int32_t *perm_dev, float *dst_nk, const double *staged_dev, int32_t n_rows,
-                        const int32_t *src_of_dev)
+                        const int32_t *src_of_dev, int row_kind)
 {
     if (n == 0) return MFREC_OK;
     if (n_rows < 0) n_rows = n;
     if (!host_kn) {
-        MF_CUDA(ctx, cudaMemsetAsync(dst_nk, 0, (size_t)n_rows * kpad * sizeof(float), ctx->stream));
+        MF_CUDA(ctx, cudaMemsetAsync(dst_nk, 0, (size_t)n_rows * kpad * (row_kind == MFREC_STORAGE_F32 ? 4 : 2), ctx->stream));
         return MFREC_OK;
     }
     DevBuf<double> stage;
@@ -379,20 +391,30 @@ int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, 
         src = stage.p;
     }
     dim3 grid((unsigned)ceil_div64(n_rows, 32), (unsigned)(kpad / 32));
-    factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, n_rows, src_of_dev, perm_dev, dst_nk);
+    if (row_kind == MFREC_STORAGE_F16)
+        factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, n_rows, src_of_dev, perm_dev, reinterpret_cast<__half *>(dst_nk));
+    else if (row_kind == MFREC_STORAGE_BF16)
+        factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, n_rows, src_of_dev, perm_dev, reinterpret_cast<__nv_bfloat16 *>(dst_nk));
+    else
+        factor_to_rows_kernel<<<grid, 256, 0, ctx->stream>>>(src, k, kpad, n, n_rows, src_of_dev, perm_dev, dst_nk);
     MF_LAUNCH_CHECK(ctx);
     if (!staged_dev) MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host buffer is borrowed
     return MFREC_OK;
 }
 
 int mfrec_download_factor(mfrec_ctx *ctx, const float *src_nk, int k, int kpad, int32_t n,
-                          const int32_t *perm_dev, double *host_kn)
+                          const int32_t *perm_dev, double *host_kn, int row_kind)
 {
     if (n == 0 || !host_kn) return MFREC_OK;
     DevBuf<double> stage;
     MF_CUDA(ctx, stage.alloc((size_t)k * n, ctx->stream));
     dim3 grid((unsigned)ceil_div64(n, 32), (unsigned)(kpad / 32));
-    rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(src_nk, k, kpad, n, perm_dev, stage.p);
+    if (row_kind == MFREC_STORAGE_F16)
+        rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const __half *>(src_nk), k, kpad, n, perm_dev, stage.p);
+    else if (row_kind == MFREC_STORAGE_BF16)
+        rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(src_nk), k, kpad, n, perm_dev, stage.p);
+    else
+        rows_to_factor_kernel<<<grid, 256, 0, ctx->stream>>>(src_nk, k, kpad, n, perm_dev, stage.p);
     MF_LAUNCH_CHECK(ctx);
     MF_TRY(mfrec_copy_d2h(ctx, host_kn, stage.p, (size_t)k * n * sizeof(double), ctx->stream));
     return MFREC_OK;
@@ -481,6 +503,8 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
     const int32_t ni_rows = layout ? layout->ni_v : ni;
     m->ni_rows = ni_rows;
     m->n_hot = layout ? layout->n_hot : 0;
+    m->p_kind = layout ? layout->storage : MFREC_STORAGE_F32;
+    const size_t p_elem = m->p_kind == MFREC_STORAGE_F32 ? 4 : 2;
     int rc = MFREC_OK;
     auto fail = [&](int code) {
         mfrec_model_destroy(m);
@@ -495,7 +519,7 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
     } while (0)
     // +64 floats of slack so vector loads of the last row never leave the allocation
     MF_M(cudaMallocAsync((void **)&m->Q, ((size_t)ni_rows * kpad + 64) * sizeof(float), ctx->stream));
-    MF_M(cudaMallocAsync((void **)&m->P, ((size_t)nu * kpad + 64) * sizeof(float), ctx->stream));
+    MF_M(cudaMallocAsync((void **)&m->P, ((size_t)nu * kpad + 64) * p_elem, ctx->stream));
     MF_M(cudaMallocAsync((void **)&m->ib, ((size_t)ni_rows + 64) * sizeof(float), ctx->stream));
     MF_M(cudaMallocAsync((void **)&m->ub, ((size_t)nu + 64) * sizeof(float), ctx->stream));
     if (layout) {
@@ -526,7 +550,7 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
     // (item rows: every virtual item takes the column of the item it is a copy of)
     if ((rc = mfrec_upload_factor(ctx, u, k, kpad, ni, layout ? layout->item_perm : nullptr, m->Q, staged.u, ni_rows,
                                   layout ? layout->vitem_src : nullptr)) != MFREC_OK) return fail(rc);
-    if ((rc = mfrec_upload_factor(ctx, v, k, kpad, nu, m->user_perm, m->P, staged.v)) != MFREC_OK) return fail(rc);
+    if ((rc = mfrec_upload_factor(ctx, v, k, kpad, nu, m->user_perm, m->P, staged.v, -1, nullptr, m->p_kind)) != MFREC_OK) return fail(rc);
     if ((rc = mfrec_upload_vec(ctx, items_bias, ni, layout ? layout->item_perm : nullptr, m->ib, staged.ib, ni_rows,
                                layout ? layout->vitem_src : nullptr)) != MFREC_OK) return fail(rc);
     if ((rc = mfrec_upload_vec(ctx, users_bias, nu, m->user_perm, m->ub, staged.ub)) != MFREC_OK) return fail(rc);
@@ -543,7 +567,7 @@ extern "C" int mfrec_model_read(mfrec_ctx *ctx, const mfrec_model *m, double *u,
     if (!ctx || !m) return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_model_read: NULL argument");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     MF_TRY(mfrec_download_factor(ctx, m->Q, m->k, m->kpad, m->ni, m->item_perm, u));
-    MF_TRY(mfrec_download_factor(ctx, m->P, m->k, m->kpad, m->nu, m->user_perm, v));
+    MF_TRY(mfrec_download_factor(ctx, m->P, m->k, m->kpad, m->nu, m->user_perm, v, m->p_kind));
     MF_TRY(mfrec_download_vec(ctx, m->ib, m->ni, m->item_perm, items_bias));
     MF_TRY(mfrec_download_vec(ctx, m->ub, m->nu, m->user_perm, users_bias));
     return MFREC_OK;

@@ -39,6 +39,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -215,11 +219,75 @@ __device__ __forceinline__ void row_cp_async(float *dst_row, const float *src_ro
 
 // base + idx * stride as ONE 64-bit multiply-add (the compiler otherwise splits the masked id into
 // shifts and masks: 5-6 instructions per row address instead of 1)
-__device__ __forceinline__ float *row_ptr(float *base, uint32_t idx, uint32_t stride_bytes)
+template <typename T>
+__device__ __forceinline__ T *row_ptr(T *base, uint32_t idx, uint32_t stride_bytes)
 {
     uint64_t a;
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"(stride_bytes), "l"(base));
-    return reinterpret_cast<float *>(a);
+    return reinterpret_cast<T *>(a);
+}
+
+// ---- user-factor storage (mfrec_opts.storage): P rows may live in HBM as fp16 or bf16; the
+// arithmetic is fp32 either way (rows are widened on load and narrowed on store).
+// fp16 narrows with round-to-nearest (11 significant bits: one SGD step moves a factor by
+// ~0.3 %, i.e. several ulps).  bf16 has 8: the same step is BELOW half an ulp, round-to-nearest
+// would discard most updates, so bf16 narrows with STOCHASTIC rounding (the low 16 bits plus a
+// per-lane pseudo-random 16-bit number carry into the kept half): unbiased, deterministic for a
+// given layout.
+template <int E, typename PT>
+__device__ __forceinline__ void pfrag_load(Frag<E> &f, const PT *row, int lane)
+{
+    if constexpr (sizeof(PT) == 4) {
+        frag_load<E>(f, reinterpret_cast<const float *>(row), lane);
+    } else {
+        constexpr int V = Frag<E>::V, NV = Frag<E>::NV;
+        static_assert(V >= 2, "16-bit rows need at least two elements per lane");
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            const PT *p = row + (c * 32 + lane) * V;
+#pragma unroll
+            for (int h = 0; h < V / 2; ++h) {
+                float2 t;
+                if constexpr (std::is_same<PT, __half>::value)
+                    t = __half22float2(*reinterpret_cast<const __half2 *>(p + 2 * h));
+                else
+                    t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p + 2 * h));
+                f.x[c * V + 2 * h] = t.x;
+                f.x[c * V + 2 * h + 1] = t.y;
+            }
+        }
+    }
+}
+
+// p already includes the lane's offset (row + lane * V)
+template <int E, typename PT>
+__device__ __forceinline__ void pfrag_store_lane(const Frag<E> &f, PT *p, uint32_t &rng)
+{
+    if constexpr (sizeof(PT) == 4) {
+        frag_store_lane<E>(f, reinterpret_cast<float *>(p));
+    } else {
+        constexpr int V = Frag<E>::V, NV = Frag<E>::NV;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            uint32_t w[V / 2];
+#pragma unroll
+            for (int h = 0; h < V / 2; ++h) {
+                const float a = f.x[c * V + 2 * h], b = f.x[c * V + 2 * h + 1];
+                if constexpr (std::is_same<PT, __half>::value) {
+                    const __half2 t = __floats2half2_rn(a, b);
+                    w[h] = *reinterpret_cast<const uint32_t *>(&t);
+                } else {
+                    rng = rng * 1664525u + 1013904223u;
+                    const uint32_t ua = __float_as_uint(a) + (rng & 0xffffu);
+                    const uint32_t ub = __float_as_uint(b) + (rng >> 16);
+                    w[h] = (ua >> 16) | (ub & 0xffff0000u);
+                }
+            }
+            PT *q = p + c * 32 * V;
+            if constexpr (V == 4) *reinterpret_cast<uint2 *>(q) = make_uint2(w[0], w[1]);
+            else *reinterpret_cast<uint32_t *>(q) = w[0];
+        }
+    }
 }
 
 // Packed fp32 pairs (sm_100: FMUL2 / FFMA2 take two independent IEEE operations per instruction;
@@ -316,9 +384,10 @@ __device__ __forceinline__ unsigned long long global_ns()
 // takes the generic path, which picks each row's source (registers / prefetch ring / global
 // memory) with warp-uniform branches.
 // ------------------------------------------------------------------------------------------
-template <int E, int KERNEL, bool TIMING, int MAXT, bool GATED, bool RING>
-// MAXT: 256 (W <= 8: 255 registers per thread) or 512; GATED: honour update_users / update_items
-// (else both on); RING: slabs move between ranks (DSGD), counters and hand-over at system scope
+template <int E, int KERNEL, bool TIMING, int MAXT, bool GATED, bool RING, typename PT = float>
+// MAXT: 256 (W <= 8: 255 registers per thread), 384 or 512; GATED: honour update_users /
+// update_items (else both on); RING: slabs move between ranks (DSGD), counters and hand-over at
+// system scope; PT: storage type of the user-factor rows in HBM (float, __half, __nv_bfloat16)
 __global__ void __launch_bounds__(MAXT, 1)
 sgd_block_kernel(const SgdParams prm)
 {
@@ -335,15 +404,15 @@ sgd_block_kernel(const SgdParams prm)
     // shared-memory carve-up (every section is a multiple of 16 bytes)
     float *Qs = reinterpret_cast<float *>(smem_raw);
     float *ibs = Qs + (size_t)prm.tile_rows * KPAD;
-    float *prow_all = ibs + ((prm.tile_rows + 3) & ~3);
-    float *pbias_all = prow_all + (size_t)W * kDepth * KPAD;
+    PT *prow_all = reinterpret_cast<PT *>(ibs + ((prm.tile_rows + 3) & ~3));
+    float *pbias_all = reinterpret_cast<float *>(prow_all + (size_t)W * kDepth * KPAD);
     PackedRating *ring_all = reinterpret_cast<PackedRating *>(pbias_all + (size_t)W * kDepth);
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring_all + (size_t)W * kRing);
     int64_t *boff = reinterpret_cast<int64_t *>(bars + 1 + kStages * W);
     double *se_s = reinterpret_cast<double *>(boff + W * W + 2);
     volatile int32_t *phase_done = reinterpret_cast<volatile int32_t *>(se_s + W);
 
-    float *prow = prow_all + (size_t)warp * kDepth * KPAD;
+    PT *prow = prow_all + (size_t)warp * kDepth * KPAD;
     float *pbias = pbias_all + warp * kDepth;
     PackedRating *ring = ring_all + (size_t)warp * kRing;
     uint64_t *tile_bar = bars;
@@ -367,7 +436,10 @@ sgd_block_kernel(const SgdParams prm)
     const bool upd_bu = (KERNEL == MFREC_KERNEL_LINEAR) || upd_u;
     const bool upd_bi = (KERNEL == MFREC_KERNEL_LINEAR) || upd_i;
     const float fx_scale = prm.fx_scale, fx_inv = prm.fx_inv;
-    float *const P_lane = R.P + lane * Frag<E>::V;   // this lane's column of every P row
+    constexpr uint32_t kRowBytes = KPAD * sizeof(PT);
+    PT *const P_rows = reinterpret_cast<PT *>(R.P);
+    PT *const P_lane = P_rows + lane * Frag<E>::V;   // this lane's column of every P row
+    uint32_t rng = 0x9e3779b9u * (blockIdx.x * 1024u + threadIdx.x + 1u);   // stochastic rounding of bf16 rows
     float *const ub_g = R.ub;
     const int64_t steps_per_epoch = (int64_t)prm.G * prm.B;
 
@@ -498,7 +570,7 @@ sgd_block_kernel(const SgdParams prm)
         // copies fill the reduction's latency instead of preceding the dependent chain.  Padding
         // entries name packed user 0, a valid row, and are never consumed.  Quads past the end
         // commit empty groups.
-        float *const prow_lane = prow + lane * Frag<E>::V;
+        PT *const prow_lane = prow + lane * Frag<E>::V;
         for (uint32_t fx = 0; fx + 1 < (uint32_t)kQuadsAhead; ++fx) {
             if (fx < nquads) {
                 if ((fx & (kChunkQ - 1)) == 0) chunk_wait(fx / kChunkQ);
@@ -507,11 +579,11 @@ sgd_block_kernel(const SgdParams prm)
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const uint32_t ut = *reinterpret_cast<const uint32_t *>(rec + 12 * t) & kIdMask;
-                    const float *gsrc = row_ptr(P_lane, ut, KPAD * 4);
+                    const PT *gsrc = row_ptr(P_lane, ut, kRowBytes);
 #pragma unroll
                     for (int c = 0; c < Frag<E>::NV; ++c)
-                        cp_async<Frag<E>::V * 4>(prow_lane + (fslot0 + t) * KPAD + c * 32 * Frag<E>::V,
-                                                 gsrc + c * 32 * Frag<E>::V);
+                        cp_async<Frag<E>::V * sizeof(PT)>(prow_lane + (fslot0 + t) * KPAD + c * 32 * Frag<E>::V,
+                                                          gsrc + c * 32 * Frag<E>::V);
                 }
                 if (lane < 4) {
                     const uint32_t ul = *reinterpret_cast<const uint32_t *>(rec + 12 * lane) & kIdMask;
@@ -593,7 +665,7 @@ sgd_block_kernel(const SgdParams prm)
         };
         auto store_p_row = [&](int u, const Frag<E> &pu) {
             if constexpr (TIMING) { if (prm.exp & 1) return; }
-            frag_store_lane<E>(pu, row_ptr(P_lane, (uint32_t)u, KPAD * 4));
+            pfrag_store_lane<E, PT>(pu, row_ptr(P_lane, (uint32_t)u, kRowBytes), rng);
         };
         auto store_p = [&](int u, const Frag<E> &pu, float bu) {
             if constexpr (TIMING) { if (prm.exp & 1) return; }
@@ -629,10 +701,10 @@ sgd_block_kernel(const SgdParams prm)
                 bu = cbu;
             } else if (stale) {
                 __syncwarp();   // lane 0's bias store of an earlier rating is visible to every lane
-                frag_load<E>(pu, row_ptr(R.P, (uint32_t)u, KPAD * 4), lane);
+                pfrag_load<E, PT>(pu, row_ptr(P_rows, (uint32_t)u, kRowBytes), lane);
                 bu = *row_ptr(ub_g, (uint32_t)u, 4);
             } else {
-                frag_load<E>(pu, prow + slot * KPAD, lane);
+                pfrag_load<E, PT>(pu, prow + slot * KPAD, lane);
                 bu = pbias[slot];
             }
             if (it != prev_i) {   // otherwise the item row is still in registers
@@ -655,7 +727,7 @@ sgd_block_kernel(const SgdParams prm)
         auto load_quad_p = [&](uint32_t slot0, Frag<E> (&p4)[4], float (&b4)[4]) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                frag_load<E>(p4[t], prow + (slot0 + t) * KPAD, lane);
+                pfrag_load<E, PT>(p4[t], prow + (slot0 + t) * KPAD, lane);
                 b4[t] = pbias[slot0 + t];
             }
         };
@@ -797,13 +869,13 @@ sgd_block_kernel(const SgdParams prm)
                                         *reinterpret_cast<const uint32_t *>(frec + 24) & kIdMask,
                                         *reinterpret_cast<const uint32_t *>(frec + 36) & kIdMask};
                 const uint32_t fslot0 = (fx & (kQuadsAhead - 1)) * 4;
-                float *const fdst = prow_lane + fslot0 * KPAD;
+                PT *const fdst = prow_lane + fslot0 * KPAD;
                 auto fetch_row = [&](int t) {
                     if constexpr (TIMING) { if (prm.exp & 8) return; }
-                    const float *gsrc = row_ptr(P_lane, fu[t], KPAD * 4);
+                    const PT *gsrc = row_ptr(P_lane, fu[t], kRowBytes);
 #pragma unroll
                     for (int c = 0; c < Frag<E>::NV; ++c)
-                        cp_async<Frag<E>::V * 4>(fdst + t * KPAD + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
+                        cp_async<Frag<E>::V * sizeof(PT)>(fdst + t * KPAD + c * 32 * Frag<E>::V, gsrc + c * 32 * Frag<E>::V);
                 };
                 lap(0);
                 cp_async_wait<kQuadsAhead - 2>();   // the four rows of this quad have landed
@@ -1086,11 +1158,11 @@ __global__ void kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, doubl
 }  // namespace
 
 // shared memory one CTA of the stratified kernel needs (also used by pack.cu to size blocks)
-size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W)
+size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W, int p_elem_bytes)
 {
     size_t b = (size_t)tile_rows * kpad * 4;               // Q tile
     b += (size_t)((tile_rows + 3) & ~3) * 4;               // item biases
-    b += (size_t)W * kDepth * kpad * 4;                    // P-row rings
+    b += (size_t)W * kDepth * kpad * p_elem_bytes;         // P-row rings (in the rows' storage type)
     b += (size_t)W * kDepth * 4;                           // user-bias rings
     b += (size_t)W * kRing * sizeof(PackedRating);         // rating rings
     b += (size_t)(1 + kStages * W) * 8;                    // mbarriers
@@ -1103,7 +1175,8 @@ size_t mfrec_sgd_smem_bytes(int tile_rows, int kpad, int W)
 namespace {
 
 template <int E, bool TIMING>
-int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative, int grid, bool ring)
+int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool cooperative, int grid, bool ring,
+               int p_kind)
 {
     const bool wide = prm.W > 8;
     // both sides updated (the training call) gets the variant without the gates; fold-in calls
@@ -1120,7 +1193,23 @@ int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool coo
 #define MF_PICK_RING(K) \
     fn = mid ? sgd_block_kernel<E, K, false, 384, false, true>                                           \
        : wide ? sgd_block_kernel<E, K, false, 512, false, true> : sgd_block_kernel<E, K, false, 256, false, true>
-    if (ring) {
+    if (p_kind != MFREC_STORAGE_F32) {
+        // 16-bit user-factor rows: the training build only (both sides updated, <= 12 warps, one device)
+        if constexpr (E >= 2 && !TIMING) {
+            if (ring || gated || prm.W > 12)
+                return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
+                                       "fp16 / bf16 user-factor storage: single device, both sides updated, at most 12 warps per CTA");
+#define MF_PICK16(K, T) fn = prm.W > 8 ? sgd_block_kernel<E, K, false, 384, false, false, T> : sgd_block_kernel<E, K, false, 256, false, false, T>
+            if (kernel == MFREC_KERNEL_LINEAR) {
+                if (p_kind == MFREC_STORAGE_F16) { MF_PICK16(MFREC_KERNEL_LINEAR, __half); } else { MF_PICK16(MFREC_KERNEL_LINEAR, __nv_bfloat16); }
+            } else {
+                if (p_kind == MFREC_STORAGE_F16) { MF_PICK16(MFREC_KERNEL_LOGISTIC, __half); } else { MF_PICK16(MFREC_KERNEL_LOGISTIC, __nv_bfloat16); }
+            }
+#undef MF_PICK16
+        } else {
+            return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "fp16 / bf16 user-factor storage needs k > 32 (and has no timing build)");
+        }
+    } else if (ring) {
         if (gated || TIMING)
             return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "ring launches train both sides and have no timing build");
         if (kernel == MFREC_KERNEL_LINEAR) { MF_PICK_RING(MFREC_KERNEL_LINEAR); } else { MF_PICK_RING(MFREC_KERNEL_LOGISTIC); }
@@ -1146,14 +1235,14 @@ int launch_sgd(mfrec_ctx *ctx, int kernel, SgdParams &prm, size_t smem, bool coo
 
 template <bool TIMING>
 int launch_sgd_kpad(mfrec_ctx *ctx, int kpad, int kernel, SgdParams &prm, size_t smem, bool cooperative,
-                    int grid = 0, bool ring = false)
+                    int grid = 0, bool ring = false, int p_kind = MFREC_STORAGE_F32)
 {
     if (grid == 0) grid = prm.B;
     switch (kpad) {
-    case 32: return launch_sgd<1, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
-    case 64: return launch_sgd<2, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
-    case 128: return launch_sgd<4, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
-    case 256: return launch_sgd<8, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring);
+    case 32: return launch_sgd<1, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring, p_kind);
+    case 64: return launch_sgd<2, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring, p_kind);
+    case 128: return launch_sgd<4, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring, p_kind);
+    case 256: return launch_sgd<8, TIMING>(ctx, kernel, prm, smem, cooperative, grid, ring, p_kind);
     default: return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "kpad=%d", kpad);
     }
 }
@@ -1243,7 +1332,7 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
                                "mfrec_sgd_epoch: a layout with hot-item copies is trained a whole epoch at a time (its copies are "
                                "merged at the end of the epoch); pack with opts.split = MFREC_SPLIT_OFF to drive single slabs");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W);
+    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, m->kpad, r->W, m->p_kind == MFREC_STORAGE_F32 ? 4 : 2);
     if (smem > ctx->smem_optin)
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,
                                "mfrec_sgd_epoch: Q tile of %d rows x %d needs %zu B shared memory (> %zu); pack with more row_blocks",
@@ -1291,7 +1380,7 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
         if (persistent) MF_CUDA(ctx, cudaMemsetAsync(ctx->ticks, 0, (size_t)r->G * r->B * 4, ctx->stream));
         if (timing_env) {
             MF_CUDA(ctx, cudaMemsetAsync(d_timing.p, 0, (size_t)r->B * r->W * 64, ctx->stream));
-            MF_TRY(launch_sgd_kpad<true>(ctx, m->kpad, kernel, prm, smem, persistent));
+            MF_TRY(launch_sgd_kpad<true>(ctx, m->kpad, kernel, prm, smem, persistent, 0, false, m->p_kind));
             std::vector<unsigned long long> h((size_t)r->B * r->W * 8);
             MF_CUDA(ctx, cudaMemcpyAsync(h.data(), d_timing.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
             MF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1312,7 +1401,7 @@ extern "C" int mfrec_sgd_epoch(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_mod
             fprintf(stderr, "\n");
             if (--timing_env == 0) prm.timing = nullptr;
         } else {
-            MF_TRY(launch_sgd_kpad<false>(ctx, m->kpad, kernel, prm, smem, persistent));
+            MF_TRY(launch_sgd_kpad<false>(ctx, m->kpad, kernel, prm, smem, persistent, 0, false, m->p_kind));
         }
     }
     if (sq_err_out) {
@@ -1378,6 +1467,8 @@ extern "C" int mfrec_ring_create(mfrec_ctx *ctx, const mfrec_ratings *r, mfrec_m
                                rank, world, r->G);
     if (m->ni != r->ni || m->nu != r->nu || !m->user_perm || m->ni_rows != r->ni_v)
         return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_create: model was not created with this layout");
+    if (m->p_kind != MFREC_STORAGE_F32)
+        return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_ring_create: the ring trains float32 user factors (opts.storage = 0)");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
     mfrec_ring *g = new (std::nothrow) mfrec_ring();
     if (!g) return mfrec_set_error(ctx, MFREC_ERR_OOM, "mfrec_ring_create: host OOM");
@@ -1511,7 +1602,7 @@ int ring_launch(mfrec_ring *const *rings, int n_ranks, int kernel, double learni
             return mfrec_set_error(ctx, MFREC_ERR_BAD_ARG, "mfrec_ring_epochs: the rings of one launch must share context and layout shape");
     }
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, g0->m->kpad, r->W);
+    const size_t smem = mfrec_sgd_smem_bytes(r->max_cb_items, g0->m->kpad, r->W, 4);
     const int grid = n_ranks * r->B;
     if (smem > ctx->smem_optin || !ctx->coop_launch || !sgd_fits_one_wave(ctx, grid, r->W, smem))
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED,

@@ -56,10 +56,18 @@ options = {
     # several CUDA devices, e.g. [0, 1, 2, 3] (MFREC_B200_DEVICES=0,1,2,3): train_linear_kernel /
     # train_logistic_kernel calls that train both sides run as a DSGD ring over them
     "devices": [int(x) for x in os.environ.get("MFREC_B200_DEVICES", "").split(",") if x.strip()],
+    # how the user-factor rows are kept in HBM while training: "f32" | "f16" | "bf16"
+    # (mfrec_opts.storage in include/mfrec_b200.h: arithmetic stays float32; single device, both
+    # sides trained, dim > 32)
+    "storage": os.environ.get("MFREC_B200_STORAGE", "f32"),
 }
+
+STORAGE = {"f32": 0, "f16": 1, "bf16": 2}
 
 
 def native_opts():
     sched = {"stratified": 0, "sequential": 1}[options["schedule"]]
+    if options["storage"] not in STORAGE:
+        raise ValueError("options['storage'] must be one of %s" % sorted(STORAGE))
     return dict(schedule=sched, row_blocks=options["row_blocks"], workers=options["workers"],
-                seed=options["seed"])
+                seed=options["seed"], storage=STORAGE[options["storage"]])

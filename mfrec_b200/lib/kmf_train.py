@@ -40,10 +40,13 @@ def _train(kernel, nbr_epochs, dim, learning_rate, K_users, K_items, K_bias, u, 
         _print_rmse(kernel, verbose)
         return None
     ctx = _native.default_context(options["device"])
+    opts = native_opts()
+    if not (update_users and update_items):
+        opts["storage"] = 0   # fold-ins keep the frozen side bit-identical: float32 rows, rows gathered
     last_rmse = _native.train_kmf(
         kernel, nbr_epochs, dim, float(learning_rate), float(K_users), float(K_items),
         float(K_bias), u[:dim], v[:dim], ratings_index, ratings, items_bias, users_bias,
-        1 if update_users else 0, 1 if update_items else 0, ctx=ctx, **native_opts())
+        1 if update_users else 0, 1 if update_items else 0, ctx=ctx, **opts)
     _print_rmse(kernel, verbose)
     return None
 
