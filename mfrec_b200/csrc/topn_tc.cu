@@ -451,14 +451,22 @@ __device__ __forceinline__ uint32_t order_bits_tc(float x)
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// One CTA per user: exact fp32 score of every candidate, masks, then the rank of every candidate by
-// counting (n is a few hundred: n^2 / 128 compares per thread beat a block radix sort, need no
-// second pass and are stable: equal scores keep ascending item order).
-// The dots are taken a warp per candidate: the 32 lanes read the item row with one coalesced
-// 512-byte request (a thread per candidate would touch 32 different rows per load instruction) and
-// reduce with shuffles; the scores, masks and the look-up in the user's rated list (staged in
-// shared memory when it is short enough) then run a thread per candidate.
+// One CTA per user: exact fp32 score of every candidate, masks, then the top N of them in order.
+//   dots    a warp per candidate, EIGHT candidates in flight: the 32 lanes read an item row with one
+//           coalesced 512-byte request (a thread per candidate would touch 32 different rows per load
+//           instruction); the eight partial sums are reduced together by a transposing butterfly
+//           (9 shuffles for 8 sums instead of 40)
+//   masks   a thread per candidate: predictor, NaN / zero / own id, look-up in the user's rated list
+//           (staged in shared memory when it is short enough)
+//   select  the candidates were filtered with a loose threshold (~2.2 N of them): a 256-bin histogram
+//           of the scores finds the bin that holds the N-th best; only the candidates from that bin
+//           upwards (N plus a few) survive, compacted in ascending item order
+//   rank    by counting among the survivors (n^2 / 128 compares per thread beat a block radix sort at
+//           n ~ N, need no second pass and are stable: equal scores keep ascending item order)
+// (round 2: ranking ALL ~220 candidates by counting was 14 k of the kernel's 20 k warp instructions
+// per user, profiles/r02m_topn_finish_full.md.)
 constexpr int kRatedStage = 2048;   // rated items of the user kept in shared memory (8 KB)
+constexpr int kSurv = 512;          // survivors the ranking step has room for (N <= 128)
 
 __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
 {
@@ -468,7 +476,12 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     __shared__ float scs[kCand];                     // first the dots, then the scores
     __shared__ int32_t rated_s[kRatedStage];
     __shared__ int32_t cand_s[kCand];
-    __shared__ int s_valid;
+    __shared__ __align__(16) uint32_t skeys[kSurv];  // survivors: keys and positions in the candidate list
+    __shared__ int16_t spos[kSurv];
+    __shared__ int hist[256];
+    __shared__ int w_cnt[4];
+    __shared__ float w_max[4], w_min[4];
+    __shared__ int s_bin;
     __shared__ float x_nth;
     const int row = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -476,9 +489,9 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     const int64_t uid = p.users ? p.users[pos] : pos;
     const int n = p.cand_cnt[row];
     const int nn = min(n, kCand);
-    if (threadIdx.x == 0) { s_valid = 0; x_nth = -INFINITY; }
+    if (threadIdx.x == 0) { x_nth = -INFINITY; s_bin = 0; }
     for (int f = threadIdx.x; f < p.kpad; f += 128) prow[f] = p.P[uid * p.kpad + f];
-    for (int c = nn + threadIdx.x; c < ((nn + 3) & ~3); c += 128) keys[c] = 0;   // pad to a multiple of 4
+    for (int j = threadIdx.x; j < 256; j += 128) hist[j] = 0;
     const int64_t ra = p.rated_indptr ? p.rated_indptr[pos] : 0, rbnd = p.rated_indptr ? p.rated_indptr[pos + 1] : 0;
     const int nrated = (rbnd - ra) > (int64_t)kRatedStage ? kRatedStage + 1 : (int)(rbnd - ra);
     const bool rated_in_smem = nrated <= kRatedStage;
@@ -488,41 +501,51 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     for (int c = threadIdx.x; c < nn; c += 128) cand_s[c] = cand[c];
     __syncthreads();
     const float bu = p.ub[uid];
-    // ---- dots: a warp per candidate, four candidates (four independent row requests) in flight;
-    //      the kernel is latency-bound otherwise: id -> row -> reduce is two dependent L2 round trips
+    // ---- dots ----------------------------------------------------------------------------------
     {
         const int nv = p.kpad / 4;   // float4 per row: 8, 16, 32 or 64 (kpad is a multiple of 32, rows zero padded)
         const float4 *pr4 = reinterpret_cast<const float4 *>(prow);
-        for (int c = warp * 4; c < nn; c += 16) {
-            int it[4];
-            const float4 *q[4];
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = warp * 8; c < nn; c += 32) {
+            const float4 *q[8];
+            float d[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                it[t] = cand_s[min(c + t, nn - 1)];
-                q[t] = reinterpret_cast<const float4 *>(p.Q + (size_t)it[t] * p.kpad);
+            for (int t = 0; t < 8; ++t) {
+                q[t] = reinterpret_cast<const float4 *>(p.Q + (size_t)cand_s[min(c + t, nn - 1)] * p.kpad);
+                d[t] = 0.f;
             }
             for (int f = lane; f < nv; f += 32) {
                 const float4 w = pr4[f];
-                float4 a[4];
+                float4 a[8];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) a[t] = q[t][f];
+                for (int t = 0; t < 8; ++t) a[t] = q[t][f];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
+                for (int t = 0; t < 8; ++t) {
                     d[t] = fmaf(w.x, a[t].x, d[t]); d[t] = fmaf(w.y, a[t].y, d[t]);
                     d[t] = fmaf(w.z, a[t].z, d[t]); d[t] = fmaf(w.w, a[t].w, d[t]);
                 }
             }
+            // transposing butterfly: at offset 16 / 8 / 4 a lane keeps the half of its sums that its
+            // lane bit selects and hands the other half over; offsets 2 and 1 finish the one sum left
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+            for (int h = 4, o = 16; h >= 1; h >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) d[t] += __shfl_xor_sync(0xffffffffu, d[t], o);
-            if (lane < 4 && c + lane < nn) scs[c + lane] = lane == 0 ? d[0] : lane == 1 ? d[1] : lane == 2 ? d[2] : d[3];
+                for (int j = 0; j < h; ++j) {
+                    const float send = up ? d[j] : d[j + h];
+                    const float keep = up ? d[j + h] : d[j];
+                    d[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            d[0] += __shfl_xor_sync(0xffffffffu, d[0], 2);
+            d[0] += __shfl_xor_sync(0xffffffffu, d[0], 1);
+            const int t = lane >> 2;   // lane bits 4, 3, 2 = the candidate of this group of four lanes
+            if ((lane & 3) == 0 && c + t < nn) scs[c + t] = d[0];
         }
     }
     __syncthreads();
     // ---- scores and masks: a thread per candidate ------------------------------------------------
     int valid = 0;
+    float smax = -INFINITY, smin = INFINITY;
     for (int c = threadIdx.x; c < nn; c += 128) {
         const int it = cand_s[c];
         const float dot = scs[c];
@@ -560,34 +583,109 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
         keys[c] = ok ? order_bits_tc(sc) : 0u;
         xs[c] = p.has_bias ? dot + bi : dot;
         scs[c] = sc;
-        valid += ok ? 1 : 0;
+        if (ok && fabsf(sc) <= 3.0e38f) {   // (an infinite score keeps its key; it only stays out of the bin range)
+            valid += 1;
+            smax = fmaxf(smax, sc);
+            smin = fminf(smin, sc);
+        } else if (ok) {
+            valid += 1;
+        }
     }
-    if (valid) atomicAdd(&s_valid, valid);
-    __syncthreads();
-    const int nvalid = s_valid;
-    const int n4 = (nn + 3) >> 2;
-    for (int c = threadIdx.x; c < nn; c += 128) {
-        const uint32_t key = keys[c];
-        if (!key) continue;
-        int rank = 0;
-        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys);
-        const int c4 = c >> 2;
-        for (int j = 0; j < n4; ++j) {           // every thread reads the same word: broadcast
-            const uint4 kk = k4[j];
-            if (j < c4) {                        // earlier candidates (lower item id) win ties
-                rank += (kk.x >= key) + (kk.y >= key) + (kk.z >= key) + (kk.w >= key);
-            } else if (j > c4) {
-                rank += (kk.x > key) + (kk.y > key) + (kk.z > key) + (kk.w > key);
-            } else {
-                const uint32_t e[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rank += (q < (c & 3)) ? (e[q] >= key) : (e[q] > key);
+    for (int o = 16; o > 0; o >>= 1) {
+        valid += __shfl_xor_sync(0xffffffffu, valid, o);
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    }
+    if (lane == 0) { w_cnt[warp] = valid; w_max[warp] = smax; w_min[warp] = smin; }
+    __syncthreads();
+    const int nvalid = w_cnt[0] + w_cnt[1] + w_cnt[2] + w_cnt[3];
+    smax = fmaxf(fmaxf(w_max[0], w_max[1]), fmaxf(w_max[2], w_max[3]));
+    smin = fminf(fminf(w_min[0], w_min[1]), fminf(w_min[2], w_min[3]));
+    // ---- select: the histogram bin of the N-th best score ------------------------------------------
+    // bin(sc) is monotone in sc (finite scores; +inf -> 255, -inf -> 0), so "bin >= the N-th best's
+    // bin" keeps every candidate that can be among the first N
+    const float scale = (smax > smin) ? 255.99f / (smax - smin) : 0.f;
+    auto bin_of = [&](float sc) { return min(255, max(0, (int)((fminf(fmaxf(sc, smin), smax) - smin) * scale))); };
+    if (nvalid > p.N) {   // (block-uniform)
+        for (int c = threadIdx.x; c < nn; c += 128)
+            if (keys[c]) atomicAdd(&hist[bin_of(scs[c])], 1);
+        __syncthreads();
+        if (warp == 0) {
+            int h[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist[lane * 8 + j]; s += h[j]; }
+            int suf = s;   // candidates in this lane's bins and above
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += t;
+            }
+            int above = suf - s;
+            if (suf >= p.N && above < p.N) {   // exactly one lane
+                int b = 7;
+                for (; b > 0; --b) {
+                    above += h[b];
+                    if (above >= p.N) break;
+                }
+                s_bin = lane * 8 + b;
             }
         }
+        __syncthreads();
+    }
+    const int bin_min = s_bin;   // 0 when every valid candidate is kept
+    // ---- compaction in ascending item order: warp w takes a contiguous quarter of the list ----------
+    const int per = ((nn + 127) >> 7) << 5;
+    const int c_lo = warp * per, c_hi = min(nn, c_lo + per);
+    int mine = 0;
+    for (int base = c_lo; base < c_hi; base += 32) {
+        const int c = base + lane;
+        const bool in = c < c_hi && keys[c] && bin_of(scs[c]) >= bin_min;
+        mine += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    __syncthreads();   // (w_cnt was read above by every thread)
+    if (lane == 0) w_cnt[warp] = mine;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; ++w) off += w_cnt[w];
+    const int n_surv_all = w_cnt[0] + w_cnt[1] + w_cnt[2] + w_cnt[3];
+    for (int base = c_lo; base < c_hi; base += 32) {
+        const int c = base + lane;
+        const bool in = c < c_hi && keys[c] && bin_of(scs[c]) >= bin_min;
+        const uint32_t bal = __ballot_sync(0xffffffffu, in);
+        const int at = off + __popc(bal & ((1u << lane) - 1u));
+        if (in && at < kSurv) { skeys[at] = keys[c]; spos[at] = (int16_t)c; }
+        off += __popc(bal);
+    }
+    const int ns = min(n_surv_all, kSurv);
+    for (int c = ns + threadIdx.x; c < ((ns + 3) & ~3); c += 128) skeys[c] = 0;   // pad to a multiple of 4
+    __syncthreads();
+    // ---- rank among the survivors ---------------------------------------------------------------------
+    const int n4 = (ns + 3) >> 2;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(skeys);
+    for (int c = threadIdx.x; c < ns; c += 128) {
+        const uint32_t key = skeys[c];
+        const int c4 = c >> 2;
+        int rank = 0;
+        for (int j = 0; j < c4; ++j) {           // earlier survivors (lower item id) win ties
+            const uint4 kk = k4[j];
+            rank += (kk.x >= key) + (kk.y >= key) + (kk.z >= key) + (kk.w >= key);
+        }
+        {
+            const uint4 kk = k4[c4];
+            const uint32_t e[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rank += (q < (c & 3)) ? (e[q] >= key) : (e[q] > key);
+        }
+        for (int j = c4 + 1; j < n4; ++j) {
+            const uint4 kk = k4[j];
+            rank += (kk.x > key) + (kk.y > key) + (kk.z > key) + (kk.w > key);
+        }
         if (rank < p.N) {
-            p.out_items[(size_t)row * p.N + rank] = cand_s[c];
-            p.out_scores[(size_t)row * p.N + rank] = (double)scs[c];
-            if (rank == p.N - 1) x_nth = xs[c];
+            const int src = spos[c];
+            p.out_items[(size_t)row * p.N + rank] = cand_s[src];
+            p.out_scores[(size_t)row * p.N + rank] = (double)scs[src];
+            if (rank == p.N - 1) x_nth = xs[src];
         }
     }
     for (int r = nvalid + threadIdx.x; r < p.N; r += 128) {   // fewer than N valid candidates: pad
@@ -598,7 +696,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     if (threadIdx.x == 0) {
         // certificate: the N-th best exact x among the valid candidates clears tau + eps, so no
         // item below the threshold can belong to the top N (x is monotone in the score per user)
-        const bool certified = n <= kCand && nvalid >= p.N && x_nth > p.tau[row] + p.eps[row];
+        const bool certified = n <= kCand && n_surv_all <= kSurv && nvalid >= p.N && x_nth > p.tau[row] + p.eps[row];
         p.out_counts[row] = min(nvalid, p.N);
         p.fallback[row] = certified ? 0 : 1;
     }
