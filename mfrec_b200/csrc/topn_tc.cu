@@ -450,6 +450,10 @@ __device__ __forceinline__ uint32_t order_bits_tc(float x)
     const uint32_t b = __float_as_uint(x);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+__device__ __forceinline__ float order_bits_inv(uint32_t key)
+{
+    return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
 
 // One CTA per user: exact fp32 score of every candidate, masks, then the top N of them in order.
 //   dots    a warp per candidate, EIGHT candidates in flight: the 32 lanes read an item row with one
@@ -468,14 +472,16 @@ __device__ __forceinline__ uint32_t order_bits_tc(float x)
 constexpr int kRatedStage = 2048;   // rated items of the user kept in shared memory (8 KB)
 constexpr int kSurv = 512;          // survivors the ranking step has room for (N <= 128)
 
-__global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
+#ifndef MFREC_FINISH_CTAS
+#define MFREC_FINISH_CTAS 7   // (8 needs 64 registers: spills in the dot loop, measured 7.2 vs 6.8 ms)
+#endif
+__global__ void __launch_bounds__(128, MFREC_FINISH_CTAS) topn_finish_kernel(const FinishParams p)
 {
     __shared__ __align__(16) float prow[256];
     __shared__ __align__(16) uint32_t keys[kCand];   // order-preserving score bits, 0 = dropped
-    __shared__ float xs[kCand];                      // exact x (the quantity the threshold is on)
-    __shared__ float scs[kCand];                     // first the dots, then the scores
+    __shared__ float xs[kCand];                      // first the dots, then the exact x (the quantity the threshold is on)
     __shared__ int32_t rated_s[kRatedStage];
-    __shared__ int32_t cand_s[kCand];
+    __shared__ __align__(16) int32_t cand_s[kCand + 8];
     __shared__ __align__(16) uint32_t skeys[kSurv];  // survivors: keys and positions in the candidate list
     __shared__ int16_t spos[kSurv];
     __shared__ int hist[256];
@@ -499,6 +505,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
         for (int j = threadIdx.x; j < nrated; j += 128) rated_s[j] = p.rated_items[ra + j];
     const int32_t *cand = p.cand + (size_t)row * kCand;
     for (int c = threadIdx.x; c < nn; c += 128) cand_s[c] = cand[c];
+    if (threadIdx.x < 8 && nn > 0) cand_s[min(nn + (int)threadIdx.x, kCand + 7)] = cand[nn - 1];   // the dots read ids in eights
     __syncthreads();
     const float bu = p.ub[uid];
     // ---- dots ----------------------------------------------------------------------------------
@@ -508,9 +515,11 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
         for (int c = warp * 8; c < nn; c += 32) {
             const float4 *q[8];
             float d[8];
+            const int4 id0 = *reinterpret_cast<const int4 *>(cand_s + c), id1 = *reinterpret_cast<const int4 *>(cand_s + c + 4);
+            const int ids[8] = {id0.x, id0.y, id0.z, id0.w, id1.x, id1.y, id1.z, id1.w};
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                q[t] = reinterpret_cast<const float4 *>(p.Q + (size_t)cand_s[min(c + t, nn - 1)] * p.kpad);
+                q[t] = reinterpret_cast<const float4 *>(p.Q) + (size_t)(uint32_t)ids[t] * (uint32_t)nv;
                 d[t] = 0.f;
             }
             for (int f = lane; f < nv; f += 32) {
@@ -539,7 +548,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
             d[0] += __shfl_xor_sync(0xffffffffu, d[0], 2);
             d[0] += __shfl_xor_sync(0xffffffffu, d[0], 1);
             const int t = lane >> 2;   // lane bits 4, 3, 2 = the candidate of this group of four lanes
-            if ((lane & 3) == 0 && c + t < nn) scs[c + t] = d[0];
+            if ((lane & 3) == 0 && c + t < nn) xs[c + t] = d[0];
         }
     }
     __syncthreads();
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     float smax = -INFINITY, smin = INFINITY;
     for (int c = threadIdx.x; c < nn; c += 128) {
         const int it = cand_s[c];
-        const float dot = scs[c];
+        const float dot = xs[c];
         const float bi = p.ib[it];
         const float bsum = bi + bu;
         float sc;
@@ -582,7 +591,6 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
         }
         keys[c] = ok ? order_bits_tc(sc) : 0u;
         xs[c] = p.has_bias ? dot + bi : dot;
-        scs[c] = sc;
         if (ok && fabsf(sc) <= 3.0e38f) {   // (an infinite score keeps its key; it only stays out of the bin range)
             valid += 1;
             smax = fmaxf(smax, sc);
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     auto bin_of = [&](float sc) { return min(255, max(0, (int)((fminf(fmaxf(sc, smin), smax) - smin) * scale))); };
     if (nvalid > p.N) {   // (block-uniform)
         for (int c = threadIdx.x; c < nn; c += 128)
-            if (keys[c]) atomicAdd(&hist[bin_of(scs[c])], 1);
+            if (keys[c]) atomicAdd(&hist[bin_of(order_bits_inv(keys[c]))], 1);
         __syncthreads();
         if (warp == 0) {
             int h[8], s = 0;
@@ -640,7 +648,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     int mine = 0;
     for (int base = c_lo; base < c_hi; base += 32) {
         const int c = base + lane;
-        const bool in = c < c_hi && keys[c] && bin_of(scs[c]) >= bin_min;
+        const bool in = c < c_hi && keys[c] && bin_of(order_bits_inv(keys[c])) >= bin_min;
         mine += __popc(__ballot_sync(0xffffffffu, in));
     }
     __syncthreads();   // (w_cnt was read above by every thread)
@@ -651,7 +659,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
     const int n_surv_all = w_cnt[0] + w_cnt[1] + w_cnt[2] + w_cnt[3];
     for (int base = c_lo; base < c_hi; base += 32) {
         const int c = base + lane;
-        const bool in = c < c_hi && keys[c] && bin_of(scs[c]) >= bin_min;
+        const bool in = c < c_hi && keys[c] && bin_of(order_bits_inv(keys[c])) >= bin_min;
         const uint32_t bal = __ballot_sync(0xffffffffu, in);
         const int at = off + __popc(bal & ((1u << lane) - 1u));
         if (in && at < kSurv) { skeys[at] = keys[c]; spos[at] = (int16_t)c; }
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(128) topn_finish_kernel(const FinishParams p)
         if (rank < p.N) {
             const int src = spos[c];
             p.out_items[(size_t)row * p.N + rank] = cand_s[src];
-            p.out_scores[(size_t)row * p.N + rank] = (double)scs[src];
+            p.out_scores[(size_t)row * p.N + rank] = (double)order_bits_inv(key);
             if (rank == p.N - 1) x_nth = xs[src];
         }
     }
