@@ -11,9 +11,13 @@
 // bit-identical to the reference order.
 //
 // Stratified schedule: the same B x B x W x W layout as the KMF kernel (pack.cu).  A warp owns a
-// bucket; its 32 lanes stage 32 ratings (triple, cache value, user scalar) with coalesced loads
-// and then replay them in order through warp shuffles, all lanes computing the (scalar) update
-// redundantly.  The item scalars of the column block live in shared memory.  The
+// bucket and takes it 32 ratings at a time, one rating per lane (coalesced loads).  An update is
+// scalar, so the only order that matters is between ratings that share a user or an item: the
+// lanes compute the dependency LEVEL of their rating inside the batch (1 + the level of the latest
+// earlier rating with the same user / the same item) and the batch runs level by level, all lanes
+// of a level at once -- bit-identical to replaying the 32 ratings one after the other, in
+// ~(number of levels) dependent updates instead of 32.  The item scalars of the column block and
+// the user scalars of the row block live in shared memory.  The
 // `while rmse <= rmse_last - min_improvement` control of the reference (rmse carried across
 // features, max_epochs ignored) runs on the host, one device reduction per pass.
 #include <algorithm>
@@ -25,11 +29,13 @@
 
 namespace {
 
+// gd_estimator.pyx:26-35 (`if x > 5: x = 5` then `if x < 1: x = 1`).  Both compares look at the
+// incoming x, so they issue together: one float64 compare + selects on the hot item's serial
+// chain instead of two compares back to back (same result for every x, NaN included).
 __device__ __forceinline__ double clamp15(double x)
 {
-    if (x > 5.0) x = 5.0;
-    if (x < 1.0) x = 1.0;
-    return x;
+    const bool hi = x > 5.0, lo = x < 1.0;
+    return hi ? 5.0 : (lo ? 1.0 : x);
 }
 
 // gd_estimator.pyx:38-73 with unfused arithmetic
@@ -85,14 +91,19 @@ __device__ __forceinline__ void funk_st_release(int32_t *p, int v)
 // a CTA-wide barrier per phase.
 //
 // A row block's user scalars stay in shared memory for the whole launch (8 bytes per user: 26 KB
-// at Netflix shape), next to the column block's item scalars: the replay loop then touches no
-// global memory and needs none of the packer's stale-prefetch hints -- a re-read of a scalar that
-// was just written is an ordinary in-order shared-memory access.  A batch of 32 ratings is staged
-// in shared memory with coalesced loads (two broadcast loads per rating in the replay), the next
-// batch is loaded while the current one is replayed, and the scalars of a run of equal items /
-// equal users are forwarded in registers so that the serial chain of a hot item is ~10 dependent
-// float64 operations per rating and nothing else.
-struct FunkStage {          // one staged rating, 32 bytes
+// at Netflix shape), next to the column block's item scalars: the replay touches no global memory
+// and needs none of the packer's stale-prefetch hints -- a re-read of a scalar that was just
+// written is an ordinary shared-memory access one level later.  The next batch's ratings, cache
+// values and biases are loaded while the current batch runs.
+// (Round 2, profiles/r02m_funk_full.md: replaying the 32 ratings of a batch one after the other,
+// every lane computing the same scalar update, was 57 warp instructions and ~360 cycles per
+// rating: 5.3 ms per 20 M-rating pass.)
+#ifndef MFREC_FUNK_DEEP_DIV
+#define MFREC_FUNK_DEEP_DIV 2
+#endif
+constexpr int kDeepDiv = MFREC_FUNK_DEEP_DIV;   // a batch with more than cnt / kDeepDiv levels is replayed serially
+
+struct FunkStage {          // one staged rating of a deep batch, 32 bytes
     int u, i;               // user / item index relative to the row block / column block
     double r, c, b;         // rating, cached partial prediction, baseline
 };
@@ -109,9 +120,9 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
     double *se_s = vfs + prm.user_rows;
     FunkStage *stage_all = reinterpret_cast<FunkStage *>(se_s + W);
     int64_t *boff = reinterpret_cast<int64_t *>(stage_all + (size_t)W * 32);
+    FunkStage *stage = stage_all + warp * 32;
     int32_t *bcnt = reinterpret_cast<int32_t *>(boff + W * W + 1);
     volatile int32_t *phase_done = reinterpret_cast<volatile int32_t *>(bcnt + ((W * W + 2) & ~1));
-    FunkStage *stage = stage_all + warp * 32;
     const double lr = prm.lr, K = prm.K;
     double se = 0.0;
     if (threadIdx.x < W) phase_done[threadIdx.x] = 0;
@@ -159,20 +170,75 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
                 }
                 __syncwarp();
             }
-            int prev_u = -1, prev_i = -1;
-            double vf_cur = 0.0, uf_cur = 0.0;
+            // A hot item's bucket (most of its first 32 ratings on the item of the first or of the last
+            // one) is ONE chain, and the hottest item's chain bounds the pass: replay it rating by
+            // rating, every lane computing the same update, the scalars of a run of equal items /
+            // equal users forwarded in registers across the whole bucket -- ~10 dependent float64
+            // operations per rating and nothing else on the chain.
+            bool hot_bucket = false;
+            if (n >= 16) {
+                const int c0 = min(32, n), il0 = (rt.i & kIdMask) - cs;
+                const int i_first = __shfl_sync(0xffffffffu, il0, 0), i_last = __shfl_sync(0xffffffffu, il0, c0 - 1);
+                hot_bucket = kDeepDiv * max(__popc(__ballot_sync(0xffffffffu, lane < c0 && il0 == i_first)),
+                                            __popc(__ballot_sync(0xffffffffu, lane < c0 && il0 == i_last))) > c0;
+            }
+            if (hot_bucket) {
+                int prev_u = -1, prev_i = -1;
+                double vf_cur = 0.0, uf_cur = 0.0, se_b = 0.0;
+                for (int base = 0; base < n; base += 32) {
+                    const int cnt = min(32, n - base);
+                    __syncwarp();   // the previous batch has been replayed by every lane
+                    {
+                        const int il = (rt.i & kIdMask) - cs;
+                        FunkStage st;
+                        st.u = (rt.u & kIdMask) - us0; st.i = il; st.r = (double)rt.r; st.c = c;
+                        // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
+                        st.b = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[il]), ubv) : 1.0;
+                        stage[lane] = st;
+                    }
+                    {   // next batch's inputs, in flight during the replay
+                        const int j = base + 32 + lane;
+                        rt.u = us0; rt.i = cs; rt.r = 0.f;
+                        c = 0.0; ubv = 0.0;
+                        if (j < n) {
+                            rt = prm.packed[a + j];
+                            c = prm.cache[a + j];
+                            if (prm.variant) ubv = prm.ubp[rt.u & kIdMask];
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll 2
+                    for (int t = 0; t < cnt; ++t) {
+                        const FunkStage x = stage[t];   // broadcast loads
+                        const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
+                        const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
+                        const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
+                        const double err = __dadd_rn(x.r, -pr);
+                        se_b = __dadd_rn(se_b, __dmul_rn(err, err));
+                        uf_cur = prm.update_items
+                                     ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
+                                     : mf;
+                        vf_cur = prm.update_users
+                                     ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
+                                     : cf;
+                        ufs[x.i] = uf_cur;     // every lane writes the same value
+                        vfs[x.u] = vf_cur;
+                        prev_u = x.u;
+                        prev_i = x.i;
+                    }
+                }
+                if (lane == 0) se = __dadd_rn(se, se_b);
+                __syncwarp();
+            } else
             for (int base = 0; base < n; base += 32) {
                 const int cnt = min(32, n - base);
-                __syncwarp();   // the previous batch has been replayed by every lane
-                {
-                    const int il = (rt.i & kIdMask) - cs;
-                    FunkStage st;
-                    st.u = (rt.u & kIdMask) - us0; st.i = il; st.r = (double)rt.r; st.c = c;
-                    // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
-                    st.b = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[il]), ubv) : 1.0;
-                    stage[lane] = st;
-                }
-                // next batch's inputs, in flight during the replay
+                // this lane's rating of the batch (loaded one batch ahead)
+                const bool live = lane < cnt;
+                const int ul = (rt.u & kIdMask) - us0, il = (rt.i & kIdMask) - cs;
+                const double r = (double)rt.r, cc = c;
+                // variant 0 uses the estimator's defaults: overall 1.0, biases 0 (:751)
+                const double bb = prm.variant ? __dadd_rn(__dadd_rn(prm.overall, ibs[il]), ubv) : 1.0;
+                // next batch's inputs, in flight while this one is replayed
                 {
                     const int j = base + 32 + lane;
                     rt.u = us0; rt.i = cs; rt.r = 0.f;
@@ -183,25 +249,86 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
                         if (prm.variant) ubv = prm.ubp[rt.u & kIdMask];
                     }
                 }
-                __syncwarp();
+                // Dependency levels: a rating depends on the latest earlier rating of the batch with
+                // the same user or the same item.  level = 1 + max(level of those two) (longest path,
+                // relaxed until nothing changes: as many rounds as there are levels).  Ratings of one
+                // level share no scalar, so the lanes of a level run together; levels run in order.
+                const unsigned below = (1u << lane) - 1u;
+                bool deep;
+                int pu = -1, pi = -1;
+                {
+                    // the packer orders a bucket by (user, item): equal users are neighbours
+                    const int u_prev = __shfl_up_sync(0xffffffffu, ul, 1);
+                    const bool sorted = !__any_sync(0xffffffffu, live && lane > 0 && ul < u_prev);
+                    if (sorted) {
+                        pu = (live && lane > 0 && ul == u_prev) ? lane - 1 : -1;
+                    } else {
+                        pu = 31 - __clz(__match_any_sync(0xffffffffu, live ? ul : -1 - lane) & below);   // -1: none
+                    }
+                    const unsigned same_i = __match_any_sync(0xffffffffu, live ? il : -1 - lane);
+                    pi = 31 - __clz(same_i & below);
+                    deep = kDeepDiv * __reduce_max_sync(0xffffffffu, __popc(same_i)) > cnt;
+                }
+                int level = 1;
+                for (int round = 1; !deep; ++round) {
+                    const int lu = __shfl_sync(0xffffffffu, level, pu < 0 ? lane : pu);
+                    const int li = __shfl_sync(0xffffffffu, level, pi < 0 ? lane : pi);
+                    int nl = 1;
+                    if (pu >= 0) nl = lu + 1;
+                    if (pi >= 0) nl = max(nl, li + 1);
+                    const bool changed = nl != level;
+                    level = nl;
+                    if (!__any_sync(0xffffffffu, changed)) break;
+                    deep = kDeepDiv * round >= cnt;   // some rating sits at level round + 1 or deeper
+                }
+                const int lmax = deep ? 0 : __reduce_max_sync(0xffffffffu, live ? level : 0);
+                if (deep) {
+                    // A deep batch (the ratings of a hot item: one chain): replay it rating by rating,
+                    // every lane computing the same update, the scalars of a run of equal items / equal
+                    // users forwarded in registers -- ~10 dependent float64 operations per rating and
+                    // no shared-memory round trip on the chain.
+                    FunkStage st;
+                    st.u = ul; st.i = il; st.r = r; st.c = cc; st.b = bb;
+                    stage[lane] = st;
+                    __syncwarp();
+                    int prev_u = -1, prev_i = -1;
+                    double vf_cur = 0.0, uf_cur = 0.0, se_b = 0.0;
 #pragma unroll 2
-                for (int t = 0; t < cnt; ++t) {
-                    const FunkStage x = stage[t];   // broadcast loads
-                    const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
-                    const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
-                    const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
-                    const double err = __dadd_rn(x.r, -pr);
-                    se = __dadd_rn(se, __dmul_rn(err, err));
-                    uf_cur = prm.update_items
-                                 ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
-                                 : mf;
-                    vf_cur = prm.update_users
-                                 ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
-                                 : cf;
-                    ufs[x.i] = uf_cur;     // every lane writes the same value
-                    vfs[x.u] = vf_cur;
-                    prev_u = x.u;
-                    prev_i = x.i;
+                    for (int t = 0; t < cnt; ++t) {
+                        const FunkStage x = stage[t];   // broadcast loads
+                        const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
+                        const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
+                        const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
+                        const double err = __dadd_rn(x.r, -pr);
+                        se_b = __dadd_rn(se_b, __dmul_rn(err, err));
+                        uf_cur = prm.update_items
+                                     ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
+                                     : mf;
+                        vf_cur = prm.update_users
+                                     ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
+                                     : cf;
+                        ufs[x.i] = uf_cur;     // every lane writes the same value
+                        vfs[x.u] = vf_cur;
+                        prev_u = x.u;
+                        prev_i = x.i;
+                    }
+                    if (lane == 0) se = __dadd_rn(se, se_b);
+                    __syncwarp();   // the batch has been replayed by every lane (stage may be refilled)
+                    continue;
+                }
+                for (int L = 1; L <= lmax; ++L) {
+                    if (live && level == L) {
+                        const double cf = vfs[ul];
+                        const double mf = ufs[il];
+                        const double pr = funk_estimate(mf, cf, cc, bb, prm.trail, 1);
+                        const double err = __dadd_rn(r, -pr);
+                        se = __dadd_rn(se, __dmul_rn(err, err));
+                        if (prm.update_items)
+                            ufs[il] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
+                        if (prm.update_users)
+                            vfs[ul] = __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))));
+                    }
+                    __syncwarp();   // the level's stores are visible to the next level's lanes
                 }
             }
             // hand the column group over: item scalars written above, then the counter
@@ -222,6 +349,9 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
         }
     }
     for (int i = threadIdx.x; i < nub; i += blockDim.x) prm.vf[us0 + i] = vfs[i];
+    // every lane holds the squared errors of its own ratings: fixed-order (deterministic) reduction
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se = __dadd_rn(se, __shfl_xor_sync(0xffffffffu, se, o));
     if (lane == 0) se_s[warp] = se;
     __syncthreads();
     if (threadIdx.x == 0) {
