@@ -403,46 +403,87 @@ __global__ void __launch_bounds__(1024) sum_parts_kernel(const double *__restric
     }
 }
 
-// ---- sequential schedule: the reference loop verbatim, one thread ---------------------------
-__global__ void funk_sequential_kernel(int variant, int min_epochs, double min_improvement, int dim,
-                                       double f_init, double lr, double K, double overall,
-                                       double *u, double *v, const int32_t *idx, const double *ratings,
-                                       int64_t nnz, int64_t ni, int64_t nu, const double *ib,
-                                       const double *ub, int update_users, int update_items,
-                                       double *cache, int32_t *feature_epochs, double *feature_rmse)
+// ---- sequential schedule: the reference loop in the reference's order --------------------------
+// One warp, 32 ratings of the stream at a time, one rating per lane, run by dependency level
+// inside the window (see funk_train_kernel): bit-identical to one thread walking the stream.  The
+// squared errors are summed in stream order -- the sum decides `rmse <= rmse_last - min_improvement`.
+__global__ void __launch_bounds__(32)
+funk_sequential_kernel(int variant, int min_epochs, double min_improvement, int dim,
+                       double f_init, double lr, double K, double overall,
+                       double *u, double *v, const int32_t *idx, const double *ratings,
+                       int64_t nnz, int64_t ni, int64_t nu, const double *ib,
+                       const double *ub, int update_users, int update_items,
+                       double *cache, int32_t *feature_epochs, double *feature_rmse)
 {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x;
+    const unsigned FULLM = 0xffffffffu, below = (1u << lane) - 1u;
     double rmse = 2.0, rmse_last = 0.0;
-    for (int64_t n = 0; n < nnz; ++n) cache[n] = 0.0;
+    for (int64_t n = lane; n < nnz; n += 32) cache[n] = 0.0;
+    __syncwarp();
     for (int f = 0; f < dim; ++f) {
         double *uf = u + (int64_t)f * ni, *vf = v + (int64_t)f * nu;
         const double trail = __dmul_rn(__dmul_rn((double)(dim - f - 1), f_init), f_init);
         int epoch = 0;
-        while (epoch < min_epochs || rmse <= __dadd_rn(rmse_last, -min_improvement)) {
+        while (epoch < min_epochs || rmse <= __dadd_rn(rmse_last, -min_improvement)) {   // (warp-uniform)
             double se = 0.0;
             rmse_last = rmse;
-            for (int64_t n = 0; n < nnz; ++n) {
-                const int user = idx[2 * n], item = idx[2 * n + 1];
-                const double bb = variant ? __dadd_rn(__dadd_rn(overall, ib[item]), ub[user]) : 1.0;
-                const double pr = funk_estimate(uf[item], vf[user], cache[n], bb, trail, 1);
-                const double err = __dadd_rn(ratings[n], -pr);
-                se = __dadd_rn(se, __dmul_rn(err, err));
-                const double cf = vf[user], mf = uf[item];
-                if (update_items)
-                    uf[item] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
-                if (update_users)
-                    vf[user] = __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))));
+            for (int64_t base = 0; base < nnz; base += 32) {
+                const int cnt = (int)(nnz - base < 32 ? nnz - base : 32);
+                const bool live = lane < cnt;
+                const int64_t n = base + lane;
+                int user = 0, item = 0;
+                double r = 0.0, cc = 0.0, bb = 1.0;
+                if (live) {
+                    user = idx[2 * n]; item = idx[2 * n + 1];
+                    r = ratings[n]; cc = cache[n];
+                    if (variant) bb = __dadd_rn(__dadd_rn(overall, ib[item]), ub[user]);
+                }
+                const int pu = 31 - __clz(__match_any_sync(FULLM, live ? user : -1 - lane) & below);   // -1: none
+                const int pi = 31 - __clz(__match_any_sync(FULLM, live ? item : -1 - lane) & below);
+                int level = 1;
+                if (__any_sync(FULLM, pu >= 0 || pi >= 0)) {
+                    for (;;) {
+                        const int lu = __shfl_sync(FULLM, level, pu < 0 ? lane : pu);
+                        const int li = __shfl_sync(FULLM, level, pi < 0 ? lane : pi);
+                        int nl = 1;
+                        if (pu >= 0) nl = lu + 1;
+                        if (pi >= 0) nl = max(nl, li + 1);
+                        const bool changed = nl != level;
+                        level = nl;
+                        if (!__any_sync(FULLM, changed)) break;
+                    }
+                }
+                const int lmax = __reduce_max_sync(FULLM, live ? level : 0);
+                double e2 = 0.0;
+                for (int L = 1; L <= lmax; ++L) {
+                    if (live && level == L) {
+                        const double cf = vf[user], mf = uf[item];
+                        const double pr = funk_estimate(mf, cf, cc, bb, trail, 1);
+                        const double err = __dadd_rn(r, -pr);
+                        e2 = __dmul_rn(err, err);
+                        if (update_items)
+                            uf[item] = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))));
+                        if (update_users)
+                            vf[user] = __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))));
+                    }
+                    __syncwarp();   // this level's stores are visible to the lanes of the next
+                }
+                for (int t = 0; t < cnt; ++t) se = __dadd_rn(se, __shfl_sync(FULLM, e2, t));   // stream order
             }
             rmse = sqrt(se / (double)nnz);
             ++epoch;
         }
-        feature_epochs[f] = epoch;
-        feature_rmse[f] = rmse;
-        for (int64_t n = 0; n < nnz; ++n) {
+        if (lane == 0) {
+            feature_epochs[f] = epoch;
+            feature_rmse[f] = rmse;
+        }
+        for (int64_t n = lane; n < nnz; n += 32) {
             const int user = idx[2 * n], item = idx[2 * n + 1];
             const double bb = variant ? __dadd_rn(__dadd_rn(overall, ib[item]), ub[user]) : 1.0;
             cache[n] = funk_estimate(uf[item], vf[user], cache[n], bb, 0.0, 0);
         }
+        __syncwarp();
     }
 }
 
@@ -507,7 +548,7 @@ extern "C" int mfrec_train_funk(mfrec_ctx *ctx, int variant, int min_epochs, int
         MF_CUDA(ctx, dfr.alloc(k, ctx->stream));
         MF_CUDA(ctx, cudaMemcpyAsync(didx.p, ratings_index, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
         MF_CUDA(ctx, cudaMemcpyAsync(dr.p, ratings, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
-        funk_sequential_kernel<<<1, 1, 0, st>>>(variant, min_epochs, min_improvement, k, f_init,
+        funk_sequential_kernel<<<1, 32, 0, st>>>(variant, min_epochs, min_improvement, k, f_init,
                                                 learning_rate, K, overall_avg, du.p, dv.p, didx.p, dr.p,
                                                 nnz, ni, nu, dib.p, dub.p, update_users, update_items,
                                                 dcache.p, dfe.p, dfr.p);

@@ -1109,49 +1109,141 @@ merge_copies_kernel(float *__restrict__ Q, float *__restrict__ ib, int kpad, con
 }
 
 // ------------------------------------------------------------------------------------------
-// Sequential schedule: the reference's loop verbatim (kmf_train.pyx:241-273), one thread,
+// Sequential schedule: the reference's loop (kmf_train.pyx:241-273) in the reference's ORDER,
 // fp64, round-to-nearest multiplies and adds kept separate (the reference build has no FMA).
+//
+// One warp takes the rating stream 32 ratings at a time, one rating per lane.  Two ratings only
+// interact through the rows / biases of a shared user or item, so the lanes compute the
+// dependency level of their rating inside the window (1 + the level of the latest earlier rating
+// with the same user / the same item) and the window runs level by level: the lanes of a level
+// touch disjoint rows, levels run in order, every lane's own arithmetic (the dot product summed
+// over f in order, the update) is the reference's -- the result is bit-identical to one thread
+// walking the stream, in (levels) steps per window instead of 32.  Shuffled ratings rarely share
+// a user or an item within 32 consecutive entries: almost every window is a single level.  The
+// squared errors are summed in stream order (the printed RMSE is the reference's, too).
 // ------------------------------------------------------------------------------------------
-__global__ void kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, double lr, double K_users,
-                                      double K_items, double K_bias, double *u, double *v,
-                                      const int32_t *idx, const double *ratings, int64_t nnz,
-                                      int64_t ni, int64_t nu, double *ib, double *ub,
-                                      int update_users, int update_items, double *rmse_out)
+constexpr int kSeqRegs = 32;   // features of a row pair kept in registers by the sequential kernel
+
+__global__ void __launch_bounds__(32)
+kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, double lr, double K_users,
+                      double K_items, double K_bias, double *u, double *v,
+                      const int32_t *idx, const double *ratings, int64_t nnz,
+                      int64_t ni, int64_t nu, double *ib, double *ub,
+                      int update_users, int update_items, double *rmse_out)
 {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (blockIdx.x != 0) return;
+    const int lane = threadIdx.x;
+    const unsigned FULLM = 0xffffffffu, below = (1u << lane) - 1u;
     for (int epoch = 0; epoch < nbr_epochs; ++epoch) {
         double se = 0.0;
-        for (int64_t n = 0; n < nnz; ++n) {
-            const int user = idx[2 * n], item = idx[2 * n + 1];
-            const double rating = ratings[n];
-            double s = __dadd_rn(__dadd_rn(0.0, ib[item]), ub[user]);
-            for (int f = 0; f < dim; ++f)
-                s = __dadd_rn(s, __dmul_rn(u[(int64_t)f * ni + item], v[(int64_t)f * nu + user]));
-            double err, grad;
-            if (kernel == MFREC_KERNEL_LINEAR) {
-                err = __dadd_rn(rating, -s);
-                grad = err;
-            } else {
-                const double sig = 1.0 / __dadd_rn(1.0, exp(-s));
-                const double p = __dadd_rn(1.0, __dmul_rn(sig, 4.0));
-                err = __dadd_rn(rating, -p);
-                grad = __dmul_rn(__dmul_rn(__dmul_rn(err, sig), __dadd_rn(1.0, -sig)), 4.0);
+        int2 ui = make_int2(0, 0);
+        double rating = 0.0;
+        if (lane < nnz) { ui = reinterpret_cast<const int2 *>(idx)[lane]; rating = ratings[lane]; }
+        for (int64_t base = 0; base < nnz; base += 32) {
+            const int cnt = (int)(nnz - base < 32 ? nnz - base : 32);
+            const bool live = lane < cnt;
+            const int user = ui.x, item = ui.y;
+            const double r = rating;
+            {   // the next window's ratings, in flight while this one runs
+                const int64_t j = base + 32 + lane;
+                if (j < nnz) { ui = reinterpret_cast<const int2 *>(idx)[j]; rating = ratings[j]; }
             }
-            se = __dadd_rn(se, __dmul_rn(err, err));
-            if (kernel == MFREC_KERNEL_LINEAR || update_users)
-                ub[user] = __dadd_rn(ub[user], __dmul_rn(lr, __dadd_rn(grad, -__dmul_rn(K_bias, ub[user]))));
-            if (kernel == MFREC_KERNEL_LINEAR || update_items)
-                ib[item] = __dadd_rn(ib[item], __dmul_rn(lr, __dadd_rn(grad, -__dmul_rn(K_bias, ib[item]))));
-            for (int f = 0; f < dim; ++f) {
-                double *pu = &u[(int64_t)f * ni + item], *pv = &v[(int64_t)f * nu + user];
-                const double cf = *pv, mf = *pu;
-                if (update_items)
-                    *pu = __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, cf), -__dmul_rn(K_items, mf))));
-                if (update_users)
-                    *pv = __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, mf), -__dmul_rn(K_users, cf))));
+            const int pu = 31 - __clz(__match_any_sync(FULLM, live ? user : -1 - lane) & below);   // -1: none
+            const int pi = 31 - __clz(__match_any_sync(FULLM, live ? item : -1 - lane) & below);
+            int level = 1;
+            if (__any_sync(FULLM, pu >= 0 || pi >= 0)) {
+                for (;;) {   // longest path, relaxed until nothing changes
+                    const int lu = __shfl_sync(FULLM, level, pu < 0 ? lane : pu);
+                    const int li = __shfl_sync(FULLM, level, pi < 0 ? lane : pi);
+                    int nl = 1;
+                    if (pu >= 0) nl = lu + 1;
+                    if (pi >= 0) nl = max(nl, li + 1);
+                    const bool changed = nl != level;
+                    level = nl;
+                    if (!__any_sync(FULLM, changed)) break;
+                }
             }
+            const int lmax = __reduce_max_sync(FULLM, live ? level : 0);
+            double e2 = 0.0;
+            for (int L = 1; L <= lmax; ++L) {
+                if (live && level == L) {
+                    double *const ui_ = u + item, *const vu_ = v + user;
+                    const double bi0 = ib[item], bu0 = ub[user];
+                    double s = __dadd_rn(__dadd_rn(0.0, bi0), bu0);
+                    auto err_grad = [&](double &err, double &grad) {
+                        if (kernel == MFREC_KERNEL_LINEAR) {
+                            err = __dadd_rn(r, -s);
+                            grad = err;
+                        } else {
+                            const double sig = 1.0 / __dadd_rn(1.0, exp(-s));
+                            const double p = __dadd_rn(1.0, __dmul_rn(sig, 4.0));
+                            err = __dadd_rn(r, -p);
+                            grad = __dmul_rn(__dmul_rn(__dmul_rn(err, sig), __dadd_rn(1.0, -sig)), 4.0);
+                        }
+                        e2 = __dmul_rn(err, err);
+                        if (kernel == MFREC_KERNEL_LINEAR || update_users)
+                            ub[user] = __dadd_rn(bu0, __dmul_rn(lr, __dadd_rn(grad, -__dmul_rn(K_bias, bu0))));
+                        if (kernel == MFREC_KERNEL_LINEAR || update_items)
+                            ib[item] = __dadd_rn(bi0, __dmul_rn(lr, __dadd_rn(grad, -__dmul_rn(K_bias, bi0))));
+                    };
+                    double err, grad;
+                    if (dim <= kSeqRegs) {
+                        // both rows fit in registers: every load of the rating is in flight at once, the
+                        // sum runs over f in order, the update reuses the registers
+                        double mf[kSeqRegs], cf[kSeqRegs];
+#pragma unroll
+                        for (int f = 0; f < kSeqRegs; ++f)
+                            if (f < dim) { mf[f] = ui_[(int64_t)f * ni]; cf[f] = vu_[(int64_t)f * nu]; }
+#pragma unroll
+                        for (int f = 0; f < kSeqRegs; ++f)
+                            if (f < dim) s = __dadd_rn(s, __dmul_rn(mf[f], cf[f]));
+                        err_grad(err, grad);
+#pragma unroll
+                        for (int f = 0; f < kSeqRegs; ++f) {
+                            if (f >= dim) continue;
+                            if (update_items)
+                                ui_[(int64_t)f * ni] =
+                                    __dadd_rn(mf[f], __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, cf[f]), -__dmul_rn(K_items, mf[f]))));
+                            if (update_users)
+                                vu_[(int64_t)f * nu] =
+                                    __dadd_rn(cf[f], __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, mf[f]), -__dmul_rn(K_users, cf[f]))));
+                        }
+                    } else {
+                        // rows are read eight features at a time (independent loads in flight together)
+                        for (int f0 = 0; f0 < dim; f0 += 8) {
+                            double a[8], b[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (f0 + j < dim) { a[j] = ui_[(int64_t)(f0 + j) * ni]; b[j] = vu_[(int64_t)(f0 + j) * nu]; }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (f0 + j < dim) s = __dadd_rn(s, __dmul_rn(a[j], b[j]));
+                        }
+                        err_grad(err, grad);
+                        for (int f0 = 0; f0 < dim; f0 += 8) {
+                            double mf[8], cf[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (f0 + j < dim) { mf[j] = ui_[(int64_t)(f0 + j) * ni]; cf[j] = vu_[(int64_t)(f0 + j) * nu]; }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (f0 + j >= dim) continue;
+                                if (update_items)
+                                    ui_[(int64_t)(f0 + j) * ni] =
+                                        __dadd_rn(mf[j], __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, cf[j]), -__dmul_rn(K_items, mf[j]))));
+                                if (update_users)
+                                    vu_[(int64_t)(f0 + j) * nu] =
+                                        __dadd_rn(cf[j], __dmul_rn(lr, __dadd_rn(__dmul_rn(grad, mf[j]), -__dmul_rn(K_users, cf[j]))));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();   // this level's stores are visible to the lanes of the next
+            }
+            for (int t = 0; t < cnt; ++t) se = __dadd_rn(se, __shfl_sync(FULLM, e2, t));   // stream order
         }
-        if (rmse_out) rmse_out[epoch] = sqrt(se / (double)nnz);
+        if (rmse_out && lane == 0) rmse_out[epoch] = sqrt(se / (double)nnz);
+        __syncwarp();
     }
 }
 
@@ -1743,7 +1835,7 @@ static int train_kmf_sequential(mfrec_ctx *ctx, int kernel, int nbr_epochs, int 
     MF_CUDA(ctx, cudaMemcpyAsync(didx.p, idx, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemcpyAsync(dib.p, ib, (size_t)ni * 8, cudaMemcpyHostToDevice, st));
     MF_CUDA(ctx, cudaMemcpyAsync(dub.p, ub, (size_t)nu * 8, cudaMemcpyHostToDevice, st));
-    kmf_sequential_kernel<<<1, 1, 0, st>>>(kernel, nbr_epochs, k, lr, K_users, K_items, K_bias, du.p,
+    kmf_sequential_kernel<<<1, 32, 0, st>>>(kernel, nbr_epochs, k, lr, K_users, K_items, K_bias, du.p,
                                            dv.p, didx.p, dr.p, nnz, ni, nu, dib.p, dub.p,
                                            update_users, update_items, drm.p);
     MF_LAUNCH_CHECK(ctx);
