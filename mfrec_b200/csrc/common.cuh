@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <future>
 #include <memory>
 #include <string>
 #include <vector>
@@ -58,6 +59,12 @@ struct mfrec_ctx {
         const double *u = nullptr, *v = nullptr, *ib = nullptr, *ub = nullptr;  // device, [k][n] / [n]
         cudaEvent_t ready = nullptr;
     } staged;                               // mfrec_model_create converts from these instead of copying
+    // Host-side gates of the same hand-over when the arrays are PAGEABLE: staging them through the
+    // bounce buffers occupies a host thread, so the one-call drop-in does it on a background thread
+    // while the calling thread already runs the packer.  An event must have been RECORDED before a
+    // stream may wait for it: the consumer first waits (on the host) for the future that the
+    // background thread fulfils right after recording the event; its value is an mfrec_status.
+    std::shared_future<int> values_enqueued, factors_enqueued;
     int refs = 1;                  // the creator + every live mfrec_ratings / mfrec_model
     std::shared_ptr<void> pack_host;   // host scratch of mfrec_ratings_pack, reused across calls
     std::shared_ptr<void> stager;      // pinned bounce buffers for large pageable host arrays (runtime.cu)
@@ -231,6 +238,8 @@ int mfrec_topn_on_model(mfrec_ctx *ctx, const mfrec_model *M, int predictor, con
 // is in `dst_host`.
 int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
 int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st);
+// true when mfrec_copy_h2d / mfrec_copy_d2h would stage this array (large and pageable), i.e. block the caller
+bool mfrec_host_needs_staging(const void *host, size_t bytes);
 // n_rows / src_of_dev: write n_rows rows, row j taken from source column src_of_dev[j] (item copies);
 // defaults: one row per source column
 int mfrec_upload_factor(mfrec_ctx *ctx, const double *host_kn, int k, int kpad, int32_t n,

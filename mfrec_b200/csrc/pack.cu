@@ -697,6 +697,11 @@ extern "C" int mfrec_ratings_pack(mfrec_ctx *ctx, const int32_t *ratings_index, 
         fill_i64_kernel<<<(unsigned)ceil_div64(packed_len + 1, 256), 256, 0, st>>>(R->order, packed_len, -1);
         MF_LAUNCH_CHECK(ctx);
     }
+    if (ctx->values_enqueued.valid()) {   // (pageable values: the background thread has recorded values_ready)
+        const int urc = ctx->values_enqueued.get();
+        ctx->values_enqueued = {};
+        if (urc != MFREC_OK) return urc;
+    }
     if (ctx->values_ready) {   // the caller is still copying the rating values on another stream
         cudaEvent_t ev = ctx->values_ready;
         ctx->values_ready = nullptr;

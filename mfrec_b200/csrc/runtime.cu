@@ -233,15 +233,19 @@ __global__ void vec_from_dev_kernel(const float *__restrict__ src, int32_t n,
 namespace {
 
 struct HostStager {
-    static constexpr int T = 4, NB = 2;
-    static constexpr size_t CH = (size_t)16 << 20;
-    char *buf[T][NB] = {};
-    cudaEvent_t ev[T][NB] = {};
+    // T host threads (MFREC_STAGE_THREADS; default: half the host's hardware threads, 2..8), each with
+    // NB bounce buffers of CH bytes.  One thread's memcpy moves ~6-10 GB/s of pageable memory; the
+    // link takes 55 GB/s.
+    static constexpr int TMAX = 16, NB = 2;
+    static constexpr size_t CH = (size_t)8 << 20;
+    int T = 4;
+    char *buf[TMAX][NB] = {};
+    cudaEvent_t ev[TMAX][NB] = {};
     bool ready = false;
     std::mutex mu;   // one staged copy at a time per context
     ~HostStager()
     {
-        for (int t = 0; t < T; ++t)
+        for (int t = 0; t < TMAX; ++t)
             for (int b = 0; b < NB; ++b) {
                 if (ev[t][b]) cudaEventDestroy(ev[t][b]);
                 if (buf[t][b]) cudaFreeHost(buf[t][b]);
@@ -250,6 +254,10 @@ struct HostStager {
     cudaError_t init()
     {
         if (ready) return cudaSuccess;
+        const char *env = getenv("MFREC_STAGE_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        T = env ? atoi(env) : std::max(2, std::min(8, hw / 2));
+        T = std::max(1, std::min(T, (int)TMAX));
         for (int t = 0; t < T; ++t)
             for (int b = 0; b < NB; ++b) {
                 cudaError_t e = cudaHostAlloc((void **)&buf[t][b], CH, cudaHostAllocDefault);
@@ -285,6 +293,11 @@ HostStager *stager_of(mfrec_ctx *ctx)
 
 }  // namespace
 
+bool mfrec_host_needs_staging(const void *host, size_t bytes)
+{
+    return host && bytes >= stage_min_bytes() && host_is_pageable(host);
+}
+
 int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st)
 {
     if (bytes == 0) return MFREC_OK;
@@ -298,14 +311,15 @@ int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t b
     const size_t CH = HostStager::CH;
     const size_t nchunks = (bytes + CH - 1) / CH;
     const int device = ctx->device;
-    cudaError_t errs[HostStager::T];
-    std::thread workers[HostStager::T];
-    for (int t = 0; t < HostStager::T; ++t) {
+    const int T = S->T;
+    cudaError_t errs[HostStager::TMAX];
+    std::thread workers[HostStager::TMAX];
+    for (int t = 0; t < T; ++t) {
         errs[t] = cudaSuccess;
         workers[t] = std::thread([=, &errs]() {
             cudaError_t e = cudaSetDevice(device);
             size_t i = 0;
-            for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += HostStager::T, ++i) {
+            for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += (size_t)T, ++i) {
                 const int b = (int)(i % HostStager::NB);
                 const size_t off = c * CH, n = std::min(CH, bytes - off);
                 e = cudaEventSynchronize(S->ev[t][b]);   // the buffer's previous transfer is done
@@ -317,8 +331,8 @@ int mfrec_copy_h2d(mfrec_ctx *ctx, void *dst_dev, const void *src_host, size_t b
             errs[t] = e;
         });
     }
-    for (auto &w : workers) w.join();
-    for (cudaError_t e : errs) MF_CUDA(ctx, e);
+    for (int t = 0; t < T; ++t) workers[t].join();
+    for (int t = 0; t < T; ++t) MF_CUDA(ctx, errs[t]);
     return MFREC_OK;
 }
 
@@ -338,9 +352,10 @@ int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t b
     const size_t CH = HostStager::CH;
     const size_t nchunks = (bytes + CH - 1) / CH;
     const int device = ctx->device;
-    cudaError_t errs[HostStager::T];
-    std::thread workers[HostStager::T];
-    for (int t = 0; t < HostStager::T; ++t) {
+    const int T = S->T;
+    cudaError_t errs[HostStager::TMAX];
+    std::thread workers[HostStager::TMAX];
+    for (int t = 0; t < T; ++t) {
         errs[t] = cudaSuccess;
         workers[t] = std::thread([=, &errs]() {
             cudaError_t e = cudaSetDevice(device);
@@ -355,7 +370,7 @@ int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t b
                 if (e == cudaSuccess) memcpy(static_cast<char *>(dst_host) + pend_off[b], S->buf[t][b], pend_n[b]);
                 pend[b] = false;
             };
-            for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += HostStager::T, ++i) {
+            for (size_t c = (size_t)t; c < nchunks && e == cudaSuccess; c += (size_t)T, ++i) {
                 const int b = (int)(i % HostStager::NB);
                 drain(b);   // the buffer still holds an earlier chunk: copy it out first
                 if (e != cudaSuccess) break;
@@ -368,8 +383,8 @@ int mfrec_copy_d2h(mfrec_ctx *ctx, void *dst_host, const void *src_dev, size_t b
             errs[t] = e;
         });
     }
-    for (auto &w : workers) w.join();
-    for (cudaError_t e : errs) MF_CUDA(ctx, e);
+    for (int t = 0; t < T; ++t) workers[t].join();
+    for (int t = 0; t < T; ++t) MF_CUDA(ctx, errs[t]);
     return MFREC_OK;
 }
 
@@ -543,6 +558,11 @@ extern "C" int mfrec_model_create(mfrec_ctx *ctx, const mfrec_ratings *layout, i
     // a one-call drop-in may have staged the float64 arrays on the device already (common.cuh)
     const auto staged = ctx->staged;
     ctx->staged = {};
+    if (ctx->factors_enqueued.valid()) {   // (pageable arrays: the background thread has recorded staged.ready)
+        const int urc = ctx->factors_enqueued.get();
+        ctx->factors_enqueued = {};
+        if (urc != MFREC_OK) return fail(urc);
+    }
     if (staged.ready) {
         cudaError_t we = cudaStreamWaitEvent(ctx->stream, staged.ready, 0);
         if (we != cudaSuccess) return fail(mfrec_set_error(ctx, MFREC_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(we)));

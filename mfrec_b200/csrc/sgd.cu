@@ -39,6 +39,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <type_traits>
 
 #include <cuda_bf16.h>
@@ -1963,11 +1964,45 @@ extern "C" int mfrec_train_kmf(mfrec_ctx *ctx, int kernel, int nbr_epochs, int k
     MF_TRY(mfrec_copy_h2d(ctx, d_idx.p, ratings_index, (size_t)nnz * 8, sa));
     MF_CUDA(ctx, cudaEventRecord(ev_idx, sa));
     MF_CUDA(ctx, cudaStreamWaitEvent(sb, ev_idx, 0));   // (also orders the pool allocations before sb's use)
-    MF_TRY(mfrec_copy_h2d(ctx, d_r.p, ratings, (size_t)nnz * 8, sb));
-    MF_CUDA(ctx, cudaEventRecord(ev_val, sb));
-    MF_TRY(mfrec_copy_h2d(ctx, d_v.p, v, (size_t)k * nu * 8, sb));
-    MF_TRY(mfrec_copy_h2d(ctx, d_u.p, u, (size_t)k * ni * 8, sb));
-    MF_CUDA(ctx, cudaEventRecord(ev_fac, sb));
+    // The remaining uploads on the copy stream.  Page-locked arrays: four asynchronous copies, this
+    // thread goes straight on to the packer.  Pageable arrays are staged through bounce buffers by
+    // host threads, which blocks the caller: a background thread does it, so the packer (which needs
+    // the values only for its last step, and the factors not at all) still overlaps with the upload.
+    auto upload_rest = [&](std::promise<int> *p_val, std::promise<int> *p_fac) -> int {
+        int urc = mfrec_copy_h2d(ctx, d_r.p, ratings, (size_t)nnz * 8, sb);
+        if (urc == MFREC_OK && cudaEventRecord(ev_val, sb) != cudaSuccess)
+            urc = mfrec_set_error(ctx, MFREC_ERR_CUDA, "mfrec_train_kmf: cudaEventRecord failed");
+        if (p_val) p_val->set_value(urc);
+        if (urc == MFREC_OK) urc = mfrec_copy_h2d(ctx, d_v.p, v, (size_t)k * nu * 8, sb);
+        if (urc == MFREC_OK) urc = mfrec_copy_h2d(ctx, d_u.p, u, (size_t)k * ni * 8, sb);
+        if (urc == MFREC_OK && cudaEventRecord(ev_fac, sb) != cudaSuccess)
+            urc = mfrec_set_error(ctx, MFREC_ERR_CUDA, "mfrec_train_kmf: cudaEventRecord failed");
+        if (p_fac) p_fac->set_value(urc);
+        return urc;
+    };
+    std::promise<int> p_val, p_fac;
+    struct UploadThread {
+        std::thread t;
+        mfrec_ctx *c;
+        ~UploadThread()
+        {
+            if (t.joinable()) t.join();
+            c->values_enqueued = {};
+            c->factors_enqueued = {};
+        }
+    } up{{}, ctx};
+    if (mfrec_host_needs_staging(ratings, (size_t)nnz * 8) || mfrec_host_needs_staging(v, (size_t)k * nu * 8) ||
+        mfrec_host_needs_staging(u, (size_t)k * ni * 8)) {
+        ctx->values_enqueued = p_val.get_future().share();
+        ctx->factors_enqueued = p_fac.get_future().share();
+        const int device = ctx->device;
+        up.t = std::thread([&upload_rest, &p_val, &p_fac, device]() {
+            cudaSetDevice(device);
+            upload_rest(&p_val, &p_fac);
+        });
+    } else {
+        MF_TRY(upload_rest(nullptr, nullptr));
+    }
     ctx->values_ready = ev_val;
     MF_TRY(mfrec_ratings_pack(ctx, d_idx.p, d_r.p, 0, 1, nnz, ni, nu, nullptr, &o, &R));
     tr.lap("pack");
