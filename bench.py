@@ -14,6 +14,7 @@ of the factors inside the timed region.  At N > 1 the line's value is STRONG sca
 weak-scaling run is the secondary key ``weak``.  One JSON line on stdout (rank 0).
 """
 import argparse
+import functools
 import json
 import os
 import subprocess
@@ -432,7 +433,8 @@ def run_native(args):
     if secondary is not None:
         del idx_d, r_d
         torch.cuda.empty_cache()
-        for name, fn in (("topn", secondary_topn), ("funk_pass", secondary_funk)):
+        for name, fn in (("topn", secondary_topn), ("funk_pass", secondary_funk),
+                         ("als_wrmf", functools.partial(secondary_als, with_cpu=not args.no_cpu))):
             try:
                 secondary[name] = fn(torch, dev, _native, ctx, local)
             except Exception as exc:
@@ -503,7 +505,7 @@ def secondary_storage(torch, dev, _native, ctx, idx_d, r_d, nu, ni, nnz, k, u0, 
     (mfrec_opts.storage; float32 arithmetic): the same warm-up + timed epochs, the running RMSE
     of the last epoch beside the float32 run's.  Beside, never instead of, the float32 line."""
     out = {"what": "same ratings, seeds, epochs and hyper-parameters as the headline; only the storage type of "
-                   "the user-factor rows P (96 %% of the model bytes) changes; arithmetic is float32",
+                   "the user-factor rows P (96 % of the model bytes) changes; arithmetic is float32",
            "f32": {"ms_per_epoch": f32_ms, "rmse_last_epoch": f32_curve[-1],
                    "model_bytes": (nu + ni) * (k * 4 + 4)}}
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -582,6 +584,55 @@ def secondary_funk(torch, dev, _native, ctx, local):
             "config": "ml20m-shaped %dx%d nnz=%d, one feature, estimator_loop_without_bias" % (nu, ni, nnz),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_update": bpu, "kernel": "funk_train_kernel"}}
+
+
+def secondary_als(torch, dev, _native, ctx, local, with_cpu=True):
+    """ALS-WRMF (als_implicit.pyx:208-352): seconds per epoch (one user sweep + one item
+    sweep) of the drop-in `als_wrmf` on ML-20M-shaped implicit feedback, k = 64, host arrays in and
+    out; beside it the reference's algorithm on one host core (the oracle's C port -- this is the one
+    other place bench.py runs the oracle, like cpu_baseline) on an ML-100K-shaped problem, both as
+    row solves per second (a row solve = one k x k system built from the row's neighbours)."""
+    from mfrec_b200 import synth
+    from mfrec_b200.lib import als_implicit
+
+    def problem(shape):
+        nu, ni, nnz, _ = synth.SHAPES[shape]
+        idx_d, _r = gpu_synth(torch, dev, nu, ni, nnz, seed=3)
+        idx = idx_d.cpu().numpy()
+        del idx_d, _r
+        users, items = idx[:, 0].astype(np.int64), idx[:, 1].astype(np.int64)
+        ou, oi = np.lexsort((items, users)), np.lexsort((users, items))
+        ur = np.r_[0, np.bincount(users, minlength=nu)].astype(np.int32)
+        ir = np.r_[0, np.bincount(items, minlength=ni)].astype(np.int32)
+        return nu, ni, nnz, ur, np.ascontiguousarray(items[ou], np.int32), ir, np.ascontiguousarray(users[oi], np.int32)
+
+    k = 64
+    nu, ni, nnz, ur, uc, ir, ic = problem("ml20m")
+    rng = np.random.default_rng(5)
+
+    def call(epochs):
+        u, v = rng.normal(0, 0.1, (k, ni)), rng.normal(0, 0.1, (k, nu))
+        t0 = time.perf_counter()
+        als_implicit.als_wrmf(epochs, k, u, v, None, None, ur, uc, ir, ic, nu, ni, c_pos=1, k=0.015)
+        return time.perf_counter() - t0
+
+    call(1)
+    lo = min(call(1) for _ in range(2))
+    hi = min(call(3) for _ in range(2))
+    per_epoch = (hi - lo) / 2.0
+    out = {"metric": "als_row_solves_per_s", "value": (nu + ni) / per_epoch, "unit": "row solves/s",
+           "s_per_epoch": per_epoch, "config": "ml20m-shaped implicit feedback %dx%d nnz=%d, k=%d, float64" % (nu, ni, nnz, k),
+           "kernel": "als_solve_kernel (one CTA per row: Gram in shared memory + Cholesky)"}
+    if with_cpu:
+        from oracle import cpu
+        nu2, ni2, nnz2, ur2, uc2, ir2, ic2 = problem("ml100k")
+        u, v = rng.normal(0, 0.1, (k, ni2)), rng.normal(0, 0.1, (k, nu2))
+        t0 = time.perf_counter()
+        cpu.als_wrmf(1, k, u, v, ur2, uc2, ir2, ic2, 1, 0.015)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (nu2 + ni2) / dt, "unit": "row solves/s", "cores": 1, "kind": "port",
+                               "sample": "one epoch on an ml100k-shaped problem (%dx%d nnz=%d), k=%d, %.2f s" % (nu2, ni2, nnz2, k, dt)}
+    return out
 
 
 # --------------------------------------------------------------------------------------------
