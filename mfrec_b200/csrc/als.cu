@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int kTile = 8;   // neighbour rows staged per step
+constexpr int kTileMin = 8, kTileMax = 32;   // neighbour rows staged per step (as many as keep >= 4 CTAs per SM)
 
 __global__ void __launch_bounds__(256)
 to_rows_f64_kernel(const double *__restrict__ src_kn, int k, int64_t n, double *__restrict__ dst_nk)
@@ -97,66 +97,112 @@ __global__ void validate_cols_kernel(const int32_t *__restrict__ col, int64_t n,
         if (col[j] < 0 || col[j] >= limit) atomicOr(bad, 1);
 }
 
-// one CTA per active row j: assemble M and b, Cholesky, two triangular solves, write Y[j]
+// one CTA per active row j: assemble M and b, Cholesky with the forward solve folded in, back
+// substitution, write Y[j].  kp = the pitch of a staged neighbour row: k rounded up so that the
+// register tiles below never leave the row (the padding is zero).
+__host__ __device__ inline int als_pitch(int k) { return ((k + 7) / 8) * 8; }
+
 __global__ void __launch_bounds__(128)
 als_solve_kernel(const double *__restrict__ X, const double *__restrict__ HH, const int64_t *__restrict__ off,
-                 const int32_t *__restrict__ col, int k, double c_pos, double reg, double *__restrict__ Y)
+                 const int32_t *__restrict__ col, int k, double c_pos, double reg, double *__restrict__ Y, int kTile)
 {
     extern __shared__ double sm[];
+    const int kp = als_pitch(k);
     double *M = sm;                 // [k][k]
     double *b = M + k * k;          // [k]
-    double *xs = b + k;             // [kTile][k]
+    double *colv = b + k;           // [k]  column c of L during the factorisation
+    double *xs = colv + k;          // [kTile][kp]
     const int j = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < k * k; e += nt) M[e] = HH[e] + ((e / k == e % k) ? reg : 0.0);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < k * k; e += nt) M[e] = HH[e];
     for (int f = tid; f < k; f += nt) b[f] = 0.0;
+    for (int e = tid; e < kTile * (kp - k); e += nt) xs[(e / (kp - k)) * kp + k + e % (kp - k)] = 0.0;   // (once per row solve)
+    __syncthreads();
+    for (int f = tid; f < k; f += nt) M[f * k + f] += reg;
+    // register tile of the Gram update: 4 rows x 8 columns of M per thread (rows ti * 4 + i, columns
+    // tj + ntc * jj: neighbouring lanes read neighbouring doubles, lanes of one ti share their row
+    // loads): 12 shared-memory loads per 32 multiply-adds and neighbour instead of 64 (round 1: one
+    // entry per thread and step; the loop was bound by its LDS traffic and by e / k, e % k).
+    const int ntr = (k + 3) / 4, ntc = kp / 8;
     const int64_t a = off[j], z = off[j + 1];
     for (int64_t t0 = a; t0 < z; t0 += kTile) {
         const int nrow = (int)min((int64_t)kTile, z - t0);
         __syncthreads();
-        for (int e = tid; e < nrow * k; e += nt) xs[e] = X[(int64_t)col[t0 + e / k] * k + e % k];
+        for (int r = warp; r < nrow; r += 4) {   // a warp copies a neighbour's row (coalesced)
+            const double *src = X + (int64_t)col[t0 + r] * k;
+            for (int f = lane; f < k; f += 32) xs[r * kp + f] = src[f];
+        }
         __syncthreads();
-        for (int e = tid; e < k * k; e += nt) {
-            const int f1 = e / k, f2 = e % k;
-            double acc = 0.0;
-            for (int r = 0; r < nrow; ++r) acc += xs[r * k + f1] * xs[r * k + f2];
-            M[e] += c_pos * acc;
+        for (int tile = tid; tile < ntr * ntc; tile += nt) {
+            const int ti = tile / ntc, tj = tile - ti * ntc;
+            // rows past k (k not a multiple of 4) read a valid, ignored entry
+            const int r0 = min(ti * 4, k - 1), r1 = min(ti * 4 + 1, k - 1), r2 = min(ti * 4 + 2, k - 1), r3 = min(ti * 4 + 3, k - 1);
+            double acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.0;
+            const double *xr = xs;
+            for (int r = 0; r < nrow; ++r, xr += kp) {
+                const double rv[4] = {xr[r0], xr[r1], xr[r2], xr[r3]};
+                double cv[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) cv[jj] = xr[tj + ntc * jj];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) acc[i][jj] += rv[i] * cv[jj];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int f1 = ti * 4 + i, f2 = tj + ntc * jj;
+                    if (f1 < k && f2 < k) M[f1 * k + f2] += c_pos * acc[i][jj];
+                }
         }
         for (int f = tid; f < k; f += nt) {
             double acc = 0.0;
-            for (int r = 0; r < nrow; ++r) acc += xs[r * k + f];
+            for (int r = 0; r < nrow; ++r) acc += xs[r * kp + f];
             b[f] += (1.0 + c_pos) * acc;
         }
     }
     __syncthreads();
-    // Cholesky M = L L^T in place (lower triangle)
-    for (int c = 0; c < k; ++c) {
-        if (tid == 0) M[c * k + c] = sqrt(M[c * k + c]);
-        __syncthreads();
-        const double d = M[c * k + c];
-        for (int r = c + 1 + tid; r < k; r += nt) M[r * k + c] /= d;
-        __syncthreads();
-        const int m = k - c - 1;   // trailing update of the lower triangle
-        for (int e = tid; e < m * m; e += nt) {
-            const int r = c + 1 + e / m, c2 = c + 1 + e % m;
-            if (c2 <= r) M[r * k + c2] -= M[r * k + c] * M[c2 * k + c];
+    // Cholesky M = L L^T in place (lower triangle), right-looking, two barriers per column, with the
+    // forward solve L y = b riding along as one more row of the trailing update (b[r] -= L[r][c] y[c]).
+    // The trailing update runs on an 8 x 16 thread grid (rows strided by 8, columns by 16: no division to
+    // find an entry -- round 1 decoded (row, column) from a flat index with e / m and e % m and walked
+    // the full square, 123 k of the kernel's 216 k warp instructions per row) and reads column c from
+    // a contiguous copy (M[c2][c] for neighbouring c2 is one bank).
+    {
+        const int tr = tid >> 4, tc = tid & 15;
+        for (int c = 0; c < k; ++c) {
+            const double d = sqrt(M[c * k + c]);   // (every thread: the entry is final since the last barrier)
+            const double yc = b[c] / d;            // y[c] (likewise)
+            for (int r = c + 1 + tid; r < k; r += nt) {
+                const double v = M[r * k + c] / d;
+                M[r * k + c] = v;
+                colv[r] = v;
+            }
+            __syncthreads();
+            if (tid == 0) { M[c * k + c] = d; b[c] = yc; }
+            for (int r = c + 1 + tr; r < k; r += 8) {
+                const double lr = colv[r];
+                for (int c2 = c + 1 + tc; c2 <= r; c2 += 16) M[r * k + c2] -= lr * colv[c2];
+                if (tc == 15) b[r] -= lr * yc;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
-    // L y = b, then L^T x = y (one warp; k is small)
+    // back substitution L^T x = y, column-oriented on one warp (row r of L is contiguous):
+    // x[r] = y[r] / L[r][r], then y[c] -= L[r][c] x[r] for every c < r
     if (tid < 32) {
-        for (int r = 0; r < k; ++r) {
-            double acc = 0.0;
-            for (int c = tid; c < r; c += 32) acc += M[r * k + c] * b[c];
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (tid == 0) b[r] = (b[r] - acc) / M[r * k + r];
-            __syncwarp();
-        }
         for (int r = k - 1; r >= 0; --r) {
-            double acc = 0.0;
-            for (int c = r + 1 + tid; c < k; c += 32) acc += M[c * k + r] * b[c];
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (tid == 0) b[r] = (b[r] - acc) / M[r * k + r];
+            const double xr_ = b[r] / M[r * k + r];
+            for (int c = lane; c < r; c += 32) b[c] -= M[r * k + c] * xr_;
+            __syncwarp();
+            if (lane == 0) b[r] = xr_;
             __syncwarp();
         }
     }
@@ -203,7 +249,11 @@ extern "C" int mfrec_train_als_wrmf(mfrec_ctx *ctx, int nbr_epochs, int k, doubl
     if (nau > nbr_users || nai > nbr_items)
         return mfrec_set_error(ctx, MFREC_ERR_INDEX, "mfrec_train_als_wrmf: more rows in the sparse structure than users / items");
     MF_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t smem = ((size_t)k * k + k + (size_t)kTile * k) * sizeof(double);
+    // neighbour rows per staging step: the loads of a step are one L2 round trip, so more rows per step
+    // hide it better, as long as four CTAs still fit an SM
+    int kTile = kTileMax;
+    while (kTile > kTileMin && ((size_t)k * k + 2 * k + (size_t)kTile * als_pitch(k)) * sizeof(double) * 4 > ctx->smem_per_sm) kTile /= 2;
+    const size_t smem = ((size_t)k * k + 2 * k + (size_t)kTile * als_pitch(k)) * sizeof(double);
     if (smem > ctx->smem_optin)
         return mfrec_set_error(ctx, MFREC_ERR_UNSUPPORTED, "mfrec_train_als_wrmf: k=%d needs %zu B of shared memory", k, smem);
     if (nbr_epochs == 0) return MFREC_OK;
@@ -254,12 +304,12 @@ extern "C" int mfrec_train_als_wrmf(mfrec_ctx *ctx, int nbr_epochs, int k, doubl
     for (int e = 0; e < nbr_epochs; ++e) {
         MF_TRY(gram(ctx, d_U.p, nbr_items, k, d_part.p, nblocks, d_HH.p));
         if (nau > 0) {
-            als_solve_kernel<<<(unsigned)nau, 128, smem, st>>>(d_U.p, d_HH.p, d_uoff.p, d_ucol.p, k, (double)c_pos, reg, d_V.p);
+            als_solve_kernel<<<(unsigned)nau, 128, smem, st>>>(d_U.p, d_HH.p, d_uoff.p, d_ucol.p, k, (double)c_pos, reg, d_V.p, kTile);
             MF_LAUNCH_CHECK(ctx);
         }
         MF_TRY(gram(ctx, d_V.p, nbr_users, k, d_part.p, nblocks, d_HH.p));
         if (nai > 0) {
-            als_solve_kernel<<<(unsigned)nai, 128, smem, st>>>(d_V.p, d_HH.p, d_ioff.p, d_icol.p, k, (double)c_pos, reg, d_U.p);
+            als_solve_kernel<<<(unsigned)nai, 128, smem, st>>>(d_V.p, d_HH.p, d_ioff.p, d_icol.p, k, (double)c_pos, reg, d_U.p, kTile);
             MF_LAUNCH_CHECK(ctx);
         }
     }
