@@ -61,8 +61,10 @@ __device__ __forceinline__ void load_p(float (&x)[V], const void *P, int64_t ele
     }
 }
 
+// (4 CTAs of 256 threads per SM = 64 registers: measured best -- 3 CTAs at 78 registers 9.5 ms per 50 M pairs,
+// 4 at 64 6.9 ms, 5 at 48 with spills 7.8 ms)
 template <int E, typename PT>
-__global__ void __launch_bounds__(256) predict_kernel(const PredParams p)
+__global__ void __launch_bounds__(256, 4) predict_kernel(const PredParams p)
 {
     constexpr int KPAD = E * 32;
     constexpr int V = E >= 4 ? 4 : E, NV = E / V;
@@ -70,22 +72,43 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredParams p)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     double s2 = 0.0, s1 = 0.0, cnt = 0.0;
-    for (int64_t j0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * G4; j0 < p.n; j0 += warps * G4) {
-        int64_t ur[G4], ir[G4];
-        bool ok[G4];
+    // Three dependent round trips per group of pairs -- pair ids, their packed row numbers, the rows --
+    // made the kernel wait out three latencies per iteration (ncu r02w: 65 % long-scoreboard stalls,
+    // 6 TB/s).  The ids of the NEXT group are requested before this group's rows and turned into row
+    // numbers after this group's dot products, so an iteration waits for one latency, the rows'.
+    int2 ui_n[G4];
+    bool ok_n[G4];
+    auto request_pairs = [&](int64_t j0) {
 #pragma unroll
         for (int t = 0; t < G4; ++t) {
             const int64_t j = j0 + t;
-            int2 ui = make_int2(0, 0);
-            ok[t] = j < p.n;
-            if (ok[t]) ui = reinterpret_cast<const int2 *>(p.pairs)[j];
-            if (ok[t] && (ui.x < 0 || ui.x >= p.nu || ui.y < 0 || ui.y >= p.ni)) {
-                if (lane == 0) atomicOr(p.bad, 1);
-                ok[t] = false;
-            }
-            ur[t] = ok[t] ? (p.user_perm ? p.user_perm[ui.x] : ui.x) : 0;
-            ir[t] = ok[t] ? (p.item_perm ? p.item_perm[ui.y] : ui.y) : 0;
+            ui_n[t] = make_int2(0, 0);
+            ok_n[t] = j < p.n;
+            if (ok_n[t]) ui_n[t] = reinterpret_cast<const int2 *>(p.pairs)[j];
         }
+    };
+    int32_t ur_n[G4], ir_n[G4];   // (packed row numbers: < 2^27)
+    auto resolve_rows = [&]() {
+#pragma unroll
+        for (int t = 0; t < G4; ++t) {
+            const int2 ui = ui_n[t];
+            if (ok_n[t] && (ui.x < 0 || ui.x >= p.nu || ui.y < 0 || ui.y >= p.ni)) {
+                if (lane == 0) atomicOr(p.bad, 1);
+                ok_n[t] = false;
+            }
+            ur_n[t] = ok_n[t] ? (p.user_perm ? p.user_perm[ui.x] : ui.x) : 0;
+            ir_n[t] = ok_n[t] ? (p.item_perm ? p.item_perm[ui.y] : ui.y) : 0;
+        }
+    };
+    const int64_t j_first = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * G4;
+    request_pairs(j_first);
+    resolve_rows();
+    for (int64_t j0 = j_first; j0 < p.n; j0 += warps * G4) {
+        int32_t ur[G4], ir[G4];
+        bool ok[G4];
+#pragma unroll
+        for (int t = 0; t < G4; ++t) { ur[t] = ur_n[t]; ir[t] = ir_n[t]; ok[t] = ok_n[t]; }
+        request_pairs(j0 + warps * G4);   // (past the end: nothing is loaded, every ok_n is false)
         float part[G4];
 #pragma unroll
         for (int t = 0; t < G4; ++t) part[t] = 0.f;
@@ -95,14 +118,15 @@ __global__ void __launch_bounds__(256) predict_kernel(const PredParams p)
             float a[G4][V], b[G4][V];
 #pragma unroll
             for (int t = 0; t < G4; ++t) {
-                load_p<V, PT>(a[t], p.P, ur[t] * KPAD + off);
-                load_p<V, float>(b[t], p.Q, ir[t] * KPAD + off);
+                load_p<V, PT>(a[t], p.P, (int64_t)ur[t] * KPAD + off);
+                load_p<V, float>(b[t], p.Q, (int64_t)ir[t] * KPAD + off);
             }
 #pragma unroll
             for (int t = 0; t < G4; ++t)
 #pragma unroll
                 for (int h = 0; h < V; ++h) part[t] = fmaf(a[t][h], b[t][h], part[t]);
         }
+        resolve_rows();   // the next group's row numbers: their loads overlap the reduction and the finish below
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
