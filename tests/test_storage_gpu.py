@@ -128,6 +128,32 @@ def test_training_on_16bit_rows_is_deterministic_and_tracks_float32(storage):
     assert a[4][-1] < a[4][0]
 
 
+@pytest.mark.parametrize("storage", ["f16", "bf16"])
+def test_16bit_rows_with_local_slabs(storage):
+    """A catalogue too large for one tile per SM is cut into local slabs inside one persistent launch
+    (the Yahoo!Music shape on one GPU): the 16-bit build walks them like the float32 one."""
+    from mfrec_b200 import _native
+    nu, ni, nnz, k = 2000, 1500, 150000, 64
+    d = synth.make_ratings(nu, ni, nnz, seed=21)
+    idx, r = d["idx"], d["r"]
+    hp = (0.01, 0.05, 0.05, 0.007)
+    code = _native.STORAGE_F16 if storage == "f16" else _native.STORAGE_BF16
+
+    def run(st):
+        R = _native.Ratings(idx, r, ni, nu, k_hint=k, row_blocks=3, workers=4, n_slabs=2, storage=st)
+        assert R.G == 2
+        u, v = synth.init_factors(nu, ni, k, seed=22)
+        M = _native.Model(k, ni, nu, u, v, np.zeros(ni), np.zeros(nu), layout=R)
+        for _ in range(6):
+            M.sgd_epoch(R, _native.KERNEL_LINEAR, *hp)
+        M.ctx.sync()
+        u1, v1, ib1, ub1 = M.read()
+        return _native.rmse_pairs("predict_linear", u1, v1, idx, r, 0.0, ib1, ub1)[0][0]
+
+    got, want = run(code), run(_native.STORAGE_F32)
+    assert abs(got - want) <= TOL[storage] * want, (got, want)
+
+
 def test_unsupported_combinations_fail_loudly():
     from mfrec_b200 import _native
     nu, ni, nnz = 400, 300, 12000
