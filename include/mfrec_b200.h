@@ -64,9 +64,10 @@ enum { MFREC_PRED_GD_RATING = 0,       /* gradient_descent.py:621-631  dot + 1.0
 
 /* Update schedules */
 enum { MFREC_SCHED_STRATIFIED = 0, /* conflict-free block schedule, fp32, all SMs (default)     */
-       MFREC_SCHED_SEQUENTIAL = 1  /* the reference's exact order, fp64, one thread: bit-exact
+       MFREC_SCHED_SEQUENTIAL = 1  /* the reference's exact order, fp64, one warp (32 ratings of
+                                      the stream at a time, run by dependency level): bit-exact
                                       with the reference for the linear / Funk kernels; meant
-                                      for verification and for tiny fold-in calls              */ };
+                                      for verification and for small fold-in calls             */ };
 
 /* Optional knobs; pass NULL for defaults.  Zero in any field means "choose for me". */
 typedef struct mfrec_opts {
