@@ -99,6 +99,18 @@ def kmf_epoch_rowmajor_f32(dim, lr, K_users, K_items, K_bias, P, Q, users_bias, 
                     _p(ratings_index, np.int32), _p(ratings, np.float32), C.c_int64(ratings.shape[0])))
 
 
+def kmf_epoch_rowmajor_f32_mt(dim, lr, K_users, K_items, K_bias, P, Q, users_bias, items_bias, ratings_index,
+                              ratings, threads):
+    """The same loop on `threads` host threads (user slices; item rows shared without locks): a
+    throughput figure for bench.py's fair-layout CPU line, nothing is compared with its result."""
+    fn = lib().oracle_kmf_epoch_rowmajor_f32_mt
+    fn.restype = C.c_double
+    return float(fn(C.c_int(dim), C.c_float(lr), C.c_float(K_users), C.c_float(K_items), C.c_float(K_bias),
+                    _p(P, np.float32), _p(Q, np.float32), _p(users_bias, np.float32), _p(items_bias, np.float32),
+                    _p(ratings_index, np.int32), _p(ratings, np.float32), C.c_int64(ratings.shape[0]),
+                    C.c_int32(P.shape[0]), C.c_int(int(threads))))
+
+
 def funk_loop_dev(min_epochs, max_epochs, min_improvement, dim, f_init, lr, K, u, v, ratings_index,
                   ratings, batch=0, rmse_hist=None):
     """estimator_loop (max_epochs >= 0, rmse_hist required) / estimator_loop2 (max_epochs < 0).

@@ -216,6 +216,65 @@ double oracle_kmf_epoch_rowmajor_f32(int dim, float lr, float K_users, float K_i
     return se;
 }
 
+/* The same loop on T host threads, thread t taking the ratings of the users in
+ * [t * nu / T, (t + 1) * nu / T) in array order: user rows are private to a thread, item rows and
+ * item biases are updated without locks (races between threads: a THROUGHPUT figure for bench.py's
+ * fair-layout CPU line, not a result anything is compared with). */
+#include <pthread.h>
+typedef struct {
+    int dim; float lr, Ku, Ki, Kb; float *P, *Q, *ub, *ib; const int32_t *idx; const float *r; int64_t nnz;
+    int32_t u_lo, u_hi; double se;
+} rowmajor_job;
+
+static void *rowmajor_worker(void *arg)
+{
+    rowmajor_job *j = (rowmajor_job *)arg;
+    const int dim = j->dim;
+    double se = 0.0;
+    for (int64_t n = 0; n < j->nnz; ++n) {
+        const int user = j->idx[2 * n];
+        if (user < j->u_lo || user >= j->u_hi) continue;
+        const int item = j->idx[2 * n + 1];
+        float *p = j->P + (int64_t)user * dim, *q = j->Q + (int64_t)item * dim;
+        float s = j->ib[item] + j->ub[user];
+        for (int f = 0; f < dim; ++f) s += p[f] * q[f];
+        const float err = j->r[n] - s;
+        se += (double)err * err;
+        j->ub[user] += j->lr * (err - j->Kb * j->ub[user]);
+        j->ib[item] += j->lr * (err - j->Kb * j->ib[item]);
+        for (int f = 0; f < dim; ++f) {
+            const float cf = p[f], mf = q[f];
+            q[f] = mf + j->lr * (err * cf - j->Ki * mf);
+            p[f] = cf + j->lr * (err * mf - j->Ku * cf);
+        }
+    }
+    j->se = se;
+    return 0;
+}
+
+double oracle_kmf_epoch_rowmajor_f32_mt(int dim, float lr, float K_users, float K_items, float K_bias,
+                                        float *P, float *Q, float *users_bias, float *items_bias,
+                                        const int32_t *ratings_index, const float *ratings, int64_t nnz,
+                                        int32_t nu, int threads)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    rowmajor_job jobs[64];
+    pthread_t tid[64];
+    for (int t = 0; t < threads; ++t) {
+        rowmajor_job j = {dim, lr, K_users, K_items, K_bias, P, Q, users_bias, items_bias, ratings_index, ratings, nnz,
+                          (int32_t)((int64_t)nu * t / threads), (int32_t)((int64_t)nu * (t + 1) / threads), 0.0};
+        jobs[t] = j;
+        pthread_create(&tid[t], 0, rowmajor_worker, &jobs[t]);
+    }
+    double se = 0.0;
+    for (int t = 0; t < threads; ++t) {
+        pthread_join(tid[t], 0);
+        se += jobs[t].se;
+    }
+    return se;
+}
+
 /*
  * A3 development variants of the Funk loop; all share the training pass
  * of estimator_loop_without_bias and the `estimator` above.  Their rating cache is a DENSE
