@@ -126,6 +126,37 @@ struct mfrec_model {
     int32_t *item_perm = nullptr;
 };
 
+// ---- dependency levels of a window of ratings (sequential schedules, sgd.cu / funk.cu) ------------
+// Up to 32 ratings of a stream, one per lane.  Two ratings interact only through the rows / biases of
+// a shared user or item, so a rating's level is 1 + the deeper level of the latest EARLIER rating of
+// the window with the same user and of the one with the same item (longest path, relaxed until
+// nothing changes: as many rounds as there are levels).  Ratings of one level touch disjoint rows
+// and may run together; running the levels in order is equivalent to walking the stream.
+// Returns this lane's level; lmax = the deepest level of a live lane (0 for an empty window).
+#ifdef __CUDACC__
+__device__ __forceinline__ int mfrec_window_levels(int user, int item, bool live, int lane, int &lmax)
+{
+    const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
+    const int pu = 31 - __clz(__match_any_sync(full, live ? user : -1 - lane) & below);   // -1: none
+    const int pi = 31 - __clz(__match_any_sync(full, live ? item : -1 - lane) & below);
+    int level = 1;
+    if (__any_sync(full, pu >= 0 || pi >= 0)) {
+        for (;;) {
+            const int lu = __shfl_sync(full, level, pu < 0 ? lane : pu);
+            const int li = __shfl_sync(full, level, pi < 0 ? lane : pi);
+            int nl = 1;
+            if (pu >= 0) nl = lu + 1;
+            if (pi >= 0) nl = max(nl, li + 1);
+            const bool changed = nl != level;
+            level = nl;
+            if (!__any_sync(full, changed)) break;
+        }
+    }
+    lmax = __reduce_max_sync(full, live ? level : 0);
+    return level;
+}
+#endif
+
 // ---- error plumbing -------------------------------------------------------------------
 int mfrec_set_error(mfrec_ctx *ctx, int code, const char *fmt, ...);
 

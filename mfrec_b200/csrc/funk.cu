@@ -125,6 +125,30 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
     volatile int32_t *phase_done = reinterpret_cast<volatile int32_t *>(bcnt + ((W * W + 2) & ~1));
     const double lr = prm.lr, K = prm.K;
     double se = 0.0;
+    // serial replay of the `cnt` ratings staged in stage[] (hot buckets and deep batches): every lane
+    // computes the same update; the scalars of a run of equal items / equal users are forwarded in
+    // registers, so a hot item's chain is ~10 dependent float64 operations per rating
+    auto replay_staged = [&](int cnt, int &prev_u, int &prev_i, double &vf_cur, double &uf_cur, double &se_b) {
+#pragma unroll 2
+        for (int t = 0; t < cnt; ++t) {
+            const FunkStage x = stage[t];   // broadcast loads
+            const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
+            const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
+            const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
+            const double err = __dadd_rn(x.r, -pr);
+            se_b = __dadd_rn(se_b, __dmul_rn(err, err));
+            uf_cur = prm.update_items
+                         ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
+                         : mf;
+            vf_cur = prm.update_users
+                         ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
+                         : cf;
+            ufs[x.i] = uf_cur;     // every lane writes the same value
+            vfs[x.u] = vf_cur;
+            prev_u = x.u;
+            prev_i = x.i;
+        }
+    };
     if (threadIdx.x < W) phase_done[threadIdx.x] = 0;
     // this row block's user scalars (no other CTA touches them during the launch)
     const int us0 = prm.row_start[rb * W], nub = prm.row_start[(rb + 1) * W] - us0;
@@ -207,25 +231,7 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
                         }
                     }
                     __syncwarp();
-#pragma unroll 2
-                    for (int t = 0; t < cnt; ++t) {
-                        const FunkStage x = stage[t];   // broadcast loads
-                        const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
-                        const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
-                        const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
-                        const double err = __dadd_rn(x.r, -pr);
-                        se_b = __dadd_rn(se_b, __dmul_rn(err, err));
-                        uf_cur = prm.update_items
-                                     ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
-                                     : mf;
-                        vf_cur = prm.update_users
-                                     ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
-                                     : cf;
-                        ufs[x.i] = uf_cur;     // every lane writes the same value
-                        vfs[x.u] = vf_cur;
-                        prev_u = x.u;
-                        prev_i = x.i;
-                    }
+                    replay_staged(cnt, prev_u, prev_i, vf_cur, uf_cur, se_b);
                 }
                 if (lane == 0) se = __dadd_rn(se, se_b);
                 __syncwarp();
@@ -293,25 +299,7 @@ __global__ void __launch_bounds__(512) funk_train_kernel(const FunkParams prm)
                     __syncwarp();
                     int prev_u = -1, prev_i = -1;
                     double vf_cur = 0.0, uf_cur = 0.0, se_b = 0.0;
-#pragma unroll 2
-                    for (int t = 0; t < cnt; ++t) {
-                        const FunkStage x = stage[t];   // broadcast loads
-                        const double cf = x.u == prev_u ? vf_cur : vfs[x.u];
-                        const double mf = x.i == prev_i ? uf_cur : ufs[x.i];
-                        const double pr = funk_estimate(mf, cf, x.c, x.b, prm.trail, 1);
-                        const double err = __dadd_rn(x.r, -pr);
-                        se_b = __dadd_rn(se_b, __dmul_rn(err, err));
-                        uf_cur = prm.update_items
-                                     ? __dadd_rn(mf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, cf), -__dmul_rn(K, mf))))
-                                     : mf;
-                        vf_cur = prm.update_users
-                                     ? __dadd_rn(cf, __dmul_rn(lr, __dadd_rn(__dmul_rn(err, mf), -__dmul_rn(K, cf))))
-                                     : cf;
-                        ufs[x.i] = uf_cur;     // every lane writes the same value
-                        vfs[x.u] = vf_cur;
-                        prev_u = x.u;
-                        prev_i = x.i;
-                    }
+                    replay_staged(cnt, prev_u, prev_i, vf_cur, uf_cur, se_b);
                     if (lane == 0) se = __dadd_rn(se, se_b);
                     __syncwarp();   // the batch has been replayed by every lane (stage may be refilled)
                     continue;
@@ -417,7 +405,7 @@ funk_sequential_kernel(int variant, int min_epochs, double min_improvement, int 
 {
     if (blockIdx.x != 0) return;
     const int lane = threadIdx.x;
-    const unsigned FULLM = 0xffffffffu, below = (1u << lane) - 1u;
+    const unsigned FULLM = 0xffffffffu;
     double rmse = 2.0, rmse_last = 0.0;
     for (int64_t n = lane; n < nnz; n += 32) cache[n] = 0.0;
     __syncwarp();
@@ -439,22 +427,8 @@ funk_sequential_kernel(int variant, int min_epochs, double min_improvement, int 
                     r = ratings[n]; cc = cache[n];
                     if (variant) bb = __dadd_rn(__dadd_rn(overall, ib[item]), ub[user]);
                 }
-                const int pu = 31 - __clz(__match_any_sync(FULLM, live ? user : -1 - lane) & below);   // -1: none
-                const int pi = 31 - __clz(__match_any_sync(FULLM, live ? item : -1 - lane) & below);
-                int level = 1;
-                if (__any_sync(FULLM, pu >= 0 || pi >= 0)) {
-                    for (;;) {
-                        const int lu = __shfl_sync(FULLM, level, pu < 0 ? lane : pu);
-                        const int li = __shfl_sync(FULLM, level, pi < 0 ? lane : pi);
-                        int nl = 1;
-                        if (pu >= 0) nl = lu + 1;
-                        if (pi >= 0) nl = max(nl, li + 1);
-                        const bool changed = nl != level;
-                        level = nl;
-                        if (!__any_sync(FULLM, changed)) break;
-                    }
-                }
-                const int lmax = __reduce_max_sync(FULLM, live ? level : 0);
+                int lmax;
+                const int level = mfrec_window_levels(user, item, live, lane, lmax);   // common.cuh
                 double e2 = 0.0;
                 for (int L = 1; L <= lmax; ++L) {
                     if (live && level == L) {

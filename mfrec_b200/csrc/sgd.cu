@@ -1134,7 +1134,7 @@ kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, double lr, double K_u
 {
     if (blockIdx.x != 0) return;
     const int lane = threadIdx.x;
-    const unsigned FULLM = 0xffffffffu, below = (1u << lane) - 1u;
+    const unsigned FULLM = 0xffffffffu;
     for (int epoch = 0; epoch < nbr_epochs; ++epoch) {
         double se = 0.0;
         int2 ui = make_int2(0, 0);
@@ -1149,22 +1149,8 @@ kmf_sequential_kernel(int kernel, int nbr_epochs, int dim, double lr, double K_u
                 const int64_t j = base + 32 + lane;
                 if (j < nnz) { ui = reinterpret_cast<const int2 *>(idx)[j]; rating = ratings[j]; }
             }
-            const int pu = 31 - __clz(__match_any_sync(FULLM, live ? user : -1 - lane) & below);   // -1: none
-            const int pi = 31 - __clz(__match_any_sync(FULLM, live ? item : -1 - lane) & below);
-            int level = 1;
-            if (__any_sync(FULLM, pu >= 0 || pi >= 0)) {
-                for (;;) {   // longest path, relaxed until nothing changes
-                    const int lu = __shfl_sync(FULLM, level, pu < 0 ? lane : pu);
-                    const int li = __shfl_sync(FULLM, level, pi < 0 ? lane : pi);
-                    int nl = 1;
-                    if (pu >= 0) nl = lu + 1;
-                    if (pi >= 0) nl = max(nl, li + 1);
-                    const bool changed = nl != level;
-                    level = nl;
-                    if (!__any_sync(FULLM, changed)) break;
-                }
-            }
-            const int lmax = __reduce_max_sync(FULLM, live ? level : 0);
+            int lmax;
+            const int level = mfrec_window_levels(user, item, live, lane, lmax);   // common.cuh
             double e2 = 0.0;
             for (int L = 1; L <= lmax; ++L) {
                 if (live && level == L) {
