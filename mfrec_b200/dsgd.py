@@ -229,16 +229,22 @@ def user_slices(torch, users, nu, world):
     return [0] + [min(int(c), nu) for c in cuts] + [nu]
 
 
-def _run_ring(torch, dist, native, args, ctx, rank, world, dev, idx_d, r_d, nu_r, ni_tot, nnz_total, deg_np,
-              u0, v0, k, hp, ClockSampler, local):
-    """Pack this rank's slice, run warm-up + timed epochs; returns a dict of measurements plus the
-    objects needed for the end-to-end arm."""
-    nnz_r = int(idx_d.shape[0])
+def _pack_slice(native, args, ctx, world, idx_d, r_d, nu_r, ni_tot, deg_np, k):
+    """This rank's slice of the ratings in the ring layout (every rank arrives at the same item layout:
+    it is derived from the global item degrees)."""
     # (the slab-at-a-time NCCL transport cannot merge item copies at the end of an epoch: no splitting)
     split = native.SPLIT_OFF if (args.exchange == "nccl" or args.no_split) else native.SPLIT_AUTO
-    R = native.Ratings(None, None, ni_tot, nu_r, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
-                       nnz=nnz_r, ratings_are_f32=True, k_hint=k, n_slabs=world, row_blocks=args.row_blocks,
-                       workers=args.workers, item_degree=deg_np, split=split)
+    return native.Ratings(None, None, ni_tot, nu_r, ctx=ctx, device_ptrs=(idx_d.data_ptr(), r_d.data_ptr()),
+                          nnz=int(idx_d.shape[0]), ratings_are_f32=True, k_hint=k, n_slabs=world,
+                          row_blocks=args.row_blocks, workers=args.workers, item_degree=deg_np, split=split)
+
+
+def _run_ring(torch, dist, native, args, ctx, rank, world, dev, idx_d, r_d, nu_r, ni_tot, nnz_total, deg_np,
+              u0, v0, k, hp, ClockSampler, local, R=None):
+    """Pack this rank's slice (unless the caller did), run warm-up + timed epochs; returns a dict of
+    measurements plus the objects needed for the end-to-end arm."""
+    if R is None:
+        R = _pack_slice(native, args, ctx, world, idx_d, r_d, nu_r, ni_tot, deg_np, k)
     M = native.Model(k, ni_tot, nu_r, u0, v0, None, None, layout=R, ctx=ctx)
     n_ep = args.warmup + args.steps
     se = torch.zeros(n_ep, device=dev, dtype=torch.float64)
@@ -407,8 +413,27 @@ def bench_multi_gpu(args, rank, world, local, nu, ni, nnz, k, hp, gpu_synth, Clo
             u0, _ = synth.init_factors(1, ni_tot, k, seed=2)      # same item init on every rank
             _, v0 = synth.init_factors(nu, 1, k, seed=100 + rank)
         deg_np = deg.cpu().numpy()
+        # Pack first and agree on the outcome before any rank enters the ring's collectives: a layout the
+        # library cannot build (e.g. the weak-scaling tile of the Yahoo shape at 8 GPUs: 1.09 M items x
+        # 1.8 M users per rank need a 71-bit sort key) fails the line's primary mode loudly, but only
+        # marks a secondary mode unavailable.
+        R_mode, pack_err = None, None
+        try:
+            R_mode = _pack_slice(native, args, ctx, world, idx_d, r_d, nu_r, ni_tot, deg_np, k)
+        except native.MfrecError as exc:
+            pack_err = str(exc)
+        agreed = torch.tensor([0 if pack_err else 1], device=dev, dtype=torch.int32)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        if int(agreed.item()) == 0:
+            if mode == modes[0]:
+                raise native.MfrecError(-5, pack_err or "another rank could not pack its slice")
+            lines[mode] = {"scaling": mode, "unavailable": pack_err or "another rank could not pack its slice"}
+            del R_mode, idx_d, r_d
+            dist.barrier()
+            continue
         m = _run_ring(torch, dist, native, args, ctx, rank, world, dev, idx_d, r_d, nu_r, ni_tot, nnz_total,
-                      deg_np, u0, v0, k, hp, ClockSampler, local)
+                      deg_np, u0, v0, k, hp, ClockSampler, local, R=R_mode)
+        del R_mode
         R, M = m.pop("R"), m.pop("M")
         value = nnz_total * args.steps / (m["ms"] * 1e-3)
         achieved = value / world * bpu / 1e9
