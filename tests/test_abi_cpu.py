@@ -69,3 +69,32 @@ def test_abi_version_and_no_cpu_fallback(lib):
         kmf_train.train_linear_kernel(1, 2, 0.1, 0.01, 0.0, 0.0, 0.05, 0.05, 0.007, 0.0, u, v, idx, r,
                                       np.zeros(3), np.zeros(4))
     assert not u.any() and not v.any()
+
+
+def test_opts_struct_matches_the_header():
+    """`mfrec_opts` as the Python binding lays it out == the C declaration (field order and names):
+    a field added on one side only would shift every later field."""
+    import ctypes as C
+    import re
+    from mfrec_b200 import _native
+    with open(os.path.join(ROOT, "include", "mfrec_b200.h")) as f:
+        text = f.read()
+    body = text[text.index("typedef struct mfrec_opts {"):text.index("} mfrec_opts;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = re.findall(r"\b(?:int32_t|uint64_t)\s+(\w+)\s*;", body)
+    assert declared == [name for name, _ in _native.Opts._fields_]
+    assert C.sizeof(_native.Opts) == 48          # 6 x int32, uint64, 3 x int32 (+ tail padding)
+
+
+def test_storage_option_is_validated_on_the_host():
+    from mfrec_b200.lib import _buffers
+    old = _buffers.options["storage"]
+    try:
+        for name, code in (("f32", 0), ("f16", 1), ("bf16", 2)):
+            _buffers.options["storage"] = name
+            assert _buffers.native_opts()["storage"] == code
+        _buffers.options["storage"] = "fp8"
+        with pytest.raises(ValueError):
+            _buffers.native_opts()
+    finally:
+        _buffers.options["storage"] = old
